@@ -1,0 +1,281 @@
+"""TEST INFRASTRUCTURE - ctypes front-end of the CPU oracle (oracle/adi3d_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module.  The product package never does.
+
+Also holds the reader for the dump files written by oracle/_ref/ref_probe3d_* (the real
+reference, see oracle/ref_probe3d.cpp) and helpers to run that binary.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+import subprocess
+from dataclasses import dataclass, field
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "_build" / "liboracle_adi.so"
+REF_DIR = HERE / "_ref"
+
+LAYER_CUR, LAYER_HALF, LAYER_NEXT, LAYER_TEMP = 0, 1, 2, 3
+DIR_X, DIR_Y, DIR_Z = 0, 1, 2
+NODE_IN, NODE_OUT, NODE_BOUND, NODE_VALVE = 0, 1, 2, 3
+BC_NOSLIP, BC_FREE = 0, 1
+
+
+def build(force: bool = False) -> Path:
+    """Compile the oracle restatement (gcc) if needed and return the library path."""
+    src = HERE / "adi3d_oracle.c"
+    srcs = [src] + ([HERE / "adi2d_oracle.c"] if (HERE / "adi2d_oracle.c").exists() else [])
+    if force or not LIB_PATH.exists() or any(LIB_PATH.stat().st_mtime < s.stat().st_mtime for s in srcs):
+        subprocess.run(["make", "-C", str(HERE)], check=True, capture_output=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(str(build()))
+    return _lib
+
+
+def _np_ft(fp_bytes: int):
+    return np.float32 if fp_bytes == 4 else np.float64
+
+
+@dataclass
+class Case:
+    """A solver case: grid, fluid parameters and the reference's Node[] as arrays."""
+    dimx: int
+    dimy: int
+    dimz: int
+    dx: float
+    dy: float
+    dz: float
+    v_T: float
+    v_vis: float
+    t_vis: float
+    t_phi: float
+    dt: float
+    num_global: int
+    num_local: int
+    fp_bytes: int
+    type: np.ndarray = None
+    bc_vel: np.ndarray = None
+    bc_temp: np.ndarray = None
+    vx: np.ndarray = None
+    vy: np.ndarray = None
+    vz: np.ndarray = None
+    T: np.ndarray = None
+    baseT: float = 1.0
+    outdims: tuple = (0, 0, 0)
+    snapshots: list = field(default_factory=list)
+
+    @property
+    def shape(self):
+        return (self.dimx, self.dimy, self.dimz)
+
+    @property
+    def ncells(self):
+        return self.dimx * self.dimy * self.dimz
+
+
+def read_probe(path) -> Case:
+    """Parse a dump written by oracle/_ref/ref_probe3d_* (format: oracle/ref_probe3d.cpp)."""
+    data = Path(path).read_bytes()
+    assert data[:8] == b"CMCPROBE", "not a probe dump"
+    off = 8
+    ints = struct.unpack_from("<12i", data, off)
+    off += 48
+    ver, fpb, dimx, dimy, dimz, ng, nl, nsteps, ox, oy, oz, _ = ints
+    dbl = struct.unpack_from("<9d", data, off)
+    off += 72
+    dx, dy, dz, dt, v_T, v_vis, t_vis, t_phi, baseT = dbl
+    N = dimx * dimy * dimz
+    ft = _np_ft(fpb)
+
+    def take(dtype, count):
+        nonlocal off
+        a = np.frombuffer(data, dtype=dtype, count=count, offset=off).copy()
+        off += a.nbytes
+        return a
+
+    case = Case(dimx, dimy, dimz, dx, dy, dz, v_T, v_vis, t_vis, t_phi, dt, ng, nl, fpb, baseT=baseT, outdims=(ox, oy, oz))
+    case.type = take(np.int32, N)
+    case.bc_vel = take(np.int32, N)
+    case.bc_temp = take(np.int32, N)
+    case.vx, case.vy, case.vz, case.T = (take(ft, N) for _ in range(4))
+    outN = ox * oy * oz
+    while off < len(data):
+        step, kind = struct.unpack_from("<2i", data, off)
+        off += 8
+        (err,) = struct.unpack_from("<d", data, off)
+        off += 8
+        if kind == 1:  # GetLayer output: Vec3D[outN] + double[outN]
+            vel = take(ft, 3 * outN).reshape(outN, 3)
+            T = take(np.float64, outN)
+            case.snapshots.append(dict(step=step, kind=kind, err=err, vel=vel, T=T))
+        else:
+            u, v, w, T = (take(ft, N) for _ in range(4))
+            case.snapshots.append(dict(step=step, kind=kind, err=err, u=u, v=v, w=w, T=T))
+    return case
+
+
+def ref_binary(fp_bytes: int) -> Path:
+    return REF_DIR / ("ref_probe3d_f32" if fp_bytes == 4 else "ref_probe3d_f64")
+
+
+def have_ref(fp_bytes: int = 8) -> bool:
+    p = ref_binary(fp_bytes)
+    return p.exists() and os.access(p, os.X_OK)
+
+
+def run_ref(data_file, config_file, out_file, nsteps, fp_bytes=8, align=True, dump="last",
+            getlayer=False, dt=None, sweep=None, threads=None, timeout=3600):
+    """Run the real reference CPU solver through the probe driver; returns its stdout."""
+    cmd = [str(ref_binary(fp_bytes)), str(data_file), str(config_file), str(out_file), str(int(nsteps))]
+    if align:
+        cmd.append("align")
+    cmd.append(f"dump={dump}")
+    if getlayer:
+        cmd.append("getlayer")
+    if dt is not None:
+        cmd.append(f"dt={dt!r}")
+    if sweep:
+        cmd.append(f"sweep={sweep}")
+    if threads:
+        cmd.append(f"threads={int(threads)}")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError(f"reference probe failed ({r.returncode}): {r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+    return r.stdout
+
+
+class Oracle3D:
+    """The CPU restatement driven like the reference's AdiSolver3D (CPU backend)."""
+
+    def __init__(self, case: Case):
+        self.case = case
+        self.fp = case.fp_bytes
+        self.ft = _np_ft(self.fp)
+        self.suf = "_f32" if self.fp == 4 else "_f64"
+        L = lib()
+        f = self._fn("oracle3d_create")
+        f.restype = C.c_void_p
+        FP = C.POINTER(C.c_float if self.fp == 4 else C.c_double)
+        IP = C.POINTER(C.c_int)
+        f.argtypes = [C.c_int] * 3 + [C.c_double] * 7 + [IP] * 3 + [FP] * 4
+        arrs_i = [np.ascontiguousarray(a, dtype=np.int32) for a in (case.type, case.bc_vel, case.bc_temp)]
+        arrs_f = [np.ascontiguousarray(a, dtype=self.ft) for a in (case.vx, case.vy, case.vz, case.T)]
+        self.h = C.c_void_p(f(case.dimx, case.dimy, case.dimz, case.dx, case.dy, case.dz,
+                              case.v_T, case.v_vis, case.t_vis, case.t_phi,
+                              *[a.ctypes.data_as(IP) for a in arrs_i], *[a.ctypes.data_as(FP) for a in arrs_f]))
+        self._FP = FP
+        self.err = 0.0
+
+    def _fn(self, name):
+        return getattr(lib(), name + self.suf)
+
+    def close(self):
+        if self.h:
+            f = self._fn("oracle3d_destroy")
+            f.argtypes = [C.c_void_p]
+            f(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def create_segments(self):
+        f = self._fn("oracle3d_create_segments")
+        f.argtypes = [C.c_void_p]
+        f(self.h)
+
+    def segments(self, d):
+        f = self._fn("oracle3d_num_segments")
+        f.argtypes = [C.c_void_p, C.c_int]
+        f.restype = C.c_int
+        n = f(self.h, d)
+        out = np.zeros((max(n, 1), 8), dtype=np.int32)
+        g = self._fn("oracle3d_get_segments")
+        g.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        g(self.h, d, out.ctypes.data_as(C.POINTER(C.c_int)))
+        return out[:n]
+
+    def update_boundaries(self):
+        f = self._fn("oracle3d_update_boundaries")
+        f.argtypes = [C.c_void_p]
+        f(self.h)
+
+    def time_step(self, dt, num_global, num_local, compute_error=True):
+        f = self._fn("oracle3d_time_step")
+        f.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        f.restype = C.c_int
+        e = C.c_double(0)
+        rc = f(self.h, float(dt), num_global, num_local, int(bool(compute_error)), C.byref(e))
+        self.err = e.value
+        if rc != 0:
+            raise RuntimeError("Error is too big! %f" % e.value)
+        return e.value
+
+    def step_prologue(self):
+        f = self._fn("oracle3d_step_prologue")
+        f.argtypes = [C.c_void_p]
+        f(self.h)
+
+    def solve_direction(self, d, dt, num_local, cur_slot, temp_slot, next_slot):
+        f = self._fn("oracle3d_solve_direction")
+        f.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
+        f(self.h, d, float(dt), num_local, cur_slot, temp_slot, next_slot)
+
+    def eval_div_error(self, slot=LAYER_NEXT):
+        f = self._fn("oracle3d_eval_div_error")
+        f.argtypes = [C.c_void_p, C.c_int]
+        f.restype = C.c_double
+        return f(self.h, slot)
+
+    def field(self, slot, var) -> np.ndarray:
+        """Zero-copy view of one field of a layer, shape (dimx, dimy, dimz)."""
+        f = self._fn("oracle3d_field")
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        f.restype = C.c_void_p
+        p = f(self.h, slot, var)
+        n = self.case.ncells
+        buf = (C.c_float if self.fp == 4 else C.c_double) * n
+        return np.frombuffer(buf.from_address(p), dtype=self.ft).reshape(self.case.shape)
+
+    def layer(self, slot):
+        return [self.field(slot, q) for q in range(4)]
+
+    def get_layer(self, ox=0, oy=0, oz=0):
+        c = self.case
+        ox, oy, oz = ox or c.dimx, oy or c.dimy, oz or c.dimz
+        vel = np.zeros((ox * oy * oz, 3), dtype=self.ft)
+        T = np.zeros(ox * oy * oz, dtype=np.float64)
+        f = self._fn("oracle3d_get_layer")
+        f.argtypes = [C.c_void_p, self._FP, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int]
+        f(self.h, vel.ctypes.data_as(self._FP), T.ctypes.data_as(C.POINTER(C.c_double)), ox, oy, oz)
+        return vel, T
+
+
+def solve_tridiagonal(a, b, c, d):
+    """Common::SolveTridiagonal on copies of a,b,c,d (dtype decides fp32/fp64)."""
+    ft = a.dtype
+    suf = "_f32" if ft == np.float32 else "_f64"
+    f = getattr(lib(), "oracle_solve_tridiagonal" + suf)
+    P = C.POINTER(C.c_float if ft == np.float32 else C.c_double)
+    f.argtypes = [P] * 5 + [C.c_int]
+    a, b, c, d = (np.array(v, dtype=ft, copy=True) for v in (a, b, c, d))
+    x = np.zeros_like(a)
+    f(*[v.ctypes.data_as(P) for v in (a, b, c, d, x)], len(a))
+    return x
