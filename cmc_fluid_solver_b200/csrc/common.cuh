@@ -1,0 +1,66 @@
+// common.cuh - device data model shared by all kernels of the ADI hot path.
+//
+// Time-layer storage (replaces ScalarField3D / TimeLayer3D, reference
+// src/FluidSolver3D/TimeLayer3D.h:249-260, 536-552): structure of arrays, one device buffer per
+// field, lines along z padded to a multiple of 16 elements (128 B in fp64) so every z-line
+// starts on a 128-byte boundary, plus one guard plane before and after the slab.  The guard
+// planes double as the halo planes of the x-slab decomposition (reference haloSize = dimy*dimz,
+// AdiSolver3D.cpp:251-258).
+//
+//   idx(i, j, k) = (i + 1) * plane + j * nzp + k,   i in [-1, nx],  plane = ny * nzp
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cmc {
+
+struct Layout {
+	int nx, ny, nz;       // cells of this slab (nx = local x-planes), reference dimx/dimy/dimz
+	int nzp;              // padded z-line length
+	int x0;               // global index of local plane 0
+	int gx;               // global dimx
+	long long plane;      // ny * nzp
+	long long total;      // (nx + 2) * plane
+	__host__ __device__ __forceinline__ long long idx(int i, int j, int k) const
+	{
+		return (long long)(i + 1) * plane + (long long)j * nzp + k;
+	}
+};
+
+// Per-cell, per-direction line descriptor byte (replaces Segment3D + NodesBoundary3D,
+// reference src/FluidSolver3D/Grid3D.h:63-93: 40 B + 2 Nodes per segment).  Built once on the
+// device from the node types by k_build_roles (GenerateListSegments, Grid3D.cpp:47-127).
+enum : unsigned {
+	R_INT   = 1u,    // interior row of a segment (cell is NODE_IN inside a terminated run)
+	R_START = 2u,    // first cell of a segment  -> ApplyBC0 row
+	R_END   = 4u,    // last cell of a segment   -> ApplyBC1 row
+	R_VFREE = 8u,    // node.bc_vel  == BC_FREE (selects the boundary row of u, v, w)
+	R_TFREE = 16u,   // node.bc_temp == BC_FREE (selects the boundary row of T)
+	R_IN    = 32u,   // node.type == NODE_IN    (merge mask)
+	R_BV    = 64u,   // node.type is NODE_BOUND or NODE_VALVE (boundary refresh / copy mask)
+	R_OUT   = 128u,  // node.type == NODE_OUT   (GetLayer writes 99999 here)
+	R_SEG   = R_INT | R_START | R_END
+};
+
+template <typename FT>
+struct SweepArgs {
+	Layout L;
+	FT dt;
+	FT h[3];                 // dx, dy, dz as FTYPE (TimeLayer3D ctor casts, AdiSolver3D.cpp:256)
+	FT v_T, v_vis, t_vis, t_phi;
+	const uint8_t *role;     // descriptor bytes of the sweep direction
+	const FT *cur[4];        // u, v, w, T of the sweep's "cur" layer
+	const FT *temp[4];       // linearisation layer (read)
+	FT *next[4];             // sweep output layer
+	FT *temp_out[4];         // merged linearisation layer (fast mode, double-buffered)
+	const FT *nodev[4];      // Node.v.x, v.y, v.z, Node.T (boundary row values)
+	FT *cv, *cT;             // exact mode: Thomas c' scratch (velocity matrix, temperature matrix)
+};
+
+// elementwise helpers -----------------------------------------------------------------------
+template <typename FT>
+struct LayerPtrs { FT *f[4]; };
+template <typename FT>
+struct ConstLayerPtrs { const FT *f[4]; };
+
+} // namespace cmc

@@ -1,0 +1,64 @@
+// kernels.h - launchers implemented by the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace cmc {
+
+// ---- kernels_exact.cu (-fmad=false) --------------------------------------------------------------
+template <typename FT>
+void launch_exact_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
+template <typename FT>
+void launch_thomas_batch(int nsys, int n, FT *a, FT *b, FT *c, FT *d, FT *x, cudaStream_t s);
+
+// ---- kernels_fast.cu -----------------------------------------------------------------------------
+// Returns false when the fast path does not support this line length (caller falls back to exact sweeps
+// + merge kernel - still on the GPU; there is no CPU path).
+template <typename FT>
+bool launch_fast_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
+template <typename FT>
+bool launch_pcr_batch(int nsys, int n, const FT *a, const FT *b, const FT *c, const FT *d, FT *x, cudaStream_t s);
+
+// ---- kernels_util.cu -----------------------------------------------------------------------------
+// line descriptors (Grid3D::GenerateListSegments, reference Grid3D.cpp:47-127)
+void launch_build_roles(int dir, const Layout &G, const uint8_t *ncode_global, const Layout &L, uint8_t *role,
+                        unsigned long long *seg_count, cudaStream_t s, long long *launches);
+// adds the type bits (R_IN / R_BV / R_OUT / R_VFREE / R_TFREE) to all three role arrays
+void launch_role_type_bits(const Layout &G, const uint8_t *ncode_global, const Layout &L,
+                           uint8_t *rx, uint8_t *ry, uint8_t *rz, cudaStream_t s, long long *launches);
+
+template <typename FT>
+void launch_copy_full(const Layout &L, ConstLayerPtrs<FT> src, LayerPtrs<FT> dst, cudaStream_t s, long long *launches);
+// dst <- src where role has `mask` bits (CopyFieldTo, reference TimeLayer3D.h:394-413)
+template <typename FT>
+void launch_copy_masked(const Layout &L, const uint8_t *role, unsigned mask, ConstLayerPtrs<FT> src, LayerPtrs<FT> dst,
+                        cudaStream_t s, long long *launches);
+// dest = (dest + src) / 2 on NODE_IN (MergeFieldTo, reference TimeLayer3D.h:415-436)
+template <typename FT>
+void launch_merge(const Layout &L, const uint8_t *role, ConstLayerPtrs<FT> src, LayerPtrs<FT> dst, cudaStream_t s, long long *launches);
+// out = (a + b) / 2 on NODE_IN, out = a elsewhere (merge into the other temp buffer)
+template <typename FT>
+void launch_merge_to(const Layout &L, const uint8_t *role, ConstLayerPtrs<FT> tmp, ConstLayerPtrs<FT> nxt, LayerPtrs<FT> out,
+                     cudaStream_t s, long long *launches);
+// cur <- Node.v / Node.T on BOUND and VALVE cells (CopyFromGrid, reference TimeLayer3D.h:926-944);
+// optionally the same values into `also` (next <- cur on BOUND/VALVE, AdiSolver3D.cpp:310-311)
+template <typename FT>
+void launch_update_boundaries(const Layout &L, const uint8_t *role, ConstLayerPtrs<FT> nodev, LayerPtrs<FT> cur,
+                              cudaStream_t s, long long *launches);
+// fills all cells of `dst` with value (guard planes included)
+template <typename FT>
+void launch_fill(FT *dst, long long n, FT value, cudaStream_t s, long long *launches);
+// TimeLayer3D::EvalDivError (reference TimeLayer3D.h:595-641): partial[0] = sum |div|, partial[1] = count
+template <typename FT>
+void launch_div_error(const Layout &L, const uint8_t *role, const FT *U, const FT *V, const FT *W,
+                      FT dx, FT dy, FT dz, double *block_partials, int max_blocks, double *result2,
+                      cudaStream_t s, long long *launches);
+// Solver3D::GetLayer: OUT cells of `layer` <- 99999 (Clear, reference TimeLayer3D.h:974-998) ...
+template <typename FT>
+void launch_clear_out(const Layout &L, const uint8_t *role, LayerPtrs<FT> layer, FT value, cudaStream_t s, long long *launches);
+// ... then nearest-lower downsample (FilterToArrays, reference TimeLayer3D.h:842-854) of the rows
+// [oi0, oi1) of the output grid that fall into this slab.
+template <typename FT>
+void launch_filter(const Layout &L, ConstLayerPtrs<FT> layer, int ox, int oy, int oz, int oi0, int oi1,
+                   FT *vel_xyz, double *T, cudaStream_t s, long long *launches);
+
+} // namespace cmc

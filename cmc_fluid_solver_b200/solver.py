@@ -1,0 +1,205 @@
+"""Host-side mirror of the reference's solver interface for the ADI path.
+
+`AdiSolver3D` keeps the reference's method names, argument meaning, call order and error
+behaviour (FluidSolver3D::Solver3D / AdiSolver3D: reference src/FluidSolver3D/Solver3D.h:24-49,
+AdiSolver3D.h:52-61; driver call sequence FluidSolver3D.cpp:191-265):
+
+    solver = AdiSolver3D()
+    solver.Init(case)                 # Solver3D::Init(backend, csv, grid, params, ...)
+    solver.CreateSegments()           # AdiSolver3D::CreateSegments
+    loop: solver.UpdateBoundaries(); solver.TimeStep(dt, num_global, num_local, computeError)
+          solver.GetLayer(outdimx, outdimy, outdimz)
+
+Everything forwards to the C ABI (include/cmc_adi.h).  No torch types, no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import FluidParams, GridDesc, LIB_PATH, load_library
+from .cases import Case
+
+CMC_OK, CMC_ERR_DIVERGED = 0, 1
+MODE_FAST, MODE_EXACT = 0, 1
+LAYER_CUR, LAYER_HALF, LAYER_NEXT, LAYER_TEMP = 0, 1, 2, 3
+DIR_X, DIR_Y, DIR_Z = 0, 1, 2
+ERR_THRESHOLD = 0.01
+
+
+class CmcError(RuntimeError):
+    """Any failure reported by the C ABI (carries the status code and cmc_last_error())."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"[cmc {code}] {msg}")
+        self.code = code
+
+
+class DivergedError(CmcError):
+    """The reference throws std::runtime_error("") after printing "Error is too big!" (AdiSolver3D.cpp:371-374)."""
+
+
+def lib_path():
+    return LIB_PATH
+
+
+def _check(rc):
+    if rc == CMC_OK:
+        return
+    msg = load_library().cmc_last_error().decode(errors="replace")
+    if rc == CMC_ERR_DIVERGED:
+        raise DivergedError(rc, msg)
+    raise CmcError(rc, msg)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class AdiSolver3D:
+    """B200 drop-in for the reference's AdiSolver3D (GPU only)."""
+
+    def __init__(self):
+        self._h = None
+        self.case = None
+        self.diffError = 0.0
+        self.rank, self.nranks = 0, 1
+
+    # -- Solver3D::Init ------------------------------------------------------------------------------------
+    def Init(self, case: Case, device: int = 0, mode: str = "fast", rank: int = 0, nranks: int = 1, nccl_id: bytes = None):
+        lib = load_library()
+        self.case = case
+        self.fp = case.fp_bytes
+        self.ft = np.float32 if self.fp == 4 else np.float64
+        g = GridDesc(case.dimx, case.dimy, case.dimz, case.dx, case.dy, case.dz)
+        p = FluidParams(case.v_T, case.v_vis, case.t_vis, case.t_phi)
+        h = C.c_void_p()
+        if nranks > 1:
+            buf = C.create_string_buffer(nccl_id, 128)
+            _check(lib.cmc_adi3d_create_dist(C.byref(g), C.byref(p), self.fp, device, rank, nranks, buf, C.byref(h)))
+        else:
+            _check(lib.cmc_adi3d_create(C.byref(g), C.byref(p), self.fp, device, C.byref(h)))
+        self._h = h
+        self.rank, self.nranks = rank, nranks
+        x0, nx = C.c_int(0), C.c_int(0)
+        _check(lib.cmc_adi3d_slab(h, C.byref(x0), C.byref(nx)))
+        self.x0, self.nx = x0.value, nx.value
+        self.set_mode(mode)
+        arr_i = [np.ascontiguousarray(a, dtype=np.int32) for a in (case.type, case.bc_vel, case.bc_temp)]
+        arr_f = [np.ascontiguousarray(a, dtype=self.ft) for a in (case.vx, case.vy, case.vz, case.T)]
+        _check(lib.cmc_adi3d_set_nodes(h, *[_ptr(a) for a in arr_i], *[_ptr(a) for a in arr_f]))
+        return self
+
+    def set_mode(self, mode):
+        m = {"fast": MODE_FAST, "exact": MODE_EXACT}[mode] if isinstance(mode, str) else int(mode)
+        _check(load_library().cmc_adi3d_set_option(self._h, b"mode", m))
+        self.mode = m
+
+    def close(self):
+        if self._h:
+            load_library().cmc_adi3d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- AdiSolver3D::CreateSegments -------------------------------------------------------------------------
+    def CreateSegments(self):
+        _check(load_library().cmc_adi3d_build_lines(self._h))
+
+    def numSegs(self, d):
+        n = C.c_int64(0)
+        _check(load_library().cmc_adi3d_num_segments(self._h, d, C.byref(n)))
+        return n.value
+
+    # -- Solver3D::UpdateBoundaries --------------------------------------------------------------------------
+    def UpdateBoundaries(self):
+        _check(load_library().cmc_adi3d_update_boundaries(self._h))
+
+    # -- Solver3D::TimeStep ------------------------------------------------------------------------------------
+    def TimeStep(self, dt, num_global, num_local, computeError=True):
+        e = C.c_double(self.diffError)
+        rc = load_library().cmc_adi3d_time_step(self._h, float(dt), int(num_global), int(num_local), int(bool(computeError)), C.byref(e))
+        self.diffError = e.value
+        _check(rc)
+        return self.diffError
+
+    def TimeStepAsync(self, dt, num_global, num_local, computeError=False):
+        _check(load_library().cmc_adi3d_time_step_async(self._h, float(dt), int(num_global), int(num_local), int(bool(computeError))))
+
+    def Sync(self):
+        e = C.c_double(0.0)
+        rc = load_library().cmc_adi3d_sync(self._h, C.byref(e))
+        self.diffError = e.value
+        _check(rc)
+        return self.diffError
+
+    # -- Solver3D::GetLayer ------------------------------------------------------------------------------------
+    def GetLayer(self, outdimx=0, outdimy=0, outdimz=0, vel=None, T=None):
+        c = self.case
+        ox, oy, oz = outdimx or c.dimx, outdimy or c.dimy, outdimz or c.dimz
+        n = ox * oy * oz
+        if vel is None:
+            vel = np.empty((n, 3), dtype=self.ft)
+        if T is None:
+            T = np.empty(n, dtype=np.float64)
+        _check(load_library().cmc_adi3d_get_layer(self._h, _ptr(vel), _ptr(T), ox, oy, oz))
+        return vel, T
+
+    # -- hooks -------------------------------------------------------------------------------------------------
+    def read_field(self, layer, var) -> np.ndarray:
+        c = self.case
+        out = np.empty((self.nx, c.dimy, c.dimz), dtype=self.ft)
+        _check(load_library().cmc_adi3d_read_field(self._h, layer, var, _ptr(out)))
+        return out
+
+    def write_field(self, layer, var, a):
+        a = np.ascontiguousarray(a, dtype=self.ft)
+        assert a.size == self.nx * self.case.dimy * self.case.dimz
+        _check(load_library().cmc_adi3d_write_field(self._h, layer, var, _ptr(a)))
+
+    def read_layer(self, layer):
+        return [self.read_field(layer, q) for q in range(4)]
+
+    def step_prologue(self):
+        _check(load_library().cmc_adi3d_step_prologue(self._h))
+
+    def SolveDirection(self, d, dt, num_local, cur_layer, next_layer):
+        _check(load_library().cmc_adi3d_solve_direction(self._h, d, float(dt), int(num_local), cur_layer, next_layer))
+
+    def EvalDivError(self, layer=LAYER_NEXT):
+        e = C.c_double(0.0)
+        _check(load_library().cmc_adi3d_eval_div_error(self._h, layer, C.byref(e)))
+        return e.value
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        _check(load_library().cmc_adi3d_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def launch_count(self, reset=False) -> int:
+        n = C.c_int64(0)
+        _check(load_library().cmc_adi3d_launch_count(self._h, C.byref(n), int(reset)))
+        return n.value
+
+    def device_bytes(self) -> int:
+        n = C.c_int64(0)
+        _check(load_library().cmc_adi3d_device_bytes(self._h, C.byref(n)))
+        return n.value
+
+
+def solve_tridiagonal_batch(a, b, c, d, mode="exact"):
+    """Batched line solve on the GPU: rows of a,b,c,d are independent systems (Common::SolveTridiagonal)."""
+    ft = a.dtype
+    assert ft in (np.float32, np.float64)
+    a, b, c, d = (np.ascontiguousarray(v, dtype=ft) for v in (a, b, c, d))
+    nsys, n = a.shape
+    x = np.empty_like(a)
+    m = {"fast": MODE_FAST, "exact": MODE_EXACT}[mode]
+    _check(load_library().cmc_solve_tridiagonal_batch(a.itemsize, m, nsys, n, _ptr(a), _ptr(b), _ptr(c), _ptr(d), _ptr(x)))
+    return x

@@ -1,0 +1,158 @@
+/*
+ * cmc_adi.h - C ABI of the B200-native implicit (ADI) time-stepping path of cmc-fluid-solver.
+ *
+ * The reference has no FFI layer; its seam for this path is the C++ abstract class
+ * FluidSolver3D::Solver3D (src/FluidSolver3D/Solver3D.h:24-49) plus AdiSolver3D::CreateSegments
+ * (src/FluidSolver3D/AdiSolver3D.h:52-61).  Every entry point below replaces one of those
+ * members; the citation on each declaration names it.  INTEGRATION.md shows the adapter
+ * (class B200AdiSolver3D : public Solver3D) a maintainer adds on the reference side.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int status
+ * (CMC_OK == 0); cmc_last_error() returns a thread-local message for the last failure.
+ * Host arrays use the reference's dense layout  idx = (i*dimy + j)*dimz + k  (k fastest,
+ * src/FluidSolver3D/TimeLayer3D.h:256-259).  `fp_bytes` (4 or 8) plays the role of the
+ * reference's compile-time FTYPE (src/Common/Geometry.h:21): all `void*` field arrays are
+ * float[] when fp_bytes == 4 and double[] when fp_bytes == 8.
+ *
+ * There is no CPU fallback: every call needs a CUDA device (sm_100a) and fails loudly otherwise.
+ */
+#ifndef CMC_ADI_H
+#define CMC_ADI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMC_ADI_ABI_VERSION 1
+
+/* status codes */
+enum {
+	CMC_OK = 0,
+	CMC_ERR_DIVERGED = 1,     /* residual > 0.01: the reference prints "Error is too big!" and throws (AdiSolver3D.cpp:371-374) */
+	CMC_ERR_INVALID = -1,     /* bad argument / call order */
+	CMC_ERR_CUDA = -2,        /* CUDA runtime or driver error (message carries device + code, cf. GPUplan.cpp:173-193) */
+	CMC_ERR_NO_DEVICE = -3,   /* no usable sm_100 device: there is no CPU fallback */
+	CMC_ERR_UNSUPPORTED = -4,
+	CMC_ERR_COMM = -5         /* NCCL error */
+};
+
+/* enum values mirror src/Common/Geometry.h:29-43 and are part of the contract */
+enum { CMC_NODE_IN = 0, CMC_NODE_OUT = 1, CMC_NODE_BOUND = 2, CMC_NODE_VALVE = 3 };
+enum { CMC_BC_NOSLIP = 0, CMC_BC_FREE = 1 };
+enum { CMC_DIR_X = 0, CMC_DIR_Y = 1, CMC_DIR_Z = 2 };
+/* src/FluidSolver3D/AdiSolver3D.h:38 */
+enum { CMC_VAR_U = 0, CMC_VAR_V = 1, CMC_VAR_W = 2, CMC_VAR_T = 3 };
+/* the four time layers AdiSolver3D keeps (AdiSolver3D.cpp:254-258) */
+enum { CMC_LAYER_CUR = 0, CMC_LAYER_HALF = 1, CMC_LAYER_NEXT = 2, CMC_LAYER_TEMP = 3 };
+
+/* solve modes (cmc_adi3d_set_option "mode") */
+enum {
+	CMC_MODE_FAST = 0,   /* partitioned (SPIKE/PCR) line solves, FMA contraction; matches the reference within tolerance */
+	CMC_MODE_EXACT = 1   /* sequential Thomas in the reference's operation order, no FMA; bit-identical with the reference CPU solver */
+};
+
+#define CMC_MISSING_VALUE 99999.0f   /* src/Common/Geometry.h:25 */
+#define CMC_ERR_THRESHOLD 0.01       /* src/FluidSolver3D/AdiSolver3D.h:32 */
+
+/* Grid3D public members read by the solver (src/FluidSolver3D/Grid3D.h:97-100) */
+typedef struct cmc_grid_desc {
+	int32_t dimx, dimy, dimz;
+	double dx, dy, dz;
+} cmc_grid_desc;
+
+/* Common::FluidParams (src/Common/Geometry.h:538-562) */
+typedef struct cmc_fluid_params {
+	double v_T, v_vis, t_vis, t_phi;
+} cmc_fluid_params;
+
+typedef struct cmc_adi3d cmc_adi3d;   /* opaque solver handle (one per GPU / rank) */
+
+const char *cmc_last_error(void);
+int cmc_abi_version(void);
+/* number of visible CUDA devices, or CMC_ERR_NO_DEVICE */
+int cmc_device_count(void);
+
+/* ---- lifetime: replaces `new AdiSolver3D` + Solver3D::Init (Solver3D.h:27, AdiSolver3D.cpp:166-268) ---- */
+int cmc_adi3d_create(const cmc_grid_desc *grid, const cmc_fluid_params *params,
+                     int fp_bytes, int device, cmc_adi3d **out);
+/* one slab of a multi-GPU run (one process per GPU).  The grid is split into contiguous slabs
+ * of whole x-planes (the slowest axis; GPUplan::splitEven1D, src/Common/GPUplan.cpp:122-141).
+ * `nccl_unique_id` is the 128-byte ncclUniqueId produced by cmc_nccl_unique_id() on rank 0 and
+ * distributed by the host (e.g. torch.distributed broadcast). */
+int cmc_nccl_unique_id(void *id128);
+int cmc_adi3d_create_dist(const cmc_grid_desc *grid, const cmc_fluid_params *params,
+                          int fp_bytes, int device, int rank, int nranks,
+                          const void *nccl_unique_id, cmc_adi3d **out);
+int cmc_adi3d_destroy(cmc_adi3d *h);           /* ~AdiSolver3D (AdiSolver3D.cpp:153-158) */
+
+/* slab owned by this handle: global x range [x0, x0+nx) */
+int cmc_adi3d_slab(const cmc_adi3d *h, int *x0, int *nx);
+
+/* ---- grid nodes: replaces Grid3D::GetNodesCPU(), GetType, GetBC_vel, GetBC_temp, GetVel, GetT (Grid3D.h:114-124) ----
+ * Arrays cover the WHOLE grid (dimx*dimy*dimz); a distributed handle takes its own slab from them.
+ * Also initialises the time layers like `new TimeLayer3D(grid)` does (TimeLayer3D.h:734-751,1077-1090):
+ * cur = (Node.v, Node.T) in every cell; half/next/temp (uninitialised in the reference) start as copies. */
+int cmc_adi3d_set_nodes(cmc_adi3d *h, const int32_t *type, const int32_t *bc_vel, const int32_t *bc_temp,
+                        const void *vx, const void *vy, const void *vz, const void *T);
+/* same, straight from the reference's `Node*` (Grid3D.h:73-88): {int type, bc_vel, bc_temp; FTYPE vx,vy,vz,T}
+ * (28 bytes in the fp32 build; 48 in fp64, where the FTYPE members start at offset 16) */
+int cmc_adi3d_set_nodes_aos(cmc_adi3d *h, const void *nodes, size_t node_stride_bytes);
+
+/* ---- AdiSolver3D::CreateSegments (AdiSolver3D.cpp:553-562; Grid3D::GenerateListSegments, Grid3D.cpp:47-127):
+ * builds the per-direction line descriptors (segment roles + boundary rows) on the device. */
+int cmc_adi3d_build_lines(cmc_adi3d *h);
+int cmc_adi3d_num_segments(const cmc_adi3d *h, int dir, int64_t *n);
+
+/* ---- Solver3D::UpdateBoundaries (Solver3D.h:35, AdiSolver3D.cpp:286-304) ---- */
+int cmc_adi3d_update_boundaries(cmc_adi3d *h);
+
+/* ---- Solver3D::TimeStep (Solver3D.h:28, AdiSolver3D.cpp:306-391).  `dt` is rounded to FTYPE like the
+ * caller's (FTYPE)dt cast (FluidSolver3D.cpp:242).  *err_out receives diffError (refreshed only when
+ * compute_error != 0).  Returns CMC_ERR_DIVERGED (layers NOT swapped) when diffError > 0.01. */
+int cmc_adi3d_time_step(cmc_adi3d *h, double dt, int num_global, int num_local,
+                        int compute_error, double *err_out);
+
+/* ---- Solver3D::GetLayer (Solver3D.h:33, Solver3D.cpp:21-25; TimeLayer3D::FilterToArrays, TimeLayer3D.h:819-924):
+ * writes 99999 into the NODE_OUT cells of `next` (the PREVIOUS time layer - and keeps that mutation, like the
+ * reference), then nearest-lower downsamples it.  vel_xyz = Vec3D[ox*oy*oz] (3 x FTYPE interleaved), T = double[].
+ * Output dims of 0 mean "grid dims".  On a distributed handle every rank must call; rank 0 receives the result. */
+int cmc_adi3d_get_layer(cmc_adi3d *h, void *vel_xyz, double *T, int outdimx, int outdimy, int outdimz);
+
+/* ---- options ----  "mode": CMC_MODE_FAST | CMC_MODE_EXACT;  "fold_boundaries": 0|1 */
+int cmc_adi3d_set_option(cmc_adi3d *h, const char *key, int64_t value);
+int cmc_adi3d_get_option(const cmc_adi3d *h, const char *key, int64_t *value);
+
+/* ---- test / debug hooks (the reference's TimeLayer3D dumps and sum_layer, AdiSolver3D.cpp:30-58) ---- */
+/* dense host copy (this handle's slab: nx*dimy*dimz values) of one field of one layer */
+int cmc_adi3d_read_field(cmc_adi3d *h, int layer, int var, void *dst);
+int cmc_adi3d_write_field(cmc_adi3d *h, int layer, int var, const void *src);
+/* TimeStep prologue only: next<-cur on BOUND/VALVE, temp<-cur (AdiSolver3D.cpp:310-320) */
+int cmc_adi3d_step_prologue(cmc_adi3d *h);
+/* one AdiSolver3D::SolveDirection (AdiSolver3D.cpp:564-666): num_local x (solve all lines, merge into temp) */
+int cmc_adi3d_solve_direction(cmc_adi3d *h, int dir, double dt, int num_local, int cur_layer, int next_layer);
+/* TimeLayer3D::EvalDivError of one layer (TimeLayer3D.h:595-641) */
+int cmc_adi3d_eval_div_error(cmc_adi3d *h, int layer, double *err_out);
+
+/* ---- device-resident control for benchmarking (inputs already in HBM) ---- */
+/* enqueue a step without any host synchronisation (compute_error results are fetched by cmc_adi3d_sync) */
+int cmc_adi3d_time_step_async(cmc_adi3d *h, double dt, int num_global, int num_local, int compute_error);
+int cmc_adi3d_sync(cmc_adi3d *h, double *err_out);
+/* the CUDA stream all work of this handle is ordered on (a cudaStream_t), for event timing */
+int cmc_adi3d_stream(const cmc_adi3d *h, void **stream_out);
+/* kernels launched by this handle since creation / since the last reset */
+int cmc_adi3d_launch_count(const cmc_adi3d *h, int64_t *n, int reset);
+/* bytes of device memory held by this handle */
+int cmc_adi3d_device_bytes(const cmc_adi3d *h, int64_t *n);
+
+/* ---- standalone batched line solver (unit tests of the GPU tridiagonal kernels against
+ * Common::SolveTridiagonal, src/Common/Algorithms.h:21-38).  Host arrays a,b,c,d,x: nsys*n, system-major. */
+int cmc_solve_tridiagonal_batch(int fp_bytes, int mode, int nsys, int n,
+                                const void *a, const void *b, const void *c, const void *d, void *x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMC_ADI_H */

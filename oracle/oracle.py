@@ -11,13 +11,15 @@ from __future__ import annotations
 import ctypes as C
 import os
 import struct
+import sys
 import subprocess
-from dataclasses import dataclass, field
 from pathlib import Path
 
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parent))
+from cmc_fluid_solver_b200.cases import Case  # noqa: E402  (plain data container, no CUDA)
 LIB_PATH = HERE / "_build" / "liboracle_adi.so"
 REF_DIR = HERE / "_ref"
 
@@ -48,43 +50,6 @@ def lib() -> C.CDLL:
 
 def _np_ft(fp_bytes: int):
     return np.float32 if fp_bytes == 4 else np.float64
-
-
-@dataclass
-class Case:
-    """A solver case: grid, fluid parameters and the reference's Node[] as arrays."""
-    dimx: int
-    dimy: int
-    dimz: int
-    dx: float
-    dy: float
-    dz: float
-    v_T: float
-    v_vis: float
-    t_vis: float
-    t_phi: float
-    dt: float
-    num_global: int
-    num_local: int
-    fp_bytes: int
-    type: np.ndarray = None
-    bc_vel: np.ndarray = None
-    bc_temp: np.ndarray = None
-    vx: np.ndarray = None
-    vy: np.ndarray = None
-    vz: np.ndarray = None
-    T: np.ndarray = None
-    baseT: float = 1.0
-    outdims: tuple = (0, 0, 0)
-    snapshots: list = field(default_factory=list)
-
-    @property
-    def shape(self):
-        return (self.dimx, self.dimy, self.dimz)
-
-    @property
-    def ncells(self):
-        return self.dimx * self.dimy * self.dimz
 
 
 def read_probe(path) -> Case:
