@@ -16,7 +16,7 @@ SYMBOLS = [
     "cmc_adi3d_set_option", "cmc_adi3d_get_option",
     "cmc_adi3d_read_field", "cmc_adi3d_write_field", "cmc_adi3d_step_prologue", "cmc_adi3d_solve_direction",
     "cmc_adi3d_eval_div_error", "cmc_adi3d_time_step_async", "cmc_adi3d_sync", "cmc_adi3d_stream",
-    "cmc_adi3d_launch_count", "cmc_adi3d_device_bytes", "cmc_solve_tridiagonal_batch",
+    "cmc_adi3d_launch_count", "cmc_adi3d_get_timing", "cmc_adi3d_device_bytes", "cmc_solve_tridiagonal_batch",
 ]
 
 
@@ -72,6 +72,7 @@ def load_library() -> C.CDLL:
         "cmc_adi3d_sync": [vp, P(dbl)],
         "cmc_adi3d_stream": [vp, P(vp)],
         "cmc_adi3d_launch_count": [vp, P(i64), i32],
+        "cmc_adi3d_get_timing": [vp, i32, P(dbl), P(i64)],
         "cmc_adi3d_device_bytes": [vp, P(i64)],
         "cmc_solve_tridiagonal_batch": [i32, i32, i32, i32, vp, vp, vp, vp, vp],
     }

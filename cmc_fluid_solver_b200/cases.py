@@ -158,15 +158,26 @@ BAFFLE_OUTLINE = [  # same channel with a wall-attached baffle (SURVEY.md Append
 ]
 
 
+# Four one-millimetre passive marks well outside the channel.  They only widen the bounding box so that a
+# coarse grid (grid_d > 2 % of the extent, the loader's fixed padding - Geometry.h:471-478) still gets an
+# OUT rim around the geometry; each mark rasterises to an isolated BOUND cell inside the OUT region.
+RIM_MARKS = [
+    ("Passive", [(-150, 500), (-150, 501)], None),
+    ("Passive", [(1150, 500), (1150, 501)], None),
+    ("Passive", [(500, -150), (501, -150)], None),
+    ("Passive", [(500, 1150), (501, 1150)], None),
+]
+
+
 def write_shape2d_case(directory, name, outline=None, grid_d=0.02, depth=1.0, depth_var=0.0, duration=10.0,
                        time_steps=100, num_global=4, num_local=2, Re=200.0, Pr=0.72, lam=1.4,
-                       out_grid=(16, 16, 16), out_time_steps=10, solver="ADI", dimension="3D"):
+                       out_grid=(16, 16, 16), out_time_steps=10, solver="ADI", dimension="3D", rim=False):
     """Write `<name>_data.txt` (Shape2D: frames / shapes / points in millimetres, `Passive` or `Motion vx vy`)
     and `<name>_config.txt` (whitespace `key value` pairs, reference src/Common/Config.h:203-245).
     Returns (data_path, config_path)."""
     directory = Path(directory)
     directory.mkdir(parents=True, exist_ok=True)
-    outline = outline or BOX_OUTLINE
+    outline = list(outline or BOX_OUTLINE) + (RIM_MARKS if rim else [])
     lines = ["1", f"{duration}", f"{len(outline)}"]
     for kind, pts, vel in outline:
         lines.append(str(len(pts)))

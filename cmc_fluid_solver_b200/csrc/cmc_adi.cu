@@ -60,10 +60,42 @@ struct cmc_adi3d {
 	long long launches = 0;
 	long long dev_bytes = 0;
 	long long num_segs[3] = {0, 0, 0};
+	long long shared_free[3] = {0, 0, 0};   // cells shared by two segments with a BC_FREE row (fast solver falls back)
 	int mode = CMC_MODE_FAST;
 	int fold_boundaries = 0;
 	bool have_nodes = false, have_lines = false;
 	DistContext *dist = nullptr;
+
+	// optional per-kernel-kind device timing (cmc_adi3d_set_option "profile"): CUDA event pairs on `stream`
+	int profile = 0;
+	struct Span { int kind; cudaEvent_t a, b; };
+	std::vector<Span> spans;
+	double kind_ms[CMC_TIMING_KINDS] = {};
+	long long kind_calls[CMC_TIMING_KINDS] = {};
+	void span_begin(int kind)
+	{
+		if (!profile) return;
+		Span sp; sp.kind = kind;
+		cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
+		cudaEventRecord(sp.a, stream);
+		spans.push_back(sp);
+	}
+	void span_end()
+	{
+		if (!profile || spans.empty()) return;
+		cudaEventRecord(spans.back().b, stream);
+	}
+	void spans_collect()
+	{
+		if (spans.empty()) return;
+		cudaStreamSynchronize(stream);
+		for (auto &sp : spans) {
+			float ms = 0.f;
+			if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { kind_ms[sp.kind] += ms; kind_calls[sp.kind]++; }
+			cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+		}
+		spans.clear();
+	}
 };
 
 namespace {
@@ -93,6 +125,7 @@ struct Solver : cmc_adi3d {
 	{
 		cudaSetDevice(device);
 		if (stream) cudaStreamSynchronize(stream);
+		spans_collect();
 		for (auto &l : field) for (auto &p : l) if (p) cudaFree(p);
 		for (auto &p : nodev) if (p) cudaFree(p);
 		for (auto &p : role) if (p) cudaFree(p);
@@ -137,7 +170,7 @@ struct Solver : cmc_adi3d {
 		if ((rc = dalloc(cT, (size_t)L.total))) return rc;
 		if ((rc = dalloc(d_partials, (size_t)2 * kMaxErrBlocks))) return rc;
 		if ((rc = dalloc(d_err2, 2))) return rc;
-		if ((rc = dalloc(d_segcount, 4))) return rc;
+		if ((rc = dalloc(d_segcount, 8))) return rc;
 		CU_TRY(cudaHostAlloc((void **)&h_err2, 2 * sizeof(double), cudaHostAllocDefault));
 		h_err2[0] = h_err2[1] = 0.0;
 		CU_TRY(cudaStreamSynchronize(stream));
@@ -236,15 +269,15 @@ struct Solver : cmc_adi3d {
 	{
 		if (!have_nodes) return fail(CMC_ERR_INVALID, "build_lines: call cmc_adi3d_set_nodes first");
 		CU_TRY(cudaSetDevice(device));
-		CU_TRY(cudaMemsetAsync(d_segcount, 0, 4 * sizeof(unsigned long long), stream));
+		CU_TRY(cudaMemsetAsync(d_segcount, 0, 8 * sizeof(unsigned long long), stream));
 		for (int d = 0; d < 3; d++) CU_TRY(cudaMemsetAsync(role[d], 0, (size_t)L.total, stream));
 		launch_role_type_bits(G, ncode, L, role[0], role[1], role[2], stream, &launches);
 		for (int d = 0; d < 3; d++) launch_build_roles(d, G, ncode, L, role[d], d_segcount + d, stream, &launches);
-		unsigned long long h[4];
+		unsigned long long h[8];
 		CU_TRY(cudaMemcpyAsync(h, d_segcount, sizeof h, cudaMemcpyDeviceToHost, stream));
 		CU_TRY(cudaStreamSynchronize(stream));
 		CU_TRY(cudaGetLastError());
-		for (int d = 0; d < 3; d++) num_segs[d] = (long long)h[d];
+		for (int d = 0; d < 3; d++) { num_segs[d] = (long long)h[d]; shared_free[d] = (long long)h[4 + d]; }
 		if (nranks > 1 && dist) {
 			int rc = dist_sum_i64(dist, &num_segs[1], 2, stream);   // Y/Z counted per slab, X counted globally
 			if (rc) return fail(CMC_ERR_COMM, dist_error());
@@ -258,7 +291,9 @@ struct Solver : cmc_adi3d {
 		if (!have_lines) return fail(CMC_ERR_INVALID, "update_boundaries: call cmc_adi3d_build_lines first");
 		CU_TRY(cudaSetDevice(device));
 		ConstLayerPtrs<FT> nv; for (int q = 0; q < 4; q++) nv.f[q] = nodev[q];
+		span_begin(CMC_TIMING_BOUNDARY);
 		launch_update_boundaries<FT>(L, role[2], nv, layer(CMC_LAYER_CUR), stream, &launches);
+		span_end();
 		return CMC_OK;
 	}
 
@@ -296,13 +331,20 @@ struct Solver : cmc_adi3d {
 				std::swap(slot[CMC_LAYER_TEMP], spare);
 				done = true;
 			}
-			if (!done && mode == CMC_MODE_FAST && launch_fast_sweep<FT>(dir, A, stream, &launches)) {
-				std::swap(slot[CMC_LAYER_TEMP], spare);      // merged temp went to the other buffer
-				done = true;
+			if (!done && mode == CMC_MODE_FAST && shared_free[dir] == 0) {
+				span_begin(CMC_TIMING_SWEEP_X + dir);
+				done = launch_fast_sweep<FT>(dir, A, stream, &launches);
+				span_end();
+				if (done) std::swap(slot[CMC_LAYER_TEMP], spare);      // merged temp went to the other buffer
+				else if (profile) spans.pop_back();
 			}
 			if (!done) {
+				span_begin(CMC_TIMING_SWEEP_X + dir);
 				launch_exact_sweep<FT>(dir, A, stream, &launches);
+				span_end();
+				span_begin(CMC_TIMING_MERGE);
 				launch_merge<FT>(L, role[dir], clayer(next_layer), layer(CMC_LAYER_TEMP), stream, &launches);
+				span_end();
 			}
 		}
 		return CMC_OK;
@@ -313,8 +355,10 @@ struct Solver : cmc_adi3d {
 		if (!have_lines) return fail(CMC_ERR_INVALID, "time_step: call cmc_adi3d_build_lines first");
 		CU_TRY(cudaSetDevice(device));
 		// cur -> next on BOUND and VALVE cells (AdiSolver3D.cpp:310-311); temp <- cur (:320)
+		span_begin(CMC_TIMING_COPY);
 		launch_copy_masked<FT>(L, role[2], R_BV, clayer(CMC_LAYER_CUR), layer(CMC_LAYER_NEXT), stream, &launches);
 		launch_copy_full<FT>(L, clayer(CMC_LAYER_CUR), layer(CMC_LAYER_TEMP), stream, &launches);
+		span_end();
 		return CMC_OK;
 	}
 
@@ -358,9 +402,16 @@ struct Solver : cmc_adi3d {
 			if ((rc = solve_direction_impl(CMC_DIR_Y, dt, nl, CMC_LAYER_NEXT, CMC_LAYER_HALF))) return rc;
 			if ((rc = solve_direction_impl(CMC_DIR_X, dt, nl, CMC_LAYER_HALF, CMC_LAYER_NEXT))) return rc;
 			// update non-linear layer once more (:354): temp = (temp + next) / 2 on NODE_IN
+			span_begin(CMC_TIMING_MERGE);
 			launch_merge<FT>(L, role[2], clayer(CMC_LAYER_NEXT), layer(CMC_LAYER_TEMP), stream, &launches);
+			span_end();
 		}
-		if (ce && (rc = enqueue_div_error(CMC_LAYER_NEXT))) return rc;
+		if (ce) {
+			span_begin(CMC_TIMING_RESIDUAL);
+			rc = enqueue_div_error(CMC_LAYER_NEXT);
+			span_end();
+			if (rc) return rc;
+		}
 		if (!async) {
 			if ((rc = fetch_error())) return rc;
 			CU_TRY(cudaGetLastError());
@@ -425,6 +476,7 @@ struct Solver : cmc_adi3d {
 		if (oy == 0) oy = G.ny;
 		if (oz == 0) oz = G.nz;
 		if (ox < 0 || oy < 0 || oz < 0) return fail(CMC_ERR_INVALID, "get_layer: negative output dims");
+		span_begin(CMC_TIMING_READBACK);
 		launch_clear_out<FT>(L, role[2], layer(CMC_LAYER_NEXT), (FT)CMC_MISSING_VALUE, stream, &launches);
 		// output rows i whose source plane x = i*dimx/outdimx lies in this slab
 		int oi0 = ox, oi1 = 0;
@@ -442,6 +494,7 @@ struct Solver : cmc_adi3d {
 			out_cap = outN;
 		}
 		launch_filter<FT>(L, clayer(CMC_LAYER_NEXT), ox, oy, oz, oi0, oi1, d_outvel, d_outT, stream, &launches);
+		span_end();
 		if (oi1 > oi0) {
 			const size_t o0 = (size_t)oi0 * oy * oz, cnt = (size_t)(oi1 - oi0) * oy * oz;
 			if (nranks == 1 || rank == 0) {
@@ -648,6 +701,12 @@ int cmc_adi3d_set_option(cmc_adi3d *h, const char *key, int64_t value)
 		return CMC_OK;
 	}
 	if (!strcmp(key, "fold_boundaries")) { h->fold_boundaries = value != 0; return CMC_OK; }
+	if (!strcmp(key, "profile")) {
+		h->spans_collect();
+		h->profile = value != 0;
+		if (value == 2) for (int k = 0; k < CMC_TIMING_KINDS; k++) { h->kind_ms[k] = 0.0; h->kind_calls[k] = 0; }
+		return CMC_OK;
+	}
 	return fail(CMC_ERR_INVALID, std::string("set_option: unknown key ") + key);
 }
 
@@ -658,6 +717,7 @@ int cmc_adi3d_get_option(const cmc_adi3d *h, const char *key, int64_t *value)
 	if (!strcmp(key, "mode")) { *value = h->mode; return CMC_OK; }
 	if (!strcmp(key, "fold_boundaries")) { *value = h->fold_boundaries; return CMC_OK; }
 	if (!strcmp(key, "nzp")) { *value = h->L.nzp; return CMC_OK; }
+	if (!strcmp(key, "shared_free_cells")) { *value = h->shared_free[0] + h->shared_free[1] + h->shared_free[2]; return CMC_OK; }
 	return fail(CMC_ERR_INVALID, std::string("get_option: unknown key ") + key);
 }
 
@@ -703,6 +763,17 @@ int cmc_adi3d_launch_count(const cmc_adi3d *h, int64_t *n, int reset)
 	H_CHECK(h);
 	if (n) *n = h->launches;
 	if (reset) const_cast<cmc_adi3d *>(h)->launches = 0;
+	return CMC_OK;
+}
+
+int cmc_adi3d_get_timing(cmc_adi3d *h, int kind, double *total_ms, int64_t *calls)
+{
+	H_CHECK(h);
+	if (kind < 0 || kind >= CMC_TIMING_KINDS) return fail(CMC_ERR_INVALID, "get_timing: bad kind");
+	cudaSetDevice(h->device);
+	h->spans_collect();
+	if (total_ms) *total_ms = h->kind_ms[kind];
+	if (calls) *calls = h->kind_calls[kind];
 	return CMC_OK;
 }
 

@@ -44,8 +44,8 @@ __global__ void k_build_roles(const Layout G, const uint8_t *__restrict__ ncode,
 		n = gnz; gbase = ((long long)(i + L.x0) * gny + j) * gnz; gstride = 1;
 		lbase = L.idx(i, j, 0); lstride = 1;
 	}
-	int state = 0, start = 0;
-	unsigned long long count = 0;
+	int state = 0, start = 0, prev_end = -1;
+	unsigned long long count = 0, shared_free = 0;
 	for (int p = 0; p + 1 < n; p++) {
 		if (code_type(ncode[gbase + (long long)(p + 1) * gstride]) == 0u /* NODE_IN */) {
 			if (state == 0) start = p;
@@ -57,11 +57,16 @@ __global__ void k_build_roles(const Layout G, const uint8_t *__restrict__ ncode,
 				const unsigned bits = q == start ? R_START : q == end ? R_END : R_INT;
 				role[lbase + (long long)q * lstride] |= (uint8_t)bits;
 			}
+			// a cell that ends one segment and starts the next one holds TWO unknowns when its boundary row is
+			// BC_FREE; the whole-line fast solver cannot represent that (exact mode can) - count such cells
+			if (start == prev_end && (ncode[gbase + (long long)start * gstride] & 12u)) shared_free++;
+			prev_end = end;
 			count++;
 			state = 0;
 		}
 	}
 	if (count) atomicAdd(seg_count, count);
+	if (shared_free) atomicAdd(seg_count + 4, shared_free);
 }
 
 void launch_build_roles(int dir, const Layout &G, const uint8_t *ncode, const Layout &L, uint8_t *role,

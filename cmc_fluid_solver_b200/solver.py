@@ -187,6 +187,20 @@ class AdiSolver3D:
         _check(load_library().cmc_adi3d_launch_count(self._h, C.byref(n), int(reset)))
         return n.value
 
+    TIMING_KINDS = ("sweep_x", "sweep_y", "sweep_z", "merge", "copy", "boundary", "residual", "readback", "comm")
+
+    def set_profile(self, on=True, reset=False):
+        _check(load_library().cmc_adi3d_set_option(self._h, b"profile", 2 if (on and reset) else int(bool(on))))
+
+    def timings(self):
+        """{kind: (total_ms, calls)} of device time per kernel family (needs set_profile(True))."""
+        out = {}
+        for k, name in enumerate(self.TIMING_KINDS):
+            ms, n = C.c_double(0), C.c_int64(0)
+            _check(load_library().cmc_adi3d_get_timing(self._h, k, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
     def device_bytes(self) -> int:
         n = C.c_int64(0)
         _check(load_library().cmc_adi3d_device_bytes(self._h, C.byref(n)))

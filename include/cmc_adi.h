@@ -121,7 +121,7 @@ int cmc_adi3d_time_step(cmc_adi3d *h, double dt, int num_global, int num_local,
  * Output dims of 0 mean "grid dims".  On a distributed handle every rank must call; rank 0 receives the result. */
 int cmc_adi3d_get_layer(cmc_adi3d *h, void *vel_xyz, double *T, int outdimx, int outdimy, int outdimz);
 
-/* ---- options ----  "mode": CMC_MODE_FAST | CMC_MODE_EXACT;  "fold_boundaries": 0|1 */
+/* ---- options ----  "mode": CMC_MODE_FAST | CMC_MODE_EXACT;  "profile": 0|1|2 (see cmc_adi3d_get_timing) */
 int cmc_adi3d_set_option(cmc_adi3d *h, const char *key, int64_t value);
 int cmc_adi3d_get_option(const cmc_adi3d *h, const char *key, int64_t *value);
 
@@ -144,6 +144,16 @@ int cmc_adi3d_sync(cmc_adi3d *h, double *err_out);
 int cmc_adi3d_stream(const cmc_adi3d *h, void **stream_out);
 /* kernels launched by this handle since creation / since the last reset */
 int cmc_adi3d_launch_count(const cmc_adi3d *h, int64_t *n, int reset);
+/* device time per kernel family, measured with CUDA event pairs on the handle's stream while option
+ * "profile" is 1 (the reference's Profiler event names, src/FluidSolver3D/AdiSolver3D.cpp:297-367:
+ * SolveSegments_X/Y/Z, MergeLayer, CopyLayer, UpdateBoundaries, EvalDivError; plus GetLayer's kernels).
+ * set_option("profile", 2) also clears the accumulators. */
+enum {
+	CMC_TIMING_SWEEP_X = 0, CMC_TIMING_SWEEP_Y = 1, CMC_TIMING_SWEEP_Z = 2, CMC_TIMING_MERGE = 3,
+	CMC_TIMING_COPY = 4, CMC_TIMING_BOUNDARY = 5, CMC_TIMING_RESIDUAL = 6, CMC_TIMING_READBACK = 7,
+	CMC_TIMING_COMM = 8, CMC_TIMING_KINDS = 9
+};
+int cmc_adi3d_get_timing(cmc_adi3d *h, int kind, double *total_ms, int64_t *calls);
 /* bytes of device memory held by this handle */
 int cmc_adi3d_device_bytes(const cmc_adi3d *h, int64_t *n);
 

@@ -483,5 +483,17 @@ void FN(oracle3d_get_layer)(void *h, FT *vel, double *T, int outdimx, int outdim
 			}
 }
 
+/* OpenMP thread count of the segment loop.  The reference's `omp for` over segments (AdiSolver3D.cpp:593-603)
+ * races when two segments share an end cell whose boundary row is BC_FREE; with one thread the later segment
+ * of the list wins, which is the order the CUDA path implements. */
+void FN(oracle_set_threads)(int n)
+{
+#ifdef _OPENMP
+	omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+#else
+	(void)n;
+#endif
+}
+
 /* standalone Thomas (unit tests of the GPU line solvers) */
 void FN(oracle_solve_tridiagonal)(FT *a, FT *b, FT *c, FT *d, FT *x, int num) { SolveTridiagonal(a, b, c, d, x, num); }

@@ -233,6 +233,13 @@ class Oracle3D:
         return vel, T
 
 
+def set_threads(n: int):
+    """OpenMP threads of the oracle's segment loop (0 = all cores)."""
+    f = lib().oracle_set_threads_f64
+    f.argtypes = [C.c_int]
+    f(int(n))
+
+
 def solve_tridiagonal(a, b, c, d):
     """Common::SolveTridiagonal on copies of a,b,c,d (dtype decides fp32/fp64)."""
     ft = a.dtype

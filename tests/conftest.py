@@ -1,0 +1,69 @@
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_golden(name):
+    """Golden vector written by tests/golden/make_golden.py from the REAL reference solver."""
+    from cmc_fluid_solver_b200.cases import Case
+    z = np.load(GOLDEN / f"{name}.npz")
+    dims = [int(v) for v in z["dims"]]
+    sp = [float(v) for v in z["spacing"]]
+    pr = [float(v) for v in z["params"]]
+    it = [int(v) for v in z["iters"]]
+    fp = int(z["fp_bytes"])
+    case = Case(*dims, *sp, *pr, float(z["dt"]), it[0], it[1], fp,
+                type=z["type"].astype(np.int32), bc_vel=z["bc_vel"].astype(np.int32), bc_temp=z["bc_temp"].astype(np.int32),
+                vx=z["vx"], vy=z["vy"], vz=z["vz"], T=z["T"], outdims=tuple(int(v) for v in z["outdims"]))
+    exp = dict(err=z["err"], last=[z["u_last"], z["v_last"], z["w_last"], z["T_last"]],
+               layer0_vel=z["layer0_vel"], layer0_T=z["layer0_T"], steps=int(z["steps"]))
+    return case, exp
+
+
+def drive(solver_like, case, steps, out_every=10, getlayer=True):
+    """The reference driver loop (FluidSolver3D.cpp:226-262): UpdateBoundaries; TimeStep; GetLayer every
+    out_time_steps.  Works for the oracle front-end and for the CUDA mirror (same method names differ only
+    in case)."""
+    errs, layers = [], []
+    for i in range(steps):
+        ce = (i % 10 == 0) or (i == steps - 1)
+        if hasattr(solver_like, "UpdateBoundaries"):
+            solver_like.UpdateBoundaries()
+            errs.append(solver_like.TimeStep(case.dt, case.num_global, case.num_local, ce))
+            if getlayer and i % out_every == 0:
+                layers.append(solver_like.GetLayer(*case.outdims))
+        else:
+            solver_like.update_boundaries()
+            errs.append(solver_like.time_step(case.dt, case.num_global, case.num_local, ce))
+            if getlayer and i % out_every == 0:
+                layers.append(solver_like.get_layer(*case.outdims))
+    return errs, layers
+
+
+def max_rel(ref, got, mask=None):
+    ref = np.asarray(ref, dtype=np.float64).ravel()
+    got = np.asarray(got, dtype=np.float64).ravel()
+    if mask is not None:
+        ref, got = ref[mask.ravel()], got[mask.ravel()]
+    scale = max(float(np.abs(ref).max()), 1e-300)
+    linf = float(np.abs(ref - got).max()) / scale
+    l2 = float(np.linalg.norm(ref - got)) / max(float(np.linalg.norm(ref)), 1e-300)
+    return linf, l2
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    from oracle import oracle as O
+    O.build()
+    return O

@@ -1,0 +1,245 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle / the reference's golden vectors.
+
+ * exact mode: bit-for-bit (every cell, fp32 and fp64);
+ * fast mode : BASELINE.json north_star tolerances - fp64 1e-10, fp32 1e-5 (relative L-inf and L2 per field).
+"""
+import numpy as np
+import pytest
+
+from conftest import drive, load_golden, max_rel
+from cmc_fluid_solver_b200 import AdiSolver3D, CmcError
+from cmc_fluid_solver_b200.cases import Case, channel_case
+from cmc_fluid_solver_b200.solver import (DIR_X, DIR_Y, DIR_Z, LAYER_CUR, LAYER_HALF, LAYER_NEXT, LAYER_TEMP,
+                                          solve_tridiagonal_batch)
+
+pytestmark = pytest.mark.gpu
+
+TOL = {8: 1e-10, 4: 1e-5}
+
+
+def _check_fields(O, ora, sol, case, mode, what=""):
+    for q in range(4):
+        ref = ora.field(O.LAYER_CUR, q)
+        got = sol.read_field(LAYER_CUR, q)
+        if mode == "exact":
+            assert np.array_equal(ref, got), f"{what}: exact mode differs from the oracle in field {q}"
+        else:
+            linf, l2 = max_rel(ref, got)
+            assert linf <= TOL[case.fp_bytes] and l2 <= TOL[case.fp_bytes], f"{what}: field {q} linf {linf:.3e} l2 {l2:.3e}"
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("name", ["box32_f64", "box32_f32", "baffle32_f64", "baffle32_f32"])
+def test_golden_vectors_from_the_reference(name, mode):
+    case, exp = load_golden(name)
+    s = AdiSolver3D().Init(case, mode=mode)
+    s.CreateSegments()
+    errs, layers = drive(s, case, exp["steps"])
+    tol = 0.0 if mode == "exact" else TOL[case.fp_bytes]
+    for q in range(4):
+        got = s.read_field(LAYER_CUR, q).ravel()
+        if mode == "exact":
+            assert np.array_equal(got, exp["last"][q])
+        else:
+            linf, l2 = max_rel(exp["last"][q], got)
+            assert linf <= tol and l2 <= tol, (q, linf, l2)
+    assert np.allclose(errs, exp["err"], rtol=1e-6 if case.fp_bytes == 4 else 1e-9, atol=0)
+    vel, T = layers[0]
+    assert np.array_equal(vel, exp["layer0_vel"]) and np.array_equal(T, exp["layer0_T"])   # layer 0 = initial condition
+    s.close()
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("fp", [8, 4])
+@pytest.mark.parametrize("dims", [(40, 36, 32), (37, 29, 23), (64, 48, 80), (24, 130, 17)])
+def test_steps_against_oracle(oracle_mod, dims, fp, mode):
+    """Masked channel (baffle + bottom perturbation), ragged dims, 5 steps with GetLayer mutation in between."""
+    O = oracle_mod
+    case = channel_case(*dims, fp_bytes=fp, depth_var=0.25)
+    case.outdims = (7, 5, 6)
+    ora = O.Oracle3D(case); ora.create_segments()
+    s = AdiSolver3D().Init(case, mode=mode); s.CreateSegments()
+    assert [s.numSegs(d) for d in range(3)] == [len(ora.segments(d)) for d in range(3)]
+    for i in range(5):
+        ora.update_boundaries(); s.UpdateBoundaries()
+        e_ref = ora.time_step(case.dt, case.num_global, case.num_local, True)
+        e = s.TimeStep(case.dt, case.num_global, case.num_local, True)
+        assert abs(e - e_ref) <= (1e-5 if fp == 4 else 1e-9) * abs(e_ref)
+        if i in (0, 3):
+            v_ref, T_ref = ora.get_layer(*case.outdims)
+            v, T = s.GetLayer(*case.outdims)
+            if mode == "exact":
+                assert np.array_equal(v, v_ref) and np.array_equal(T, T_ref)
+            else:
+                assert np.allclose(v, v_ref, rtol=0, atol=TOL[fp] * 1e5) and np.allclose(T, T_ref, rtol=0, atol=TOL[fp] * 1e5)
+        _check_fields(O, ora, s, case, mode, f"step {i}")
+    s.close()
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("fp", [8, 4])
+@pytest.mark.parametrize("d", [DIR_X, DIR_Y, DIR_Z])
+def test_single_sweep_against_oracle(oracle_mod, d, fp, mode):
+    """Component level: one SolveDirection (num_local x {all lines, merge}) from a developed flow state."""
+    O = oracle_mod
+    case = channel_case(48, 40, 56, fp_bytes=fp)
+    ora = O.Oracle3D(case); ora.create_segments()
+    for _ in range(2):
+        ora.update_boundaries(); ora.time_step(case.dt, 2, 1, False)
+    s = AdiSolver3D().Init(case, mode=mode); s.CreateSegments()
+    for slot in (LAYER_CUR, LAYER_HALF, LAYER_NEXT, LAYER_TEMP):
+        for q in range(4):
+            s.write_field(slot, q, ora.field(slot, q))
+    ora.update_boundaries(); s.UpdateBoundaries()
+    ora.step_prologue(); s.step_prologue()
+    ora.solve_direction(d, case.dt, 2, O.LAYER_CUR, O.LAYER_TEMP, O.LAYER_NEXT)
+    s.SolveDirection(d, case.dt, 2, LAYER_CUR, LAYER_NEXT)
+    for slot in (LAYER_NEXT, LAYER_TEMP):
+        for q in range(4):
+            ref, got = ora.field(slot, q), s.read_field(slot, q)
+            if mode == "exact":
+                assert np.array_equal(ref, got), (slot, q)
+            else:
+                linf, l2 = max_rel(ref, got)
+                assert linf <= TOL[fp] and l2 <= TOL[fp], (slot, q, linf, l2)
+    s.close()
+
+
+def _line_case(line_types, bc_free_cells=(), fp=8):
+    """3 x 3 x n grid whose centre z-line has the given node types."""
+    n = len(line_types)
+    t = np.full((3, 3, n), 1, dtype=np.int32)
+    t[1, 1, :] = line_types
+    bcv = np.zeros(t.shape, np.int32); bct = np.zeros(t.shape, np.int32)
+    for k in bc_free_cells:
+        bcv[1, 1, k] = 1; bct[1, 1, k] = 1
+    ft = np.float32 if fp == 4 else np.float64
+    vx = np.zeros(t.shape, ft); T = np.ones(t.shape, ft)
+    vx[1, 1, :] = np.linspace(0.2, 1.0, n)
+    z = np.zeros(t.size, ft)
+    return Case(3, 3, n, .05, .05, .05, 1.0, 0.005, 0.007, 0.0014, 0.05, 2, 2, fp, type=t.ravel(), bc_vel=bcv.ravel(),
+                bc_temp=bct.ravel(), vx=vx.ravel(), vy=z, vz=vx.ravel().copy(), T=T.ravel())
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_edge_case_lines(oracle_mod, mode):
+    """A cell shared by two segments (NOSLIP and FREE boundary rows; FREE makes the fast solver fall back to the
+    exact kernels), segments of the minimum length 3, valves inside the line."""
+    O = oracle_mod
+    line = [1, 2, 0, 2, 0, 0, 2, 1, 2, 0, 2, 1, 1, 2, 0, 0, 0, 3, 0, 0, 0, 0, 3, 0, 0, 2, 1, 1]
+    O.set_threads(1)     # the reference's segment loop races on a shared FREE cell; one thread = list order
+    for free in ((), (22,), (3, 22)):
+        case = _line_case(line, free)
+        ora = O.Oracle3D(case); ora.create_segments()
+        s = AdiSolver3D().Init(case, mode=mode); s.CreateSegments()
+        assert [s.numSegs(d) for d in range(3)] == [len(ora.segments(d)) for d in range(3)]
+        for i in range(3):
+            ora.update_boundaries(); s.UpdateBoundaries()
+            ora.time_step(case.dt, 2, 2, False); s.TimeStep(case.dt, 2, 2, False)
+        _check_fields(O, ora, s, case, mode, f"free={free}")
+        s.close()
+    O.set_threads(0)
+
+
+def test_segment_counts_with_dropped_runs(oracle_mod):
+    """GenerateListSegments corner cases that make the reference read out of bounds when stepped (IN cells on a
+    domain face): only the line descriptors are compared - unterminated run dropped, IN cell at index 0 = start."""
+    O = oracle_mod
+    line = [0, 0, 2, 0, 0, 2, 1, 2, 0, 2, 1, 1, 2, 0, 0, 0]
+    case = _line_case(line)
+    ora = O.Oracle3D(case); ora.create_segments()
+    s = AdiSolver3D().Init(case); s.CreateSegments()
+    assert [s.numSegs(d) for d in range(3)] == [len(ora.segments(d)) for d in range(3)]
+    assert s.numSegs(DIR_Z) == 3
+    s.close()
+
+
+def test_get_layer_returns_previous_layer_and_mutates_it(oracle_mod):
+    O = oracle_mod
+    case = channel_case(20, 18, 16, fp_bytes=8, baffle=False)
+    s = AdiSolver3D().Init(case, mode="exact"); s.CreateSegments()
+    s.UpdateBoundaries(); s.TimeStep(case.dt, 1, 1, True)
+    vel, T = s.GetLayer()                                   # full resolution
+    vel = vel.reshape(*case.shape, 3)
+    out = case.type.reshape(case.shape) == 1
+    assert np.all(vel[out] == 99999.0) and np.all(T.reshape(case.shape)[out] == 99999.0)
+    # previous layer = initial condition: inflow valve u = 1, T = 1 in the fluid
+    init_u = case.vx.reshape(case.shape)
+    assert np.array_equal(vel[..., 0][~out], init_u[~out])
+    assert np.all(s.read_field(LAYER_NEXT, 0)[out] == 99999.0)     # mutation is kept in `next`
+    s.close()
+
+
+def test_divergence_guard(oracle_mod):
+    """dt far beyond the diagonal-dominance limit: residual > 0.01 -> CMC_ERR_DIVERGED, layers not swapped."""
+    from cmc_fluid_solver_b200 import DivergedError
+    case = channel_case(20, 18, 16, fp_bytes=8, baffle=False, inflow=400.0)
+    s = AdiSolver3D().Init(case, mode="exact"); s.CreateSegments()
+    s.UpdateBoundaries()
+    before = s.read_field(LAYER_CUR, 0)
+    with pytest.raises(DivergedError) as ei:
+        for _ in range(20):
+            s.TimeStep(5.0, 2, 1, True)
+            before = s.read_field(LAYER_CUR, 0)
+    assert "Error is too big!" in str(ei.value)
+    assert np.array_equal(before, s.read_field(LAYER_CUR, 0))
+    s.close()
+
+
+def test_call_order_and_argument_errors():
+    case = channel_case(12, 12, 12, baffle=False)
+    s = AdiSolver3D().Init(case)
+    with pytest.raises(CmcError):
+        s.TimeStep(0.1, 1, 1, True)          # CreateSegments not called
+    s.CreateSegments()
+    with pytest.raises(CmcError):
+        s.SolveDirection(5, 0.1, 1, LAYER_CUR, LAYER_NEXT)
+    s.close()
+
+
+@pytest.mark.parametrize("fp", [8, 4])
+@pytest.mark.parametrize("n", [3, 8, 64, 77, 200, 512])
+def test_batched_line_solver_against_thomas(oracle_mod, n, fp):
+    """Unit level: GPU Thomas (exact, bit-for-bit) and partition+PCR (fast, tolerance) vs Common::SolveTridiagonal."""
+    O = oracle_mod
+    ft = np.float32 if fp == 4 else np.float64
+    rng = np.random.default_rng(n)
+    nsys = 37
+    a = rng.uniform(-1.2, -0.2, (nsys, n)).astype(ft); c = rng.uniform(-1.2, -0.2, (nsys, n)).astype(ft)
+    b = (2.6 + rng.uniform(0, 1, (nsys, n))).astype(ft); d = rng.normal(size=(nsys, n)).astype(ft)
+    ref = np.stack([O.solve_tridiagonal(a[i], b[i], c[i], d[i]) for i in range(nsys)])
+    assert np.array_equal(solve_tridiagonal_batch(a, b, c, d, "exact"), ref)
+    got = solve_tridiagonal_batch(a, b, c, d, "fast")
+    assert np.abs(got - ref).max() <= (2e-5 if fp == 4 else 1e-12) * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("fp", [8, 4])
+def test_full_size_properties(fp):
+    """BASELINE config sizes (256^3 masked) are too slow for the CPU oracle inside the test budget: check the fast
+    path against the bit-exact GPU path (itself pinned to the oracle above) and invariants of the scheme."""
+    dims = (256, 256, 256)
+    case = channel_case(*dims, fp_bytes=fp)
+    sols = {m: AdiSolver3D().Init(case, mode=m) for m in ("exact", "fast")}
+    for s in sols.values():
+        s.CreateSegments()
+    assert sols["exact"].numSegs(0) == sols["fast"].numSegs(0) > 0
+    errs = {}
+    for m, s in sols.items():
+        for i in range(2):
+            s.UpdateBoundaries()
+            errs[m] = s.TimeStep(case.dt, case.num_global, case.num_local, True)
+    assert abs(errs["fast"] - errs["exact"]) <= 1e-6 * errs["exact"]
+    out = (case.type == 1).reshape(dims)
+    bnd = ((case.type == 2) | (case.type == 3)).reshape(dims)
+    noslip = bnd & (case.bc_vel.reshape(dims) == 0)
+    for q in range(4):
+        ref = sols["exact"].read_field(LAYER_CUR, q); got = sols["fast"].read_field(LAYER_CUR, q)
+        linf, l2 = max_rel(ref, got)
+        assert linf <= TOL[fp] and l2 <= TOL[fp], (q, linf, l2)
+        init = (case.vx, case.vy, case.vz, case.T)[q].reshape(dims)
+        assert np.array_equal(got[out], init[out])                 # OUT cells are never written by a sweep
+        if q < 3:
+            assert np.array_equal(got[noslip], init[noslip])       # no-slip rows reproduce the node value exactly
+        assert np.isfinite(got).all()
+    for s in sols.values():
+        s.close()
