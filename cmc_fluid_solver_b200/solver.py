@@ -217,3 +217,10 @@ def solve_tridiagonal_batch(a, b, c, d, mode="exact"):
     m = {"fast": MODE_FAST, "exact": MODE_EXACT}[mode]
     _check(load_library().cmc_solve_tridiagonal_batch(a.itemsize, m, nsys, n, _ptr(a), _ptr(b), _ptr(c), _ptr(d), _ptr(x)))
     return x
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte ncclUniqueId for cmc_adi3d_create_dist (call on rank 0, broadcast to the others)."""
+    buf = C.create_string_buffer(128)
+    _check(load_library().cmc_nccl_unique_id(buf))
+    return buf.raw

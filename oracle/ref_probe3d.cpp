@@ -183,7 +183,9 @@ int main(int argc, char **argv)
 			double t0 = omp_get_wtime();
 			solver->UpdateBoundaries();
 			solver->TimeStep((FTYPE)dt, Config::num_global, Config::num_local, computeError);
-			t_steps += omp_get_wtime() - t0;
+			const double t1 = omp_get_wtime();
+			t_steps += t1 - t0;
+			printf("\nprobe: step %d seconds %.6f\n", i, t1 - t0);
 			if (getlayer && (i % Config::out_time_steps) == 0) {
 				solver->GetLayer(resVel, resT, Config::outdimx, Config::outdimy, Config::outdimz);
 				put_i32(i); put_i32(1); put_f64(solver->diffError);
