@@ -12,9 +12,9 @@
 //     M = 8 rows, one thread per chunk; the last row of each chunk is its separator;
 //   * the 7 interior rows are eliminated in registers (forward sweep carrying the left spike), a short
 //     backward recurrence gives the chunk's coupling to its two separators;
-//   * the separators form a reduced tridiagonal system of G = n/8 unknowns per line, solved by
-//     parallel cyclic reduction (PCR) in shared memory, one thread per unknown, normalised rows
-//     (one reciprocal per step);
+//   * the separators form a reduced tridiagonal system of GP = n/8 unknowns per line, solved in shared
+//     memory by cyclic reduction down to 8 rows + parallel cyclic reduction (normalised rows, one
+//     reciprocal per step);
 //   * back substitution of the interior rows from registers, results stored once.
 //
 // Thread mapping.  X and Y sweeps (strided lines): a CTA owns NL = 8 neighbouring k-columns of one
@@ -23,13 +23,15 @@
 // warp reads 32 consecutive 64-byte chunks = 2 KB of one line with 128-bit loads.
 // HBM traffic per cell and sweep is the algorithmic 16 values + 1 descriptor byte: stencil neighbours and
 // re-reads for the merge are served by L1/L2.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 #include "kernels.h"
-#include "rows.cuh"
 
 namespace cmc {
 
 constexpr int M = 8;          // rows per chunk
-constexpr int NL = 8;         // lines per CTA
+constexpr int NLB = 8;        // systems per CTA of the standalone batch solver
 
 // Reciprocal without the IEEE division slow path: hardware seed + Newton steps (fp64: MUFU.RCP64H seed, two
 // fused Newton iterations -> < 1 ulp for the well-scaled pivots of a diagonally dominant system).
@@ -51,15 +53,16 @@ template <> __device__ __forceinline__ double rcp<double>(double x)
 template <typename FT>
 struct FastConst {
 	FT inv2h;            // 1 / (2 h_D)
-	FT inv2hx, inv2hy, inv2hz;
+	FT inv2h1, inv2h2;   // 1 / (2 h) of the two cross directions
 	FT vis_v, vis_T, b_v, b_T;
 	FT c3dt;             // 3 / dt
 	FT v_T, t_phi;
-	__device__ __forceinline__ void init(const SweepArgs<FT> &A, int dir)
+	__host__ __device__ __forceinline__ void init(const SweepArgs<FT> &A, int dir)
 	{
 		const FT h = A.h[dir];
 		inv2h = FT(1) / (2 * h);
-		inv2hx = FT(1) / (2 * A.h[0]); inv2hy = FT(1) / (2 * A.h[1]); inv2hz = FT(1) / (2 * A.h[2]);
+		inv2h1 = FT(1) / (2 * A.h[dir == 0 ? 1 : 0]);
+		inv2h2 = FT(1) / (2 * A.h[dir == 2 ? 1 : 2]);
 		vis_v = A.v_vis / (h * h); vis_T = A.t_vis / (h * h);
 		c3dt = 3 / A.dt;
 		b_v = c3dt + 2 * vis_v; b_T = c3dt + 2 * vis_T;
@@ -67,79 +70,118 @@ struct FastConst {
 	}
 };
 
-// RHS of the temperature row: cur.T*3/dt + t_phi * DissFunc_D(temp) (TimeLayer3D.h:554-588)
-template <typename FT, int DIR>
-__device__ __forceinline__ FT temperature_rhs(const SweepArgs<FT> &A, const FastConst<FT> &K, long long id, long long sx, long long sy, long long sz)
-{
-	const FT *tu = A.temp[0], *tv = A.temp[1], *tw = A.temp[2];
-	FT diss;
-	if (DIR == 0) {
-		const FT u_x = (tu[id + sx] - tu[id - sx]) * K.inv2hx, v_x = (tv[id + sx] - tv[id - sx]) * K.inv2hx, w_x = (tw[id + sx] - tw[id - sx]) * K.inv2hx;
-		const FT u_y = (tu[id + sy] - tu[id - sy]) * K.inv2hy, u_z = (tu[id + sz] - tu[id - sz]) * K.inv2hz;
-		diss = 2 * u_x * u_x + v_x * v_x + w_x * w_x + v_x * u_y + w_x * u_z;
-	} else if (DIR == 1) {
-		const FT u_y = (tu[id + sy] - tu[id - sy]) * K.inv2hy, v_y = (tv[id + sy] - tv[id - sy]) * K.inv2hy, w_y = (tw[id + sy] - tw[id - sy]) * K.inv2hy;
-		const FT v_x = (tv[id + sx] - tv[id - sx]) * K.inv2hx, v_z = (tv[id + sz] - tv[id - sz]) * K.inv2hz;
-		diss = u_y * u_y + 2 * v_y * v_y + w_y * w_y + u_y * v_x + w_y * v_z;
-	} else {
-		const FT u_z = (tu[id + sz] - tu[id - sz]) * K.inv2hz, v_z = (tv[id + sz] - tv[id - sz]) * K.inv2hz, w_z = (tw[id + sz] - tw[id - sz]) * K.inv2hz;
-		const FT w_x = (tw[id + sx] - tw[id - sx]) * K.inv2hx, w_y = (tw[id + sy] - tw[id - sy]) * K.inv2hy;
-		diss = u_z * u_z + v_z * v_z + 2 * w_z * w_z + u_z * w_x + v_z * w_y;
-	}
-	return A.cur[3][id] * K.c3dt + K.t_phi * diss;
-}
-
-// ---- PCR over the reduced systems of a CTA ---------------------------------------------------------------
-// Rows are normalised (B == 1).  sys[(slot*NR + r) * GP * NL + g * NL + l], slot in {0,1} ping-pong.
-// NR = 2 + NRHS (A, C, D...).  Element (g, l) = chunk g of line l.  GP = G rounded up to a power of two
-// (rows >= G are identity rows).
-template <typename FT, int NRHS>
-__device__ __forceinline__ void pcr_solve(FT *sys, int GP, int g, int e, int gstep, FT Ain, FT Cin, const FT (&Din)[NRHS], FT (&X)[NRHS])
+// ---- reduced systems of a CTA: cyclic reduction + PCR hybrid in shared memory ----------------------------------
+// One thread per reduced row (chunk g of a line), rows normalised (B == 1).  GP = chunks per line rounded up to a
+// power of two (rows >= G are identity rows).  e = shared-memory element of this row, GS = element distance of
+// neighbouring chunks of the same line.
+//   forward : L levels of cyclic reduction - at level l (stride s = 2^l) every second surviving row is eliminated:
+//             it publishes (A, C, D) once and keeps them in registers; its two neighbours absorb it;
+//   middle  : PCR over the GP / 2^L surviving rows (<= 8: three steps);
+//   backward: eliminated rows recover x from their two (already solved) neighbours.
+// The solutions of ALL rows end up in sol[q * STR + e].  Fully unrolled: GP, GS are compile-time.
+template <typename FT, int NRHS, int GP, int GS, int NL>
+__device__ __forceinline__ void reduced_solve(FT *sys, FT *sol, int g, int e, FT Ain, FT Cin, const FT (&Din)[NRHS], FT (&X)[NRHS])
 {
 	constexpr int NR = 2 + NRHS;
-	const int stride = GP * NL;
+	constexpr int STR = GP * NL;
+	constexpr int L = GP > 8 ? (GP == 16 ? 1 : GP == 32 ? 2 : 3) : 0;
 	FT A = Ain, Cc = Cin, D[NRHS];
 #pragma unroll
 	for (int q = 0; q < NRHS; q++) D[q] = Din[q];
-	int buf = 0;
-	for (int s = 1; s < GP; s <<= 1) {
-		FT *w = sys + buf * NR * stride;
-		w[0 * stride + e] = A; w[1 * stride + e] = Cc;
+	FT *crs = sys;                       // CR publications: NR arrays (each row publishes once, at its own element)
+	FT *pp = sys + NR * STR;             // PCR ping-pong: 2 * NR arrays (only surviving rows used)
+	int my_level = -1;                   // level at which this row was eliminated (-1: survives into the PCR)
 #pragma unroll
-		for (int q = 0; q < NRHS; q++) w[(2 + q) * stride + e] = D[q];
-		__syncthreads();
-		const bool lo = g - s >= 0, hi = g + s < GP;
-		const int el = e - s * gstep, eh = e + s * gstep;
-		const FT Al = lo ? w[0 * stride + el] : FT(0), Cl = lo ? w[1 * stride + el] : FT(0);
-		const FT Ah = hi ? w[0 * stride + eh] : FT(0), Ch = hi ? w[1 * stride + eh] : FT(0);
-		const FT r = rcp<FT>(FT(1) - A * Cl - Cc * Ah);
+	for (int lv = 0; lv < L; lv++) {
+		const int s = 1 << lv;
+		const bool alive = (g & (s - 1)) == 0 && my_level < 0;
+		const bool odd = alive && ((g >> lv) & 1);
+		if (odd) {
+			my_level = lv;
+			crs[0 * STR + e] = A; crs[1 * STR + e] = Cc;
 #pragma unroll
-		for (int q = 0; q < NRHS; q++) {
-			const FT Dl = lo ? w[(2 + q) * stride + el] : FT(0), Dh = hi ? w[(2 + q) * stride + eh] : FT(0);
-			D[q] = (D[q] - A * Dl - Cc * Dh) * r;
+			for (int q = 0; q < NRHS; q++) crs[(2 + q) * STR + e] = D[q];
 		}
-		A = -A * Al * r;
-		Cc = -Cc * Ch * r;
-		buf ^= 1;
+		__syncthreads();
+		if (alive && !odd) {
+			const bool lo = g - s >= 0, hi = g + s < GP;
+			const FT *l = crs + e - s * GS, *h = crs + e + s * GS;
+			const FT Al = lo ? l[0 * STR] : FT(0), Cl = lo ? l[1 * STR] : FT(0);
+			const FT Ah = hi ? h[0 * STR] : FT(0), Ch = hi ? h[1 * STR] : FT(0);
+			const FT r = rcp<FT>(FT(1) - A * Cl - Cc * Ah);
+#pragma unroll
+			for (int q = 0; q < NRHS; q++) {
+				const FT Dl = lo ? l[(2 + q) * STR] : FT(0), Dh = hi ? h[(2 + q) * STR] : FT(0);
+				D[q] = (D[q] - A * Dl - Cc * Dh) * r;
+			}
+			A = -A * Al * r;
+			Cc = -Cc * Ch * r;
+		}
+	}
+	const bool survivor = my_level < 0 && (g & ((1 << L) - 1)) == 0;
+#pragma unroll
+	for (int st = 0; (1 << (L + st)) < GP; st++) {
+		const int s = 1 << (L + st);
+		FT *w = pp + (st & 1) * NR * STR;
+		if (survivor) {
+			w[0 * STR + e] = A; w[1 * STR + e] = Cc;
+#pragma unroll
+			for (int q = 0; q < NRHS; q++) w[(2 + q) * STR + e] = D[q];
+		}
+		__syncthreads();
+		if (survivor) {
+			const bool lo = g - s >= 0, hi = g + s < GP;
+			const FT *l = w + e - s * GS, *h = w + e + s * GS;
+			const FT Al = lo ? l[0 * STR] : FT(0), Cl = lo ? l[1 * STR] : FT(0);
+			const FT Ah = hi ? h[0 * STR] : FT(0), Ch = hi ? h[1 * STR] : FT(0);
+			const FT r = rcp<FT>(FT(1) - A * Cl - Cc * Ah);
+#pragma unroll
+			for (int q = 0; q < NRHS; q++) {
+				const FT Dl = lo ? l[(2 + q) * STR] : FT(0), Dh = hi ? h[(2 + q) * STR] : FT(0);
+				D[q] = (D[q] - A * Dl - Cc * Dh) * r;
+			}
+			A = -A * Al * r;
+			Cc = -Cc * Ch * r;
+		}
+	}
+	if (survivor) {
+#pragma unroll
+		for (int q = 0; q < NRHS; q++) sol[q * STR + e] = D[q];
+	}
+	__syncthreads();
+#pragma unroll
+	for (int lv = L - 1; lv >= 0; lv--) {
+		const int s = 1 << lv;
+		if (my_level == lv) {
+			const bool lo = g - s >= 0, hi = g + s < GP;
+#pragma unroll
+			for (int q = 0; q < NRHS; q++) {
+				const FT xl = lo ? sol[q * STR + e - s * GS] : FT(0), xh = hi ? sol[q * STR + e + s * GS] : FT(0);
+				D[q] = D[q] - A * xl - Cc * xh;
+				sol[q * STR + e] = D[q];
+			}
+		}
+		__syncthreads();
 	}
 #pragma unroll
 	for (int q = 0; q < NRHS; q++) X[q] = D[q];
 }
 
 // ---- line I/O: 8 consecutive rows of this thread's chunk ----------------------------------------------------
-// X / Y sweeps: rows are `stride` apart, lanes of a warp sit on neighbouring k (coalesced 64-byte segments).
-// Z sweep: the 8 rows are 8 contiguous elements (64 bytes in fp64) -> 128-bit vector accesses.
+// X / Y sweeps: rows are `stride` apart, lanes of a warp sit on neighbouring k (coalesced 64-byte segments);
+// off[i] = element offset of row i (clamped into the line, computed once and shared by all fields).
+// Z sweep: the 8 rows are 8 contiguous elements (64 bytes in fp64) -> 128-bit vector accesses at off[0].
 template <typename FT> struct Vec16;
 template <> struct Vec16<double> { typedef double2 type; static constexpr int N = 2; };
 template <> struct Vec16<float> { typedef float4 type; static constexpr int N = 4; };
 
 template <typename FT, int DIR>
-__device__ __forceinline__ void load8(const FT *__restrict__ p, long long base, long long stride, int r0, int n, FT (&o)[M])
+__device__ __forceinline__ void load8(const FT *__restrict__ p, const int (&off)[M], FT (&o)[M])
 {
 	if (DIR == 2) {
 		typedef typename Vec16<FT>::type V;
 		constexpr int N = Vec16<FT>::N;
-		const V *q = reinterpret_cast<const V *>(p + base + r0);     // r0 % 8 == 0 and lines are 128-byte aligned
+		const V *q = reinterpret_cast<const V *>(p + off[0]);        // 64-byte aligned: r0 % 8 == 0, lines 128-byte aligned
 #pragma unroll
 		for (int v = 0; v < M / N; v++) {
 			const V t = q[v];
@@ -149,44 +191,40 @@ __device__ __forceinline__ void load8(const FT *__restrict__ p, long long base, 
 		}
 	} else {
 #pragma unroll
-		for (int i = 0; i < M; i++) {
-			const int r = min(r0 + i, n - 1);                         // rows past the end: any valid address (value unused)
-			o[i] = p[base + (long long)r * stride];
-		}
+		for (int i = 0; i < M; i++) o[i] = p[off[i]];
 	}
 }
 
+// store rows whose bit is set in `mask` (Z: whole chunk with vector stores when all 8 bits are set)
 template <typename FT, int DIR>
-__device__ __forceinline__ void store8(FT *__restrict__ p, long long base, long long stride, int r0, int n, const FT (&v)[M])
+__device__ __forceinline__ void store8(FT *__restrict__ p, const int (&off)[M], unsigned mask, const FT (&v)[M])
 {
 	if (DIR == 2) {
-		typedef typename Vec16<FT>::type V;
-		constexpr int N = Vec16<FT>::N;
-		V *q = reinterpret_cast<V *>(p + base + r0);                  // the padded tail of a z-line may be written freely
+		if (mask == 0xffu) {
+			typedef typename Vec16<FT>::type V;
+			constexpr int N = Vec16<FT>::N;
+			V *q = reinterpret_cast<V *>(p + off[0]);
 #pragma unroll
-		for (int w = 0; w < M / N; w++) {
-			V t;
-			FT *e = reinterpret_cast<FT *>(&t);
+			for (int w = 0; w < M / N; w++) {
+				V t;
+				FT *e = reinterpret_cast<FT *>(&t);
 #pragma unroll
-			for (int k = 0; k < N; k++) e[k] = v[w * N + k];
-			q[w] = t;
+				for (int k = 0; k < N; k++) e[k] = v[w * N + k];
+				q[w] = t;
+			}
+		} else {
+#pragma unroll
+			for (int i = 0; i < M; i++)
+				if (mask & (1u << i)) p[off[0] + i] = v[i];
 		}
 	} else {
 #pragma unroll
 		for (int i = 0; i < M; i++)
-			if (r0 + i < n) p[base + (long long)(r0 + i) * stride] = v[i];
+			if (mask & (1u << i)) p[off[i]] = v[i];
 	}
 }
 
-// rows r0-1 and r0+8 (clamped into the line; only interior rows use them and their neighbours always exist)
-template <typename FT>
-__device__ __forceinline__ void load_ends(const FT *__restrict__ p, long long base, long long stride, int r0, int n, FT &lo, FT &hi)
-{
-	lo = p[base + (long long)max(r0 - 1, 0) * stride];
-	hi = p[base + (long long)min(r0 + M, n - 1) * stride];
-}
-
-// central difference along the line for the 8 rows of a chunk
+// central difference along the line for the 8 rows of a chunk (lo / hi = rows r0-1 and r0+8)
 template <typename FT>
 __device__ __forceinline__ FT cdiff(const FT (&f)[M], FT lo, FT hi, int i, FT inv2h)
 {
@@ -194,21 +232,32 @@ __device__ __forceinline__ FT cdiff(const FT (&f)[M], FT lo, FT hi, int i, FT in
 	return (p - m) * inv2h;
 }
 
-template <typename FT, int DIR>
-__global__ void __launch_bounds__(512, 1) k_fast_sweep(const SweepArgs<FT> A, const int G, const int GP)
+// One chunk: eliminate the 7 interior rows of (a, b, c | d[NRHS]) given row by row, keep the separator raw.
+// cp/lp/dp hold c', the left spike and d' of the interior rows; entry M-1 holds the raw separator (lp = a, cp = c).
+#define CMC_ELIM_ROW(i, a, b, c)                                                   \
+	if ((i) == M - 1) { lp[i] = (a); cp[i] = (c); b7 = (b); }                      \
+	else if ((i) == 0) { rr = rcp<FT>(b); cp[0] = (c) * rr; lp[0] = (a) * rr; }    \
+	else { rr = rcp<FT>((b) - (a) * cp[(i) - 1]); cp[i] = (c) * rr; lp[i] = -(a) * lp[(i) - 1] * rr; }
+
+template <typename FT, int DIR, int GP, int NL>
+__global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_sweep(const SweepArgs<FT> A, const FastConst<FT> K, long long *trace, const int one)
 {
+#define CMC_MARK(k) do { if (trace) { __syncthreads(); if (threadIdx.x == 0) trace[(size_t)blockIdx.x * 16 + (k)] = clock64(); } } while (0)
+	CMC_MARK(0);
+	constexpr int STR = GP * NL;
+	constexpr int GS = DIR == 2 ? 1 : NL;          // shared-memory distance of neighbouring chunks of a line
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	FT *sys = reinterpret_cast<FT *>(smem_raw);
-	FT *head = sys + 2 * 5 * GP * NL;
-	FT *sol = head + 5 * GP * NL;
+	FT *sys = reinterpret_cast<FT *>(smem_raw);    // 3 * 5 arrays (CR publications + PCR ping-pong)
+	FT *head = sys + 3 * 5 * STR;                  // 5 arrays: y0[3], v0, w0 of every chunk
+	FT *sol = head + 5 * STR;                      // 3 arrays: separator solutions
 
 	const Layout &L = A.L;
 	const int t = threadIdx.x;
-	int g, l;                       // chunk, line-in-CTA
+	int g, l;                                      // chunk, line-in-CTA
 	if (DIR == 2) { g = t % GP; l = t / GP; } else { l = t % NL; g = t / NL; }
+	const int e = t;                               // == l * GP + g (Z) or g * NL + l (X, Y): lanes -> consecutive elements
 
 	// ---- which line ----------------------------------------------------------------------------------------
-	const long long sx = L.plane, sy = L.nzp, sz = 1;
 	long long base;                 // element index of row 0 of this thread's line
 	long long stride;               // along the line
 	int n;                          // rows of the line
@@ -216,71 +265,85 @@ __global__ void __launch_bounds__(512, 1) k_fast_sweep(const SweepArgs<FT> A, co
 	if (DIR == 0) {                 // lines along x: CTA = (j, k-tile)
 		const int ktiles = (L.nz + NL - 1) / NL;
 		const int j = blockIdx.x / ktiles, k = (blockIdx.x % ktiles) * NL + l;
-		line_ok = k < L.nz; n = L.nx; stride = sx; base = L.idx(0, j, line_ok ? k : 0);
+		line_ok = k < L.nz; n = L.nx; stride = L.plane; base = L.idx(0, j, line_ok ? k : 0);
 	} else if (DIR == 1) {          // lines along y: CTA = (i, k-tile)
 		const int ktiles = (L.nz + NL - 1) / NL;
 		const int i = blockIdx.x / ktiles, k = (blockIdx.x % ktiles) * NL + l;
-		line_ok = k < L.nz; n = L.ny; stride = sy; base = L.idx(i, 0, line_ok ? k : 0);
+		line_ok = k < L.nz; n = L.ny; stride = L.nzp; base = L.idx(i, 0, line_ok ? k : 0);
 	} else {                        // lines along z: CTA = (i, j-tile)
 		const int jtiles = (L.ny + NL - 1) / NL;
 		const int i = blockIdx.x / jtiles, j = (blockIdx.x % jtiles) * NL + l;
-		line_ok = j < L.ny; n = L.nz; stride = sz; base = L.idx(i, line_ok ? j : 0, 0);
+		line_ok = j < L.ny; n = L.nz; stride = 1; base = L.idx(i, line_ok ? j : 0, 0);
 	}
 	const int r0 = g * M;           // first row of this chunk
-	// a chunk takes part in the loads/stores when it overlaps the line (z-lines: the 128-byte padded line)
-	const bool chunk_ok = line_ok && r0 < (DIR == 2 ? L.nzp : n);
-	FastConst<FT> K; K.init(A, DIR);
-
-	// shared-memory element of (chunk g, line l): consecutive lanes -> consecutive addresses in both mappings
-	const int e = DIR == 2 ? l * GP + g : g * NL + l;
-	const int e_next = DIR == 2 ? e + 1 : e + NL;      // chunk g+1 of the same line
-	const int e_prev = DIR == 2 ? e - 1 : e - NL;
-	const int gstep = DIR == 2 ? 1 : NL;               // shared-memory distance of neighbouring chunks
-	const int stride_s = GP * NL;
-
-	// roles of the chunk's rows (rows >= n or lines outside the grid: no segment, no store)
-	unsigned role[M];
-	{
-		uint8_t rb[M];
+	// Row offsets, clamped into the line so that EVERY thread issues valid (if redundant) loads: threads of padding
+	// chunks / lines outside the grid see role 0 everywhere, compute identity rows and store nothing.
+	int off[M], off_lo, off_hi;      // 32-bit element offsets (launch_fast_sweep checks total < 2^31)
+	if (DIR == 2) {
+		const int rc = min(r0, L.nzp - M);
 #pragma unroll
-		for (int i = 0; i < M; i++) rb[i] = 0;
-		if (chunk_ok) {
-			if (DIR == 2) {
-				const uint2 w = *reinterpret_cast<const uint2 *>(A.role + base + r0);
+		for (int i = 0; i < M; i++) off[i] = (int)base + rc + i;
+		off_lo = (int)base + max(r0 - 1, 0);
+		off_hi = (int)base + min(r0 + M, n - 1);
+	} else {
 #pragma unroll
-				for (int i = 0; i < 4; i++) { rb[i] = (uint8_t)(w.x >> (8 * i)); rb[4 + i] = (uint8_t)(w.y >> (8 * i)); }
-			} else {
-#pragma unroll
-				for (int i = 0; i < M; i++) rb[i] = A.role[base + (long long)min(r0 + i, n - 1) * stride];
-			}
-		}
-#pragma unroll
-		for (int i = 0; i < M; i++) role[i] = (r0 + i < n) ? (unsigned)rb[i] : 0u;
+		for (int i = 0; i < M; i++) off[i] = (int)base + min(r0 + i, n - 1) * (int)stride;
+		off_lo = (int)base + max(r0 - 1, 0) * (int)stride;
+		off_hi = (int)base + min(r0 + M, n - 1) * (int)stride;
 	}
+	unsigned rowmask = 0;           // rows of this chunk that exist
+#pragma unroll
+	for (int i = 0; i < M; i++) rowmask |= (line_ok && r0 + i < n) ? (1u << i) : 0u;
+
+	// roles of the chunk's rows
+	unsigned rw0 = 0, rw1 = 0;      // role bytes of rows 0-3 / 4-7, packed
+	if (DIR == 2) {
+		const uint2 w = *reinterpret_cast<const uint2 *>(A.role + off[0]);
+		rw0 = w.x; rw1 = w.y;
+	} else {
+#pragma unroll
+		for (int i = 0; i < 4; i++) { rw0 |= (unsigned)A.role[off[i]] << (8 * i); rw1 |= (unsigned)A.role[off[4 + i]] << (8 * i); }
+	}
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		if (!(rowmask & (1u << i))) rw0 &= ~(0xffu << (8 * i));
+		if (!(rowmask & (1u << (4 + i)))) rw1 &= ~(0xffu << (8 * i));
+	}
+#define ROLE(i) (((i) < 4 ? rw0 >> (8 * (i)) : rw1 >> (8 * ((i) - 4))) & 0xffu)
+	unsigned segmask = 0, inmask = 0;
+#pragma unroll
+	for (int i = 0; i < M; i++) {
+		segmask |= (ROLE(i) & R_SEG) ? (1u << i) : 0u;
+		inmask |= (ROLE(i) & R_IN) ? (1u << i) : 0u;
+	}
+	const bool any_int = ((rw0 | rw1) & (R_INT * 0x01010101u)) != 0;
+	const unsigned holes = inmask & ~segmask;      // fluid cells outside every segment (dropped runs)
+	// z-lines: the padded tail of the last chunk may be rewritten freely, which keeps the vector path
+	const unsigned full = (DIR == 2 && line_ok && r0 < n) ? 0xffu : rowmask;
+	const unsigned segfull = (segmask | (full & ~rowmask)) == 0xffu ? 0xffu : segmask;
 
 	// ======================================= phase V: u, v, w ==============================================
 	FT cp[M], lp[M], dp[3][M];
-	FT b7 = FT(1);
+	FT b7 = FT(1), rr;
 	{
-		FT V[M], Tl[M], Tlo = FT(0), Thi = FT(0);
-#pragma unroll
-		for (int i = 0; i < M; i++) { V[i] = FT(0); Tl[i] = FT(0); dp[0][i] = FT(0); dp[1][i] = FT(0); dp[2][i] = FT(0); }
-		if (chunk_ok) {
-			load8<FT, DIR>(A.temp[DIR], base, stride, r0, n, V);
-			load8<FT, DIR>(A.cur[0], base, stride, r0, n, dp[0]);
-			load8<FT, DIR>(A.cur[1], base, stride, r0, n, dp[1]);
-			load8<FT, DIR>(A.cur[2], base, stride, r0, n, dp[2]);
-			load8<FT, DIR>(A.temp[3], base, stride, r0, n, Tl);
-			load_ends<FT>(A.temp[3], base, stride, r0, n, Tlo, Thi);
+		FT V[M], Tl[M], Tlo, Thi;
+		// `one` is always 1: the real branch keeps every load of the phase in one basic block, ahead of the
+		// arithmetic, so that they are all in flight together (ptxas does not schedule across the branch)
+		if (one) {
+			load8<FT, DIR>(A.temp[DIR], off, V);
+			load8<FT, DIR>(A.cur[0], off, dp[0]);
+			load8<FT, DIR>(A.cur[1], off, dp[1]);
+			load8<FT, DIR>(A.cur[2], off, dp[2]);
+			load8<FT, DIR>(A.temp[3], off, Tl);
+			Tlo = A.temp[3][off_lo]; Thi = A.temp[3][off_hi];
 		}
 #pragma unroll
 		for (int i = 0; i < M; i++) {
-			const unsigned r = role[i];
+			const unsigned r = ROLE(i);
 			const bool is_int = r & R_INT, is_bc = r & (R_START | R_END), vfree = r & R_VFREE;
 			FT bd0 = FT(0), bd1 = FT(0), bd2 = FT(0);
 			if (is_bc && !vfree) {        // no-slip boundary row: value of the node (rare: two rows per segment)
-				const long long id = base + (long long)(r0 + i) * stride;
-				bd0 = A.nodev[0][id]; bd1 = A.nodev[1][id]; bd2 = A.nodev[2][id];
+				bd0 = A.nodev[0][off[i]]; bd1 = A.nodev[1][off[i]]; bd2 = A.nodev[2][off[i]];
 			}
 			const FT Vh = V[i] * K.inv2h;
 			const FT a = is_int ? -Vh - K.vis_v : ((r & R_END) && vfree ? FT(-1) : FT(0));
@@ -291,20 +354,17 @@ __global__ void __launch_bounds__(512, 1) k_fast_sweep(const SweepArgs<FT> A, co
 			d[1] = is_int ? dp[1][i] * K.c3dt : bd1;
 			d[2] = is_int ? dp[2][i] * K.c3dt : bd2;
 			if (is_int) d[DIR] -= K.v_T * cdiff<FT>(Tl, Tlo, Thi, i, K.inv2h);
-			if (i == M - 1) {       // separator row stays raw
-				lp[i] = a; cp[i] = c; b7 = b; dp[0][i] = d[0]; dp[1][i] = d[1]; dp[2][i] = d[2];
-			} else if (i == 0) {
-				const FT rr = rcp<FT>(b);
-				cp[0] = c * rr; lp[0] = a * rr; dp[0][0] = d[0] * rr; dp[1][0] = d[1] * rr; dp[2][0] = d[2] * rr;
-			} else {
-				const FT rr = rcp<FT>(b - a * cp[i - 1]);
-				cp[i] = c * rr; lp[i] = -a * lp[i - 1] * rr;
+			CMC_ELIM_ROW(i, a, b, c)
+			if (i == M - 1) { dp[0][i] = d[0]; dp[1][i] = d[1]; dp[2][i] = d[2]; }
+			else if (i == 0) { dp[0][0] = d[0] * rr; dp[1][0] = d[1] * rr; dp[2][0] = d[2] * rr; }
+			else {
 				dp[0][i] = (d[0] - a * dp[0][i - 1]) * rr;
 				dp[1][i] = (d[1] - a * dp[1][i - 1]) * rr;
 				dp[2][i] = (d[2] - a * dp[2][i - 1]) * rr;
 			}
 		}
 	}
+	CMC_MARK(1);   // phase V loads + elimination done
 	FT E[3];
 	{
 		// coupling of the first interior row to the two separators: x_0 = y0 - v0*E(g-1) - w0*E(g)
@@ -314,208 +374,217 @@ __global__ void __launch_bounds__(512, 1) k_fast_sweep(const SweepArgs<FT> A, co
 			y0[0] = dp[0][i] - cp[i] * y0[0]; y0[1] = dp[1][i] - cp[i] * y0[1]; y0[2] = dp[2][i] - cp[i] * y0[2];
 			v0 = lp[i] - cp[i] * v0; w0 = -cp[i] * w0;
 		}
-		head[0 * stride_s + e] = y0[0]; head[1 * stride_s + e] = y0[1]; head[2 * stride_s + e] = y0[2];
-		head[3 * stride_s + e] = v0; head[4 * stride_s + e] = w0;
+		head[0 * STR + e] = y0[0]; head[1 * STR + e] = y0[1]; head[2 * STR + e] = y0[2];
+		head[3 * STR + e] = v0; head[4 * STR + e] = w0;
 		__syncthreads();
 		// reduced row of this chunk's separator (row M-1): needs the head of chunk g+1
-		FT Ra, Rc, Rd[3];
 		const bool has_next = g + 1 < GP;
-		const FT ny0 = has_next ? head[0 * stride_s + e_next] : FT(0), ny1 = has_next ? head[1 * stride_s + e_next] : FT(0),
-		         ny2 = has_next ? head[2 * stride_s + e_next] : FT(0);
-		const FT nv = has_next ? head[3 * stride_s + e_next] : FT(0), nw = has_next ? head[4 * stride_s + e_next] : FT(0);
+		const FT *hn = head + e + GS;
+		const FT ny0 = has_next ? hn[0 * STR] : FT(0), ny1 = has_next ? hn[1 * STR] : FT(0), ny2 = has_next ? hn[2 * STR] : FT(0);
+		const FT nv = has_next ? hn[3 * STR] : FT(0), nw = has_next ? hn[4 * STR] : FT(0);
 		const FT a7 = lp[M - 1], c7 = cp[M - 1];
-		const FT rr = rcp<FT>(b7 - a7 * cp[M - 2] - c7 * nv);
-		Ra = -a7 * lp[M - 2] * rr; Rc = -c7 * nw * rr;
+		rr = rcp<FT>(b7 - a7 * cp[M - 2] - c7 * nv);
+		FT Rd[3];
 		Rd[0] = (dp[0][M - 1] - a7 * dp[0][M - 2] - c7 * ny0) * rr;
 		Rd[1] = (dp[1][M - 1] - a7 * dp[1][M - 2] - c7 * ny1) * rr;
 		Rd[2] = (dp[2][M - 1] - a7 * dp[2][M - 2] - c7 * ny2) * rr;
-		pcr_solve<FT, 3>(sys, GP, g, e, gstep, Ra, Rc, Rd, E);
-		// publish separator solutions for the chunk on the right
-		sol[0 * stride_s + e] = E[0]; sol[1 * stride_s + e] = E[1]; sol[2 * stride_s + e] = E[2];
-		__syncthreads();
+		reduced_solve<FT, 3, GP, GS, NL>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, E);    // every row's solution -> sol[]
 	}
+	CMC_MARK(2);   // phase V reduced solve done
 	// back substitution, store u, v, w and the relaxed linearisation layer
 #pragma unroll
 	for (int q = 0; q < 3; q++) {
-		const FT El = g > 0 ? sol[q * stride_s + e_prev] : FT(0);
+		const FT El = g > 0 ? sol[q * STR + e - GS] : FT(0);
 		FT x[M], tq[M];
+		if (one) load8<FT, DIR>(A.temp[q], off, tq);
 		x[M - 1] = E[q];
 #pragma unroll
 		for (int i = M - 2; i >= 0; i--) x[i] = dp[q][i] - lp[i] * El - cp[i] * x[i + 1];
-		if (chunk_ok) {
-			load8<FT, DIR>(A.temp[q], base, stride, r0, n, tq);
-			bool all_seg = true, hole = false;
+		if (holes) {                      // merge those with the OLD value of `next` (MergeFieldTo reads whatever is there)
 #pragma unroll
-			for (int i = 0; i < M; i++) {
-				const bool seg = role[i] & R_SEG, in = role[i] & R_IN;
-				all_seg &= seg || (DIR == 2 && r0 + i >= n);
-				hole |= in && !seg;
-			}
-			if (hole) {                       // fluid cell outside every segment (dropped run): merge with the old `next`
-#pragma unroll
-				for (int i = 0; i < M; i++)
-					if ((role[i] & R_IN) && !(role[i] & R_SEG)) x[i] = A.next[q][base + (long long)(r0 + i) * stride];
-			}
-#pragma unroll
-			for (int i = 0; i < M; i++) tq[i] = (role[i] & R_IN) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
-			store8<FT, DIR>(A.temp_out[q], base, stride, r0, n, tq);
-			if (all_seg) store8<FT, DIR>(A.next[q], base, stride, r0, n, x);
-			else {
-#pragma unroll
-				for (int i = 0; i < M; i++)
-					if (role[i] & R_SEG) A.next[q][base + (long long)(r0 + i) * stride] = x[i];
-			}
+			for (int i = 0; i < M; i++)
+				if (holes & (1u << i)) x[i] = A.next[q][off[i]];
 		}
+#pragma unroll
+		for (int i = 0; i < M; i++) tq[i] = (inmask & (1u << i)) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
+		store8<FT, DIR>(A.temp_out[q], off, full, tq);
+		store8<FT, DIR>(A.next[q], off, segfull, x);
 	}
+	CMC_MARK(3);   // phase V stores issued
 
 	// ======================================= phase T ======================================================
 	__syncthreads();                // head / sol / sys are reused
 	FT (&dT)[M] = dp[0];
 	{
-		FT V[M], cT[M];
-#pragma unroll
-		for (int i = 0; i < M; i++) { V[i] = FT(0); cT[i] = FT(0); }
-		FT diss[M];
-#pragma unroll
-		for (int i = 0; i < M; i++) diss[i] = FT(0);
-		if (chunk_ok) {
-			load8<FT, DIR>(A.temp[DIR], base, stride, r0, n, V);
-			load8<FT, DIR>(A.cur[3], base, stride, r0, n, cT);
+		FT diss[M], V[M], cT[M];
+		load8<FT, DIR>(A.cur[3], off, cT);
+		{
 			// dissipation function of the sweep direction (TimeLayer3D.h:554-588): derivatives along the line of
 			// u, v, w plus the two cross-line derivatives of the component aligned with the sweep
-			FT f[M], lo, hi, d_u[M], d_v[M], d_w[M];
-			load8<FT, DIR>(A.temp[0], base, stride, r0, n, f); load_ends<FT>(A.temp[0], base, stride, r0, n, lo, hi);
+			//   X: 2 u_x^2 + v_x^2 + w_x^2 + v_x u_y + w_x u_z ; Y: u_y^2 + 2 v_y^2 + w_y^2 + u_y v_x + w_y v_z ;
+			//   Z: u_z^2 + v_z^2 + 2 w_z^2 + u_z w_x + v_z w_y
+			FT f[M], dd[3][M];
 #pragma unroll
-			for (int i = 0; i < M; i++) d_u[i] = cdiff<FT>(f, lo, hi, i, K.inv2h);
-			load8<FT, DIR>(A.temp[1], base, stride, r0, n, f); load_ends<FT>(A.temp[1], base, stride, r0, n, lo, hi);
+			for (int q = 0; q < 3; q++) {
+				load8<FT, DIR>(A.temp[q], off, f);
+				const FT lo = A.temp[q][off_lo], hi = A.temp[q][off_hi];
 #pragma unroll
-			for (int i = 0; i < M; i++) d_v[i] = cdiff<FT>(f, lo, hi, i, K.inv2h);
-			load8<FT, DIR>(A.temp[2], base, stride, r0, n, f); load_ends<FT>(A.temp[2], base, stride, r0, n, lo, hi);
+				for (int i = 0; i < M; i++) dd[q][i] = cdiff<FT>(f, lo, hi, i, K.inv2h);
+				if (q == DIR) {
 #pragma unroll
-			for (int i = 0; i < M; i++) d_w[i] = cdiff<FT>(f, lo, hi, i, K.inv2h);
-			// cross-line derivatives of temp[DIR] in the two other directions
-			const long long s1 = DIR == 0 ? sy : sx, s2 = DIR == 2 ? sy : sz;
-			const FT i1 = DIR == 0 ? K.inv2hy : K.inv2hx, i2 = DIR == 2 ? K.inv2hy : K.inv2hz;
+					for (int i = 0; i < M; i++) V[i] = f[i];
+				}
+			}
+			// cross-line neighbours of temp[DIR]; lines next to an interior cell always exist, for everything else
+			// the (clamped, valid) addresses just deliver values that are never selected
+			const long long s1 = DIR == 0 ? L.nzp : L.plane, s2 = DIR == 2 ? L.nzp : 1;
+			const FT *tp = A.temp[DIR];
 			FT p1[M], m1[M], p2[M], m2[M];
-			const bool any_int = (role[0] | role[1] | role[2] | role[3] | role[4] | role[5] | role[6] | role[7]) & R_INT;
-			if (any_int) {          // neighbouring lines exist around every interior cell
-				if (DIR == 2) {
-					load8<FT, DIR>(A.temp[DIR], base + s1, stride, r0, n, p1); load8<FT, DIR>(A.temp[DIR], base - s1, stride, r0, n, m1);
-					load8<FT, DIR>(A.temp[DIR], base + s2, stride, r0, n, p2); load8<FT, DIR>(A.temp[DIR], base - s2, stride, r0, n, m2);
-				} else {
-					load8<FT, DIR>(A.temp[DIR], base + s1, stride, r0, n, p1); load8<FT, DIR>(A.temp[DIR], base - s1, stride, r0, n, m1);
-					load8<FT, DIR>(A.temp[DIR], base + s2, stride, r0, n, p2); load8<FT, DIR>(A.temp[DIR], base - s2, stride, r0, n, m2);
+#pragma unroll
+			for (int i = 0; i < M; i++) diss[i] = FT(0);
+			if (any_int) {
+				load8<FT, DIR>(tp + s1, off, p1); load8<FT, DIR>(tp - s1, off, m1);
+				if (DIR == 2) { load8<FT, DIR>(tp + s2, off, p2); load8<FT, DIR>(tp - s2, off, m2); }
+				else {          // +-1 element along k: unaligned, scalar
+#pragma unroll
+					for (int i = 0; i < M; i++) { p2[i] = tp[off[i] + 1]; m2[i] = tp[off[i] - 1]; }
 				}
 #pragma unroll
 				for (int i = 0; i < M; i++) {
-					const FT c1 = (p1[i] - m1[i]) * i1, c2 = (p2[i] - m2[i]) * i2;
-					// X: 2 u_x^2 + v_x^2 + w_x^2 + v_x u_y + w_x u_z ; Y: u_y^2 + 2 v_y^2 + w_y^2 + u_y v_x + w_y v_z ;
-					// Z: u_z^2 + v_z^2 + 2 w_z^2 + u_z w_x + v_z w_y
+					const FT c1 = (p1[i] - m1[i]) * K.inv2h1, c2 = (p2[i] - m2[i]) * K.inv2h2;
+					const FT du = dd[0][i], dv = dd[1][i], dw = dd[2][i];
 					FT s;
-					if (DIR == 0) s = 2 * d_u[i] * d_u[i] + d_v[i] * d_v[i] + d_w[i] * d_w[i] + d_v[i] * c1 + d_w[i] * c2;
-					else if (DIR == 1) s = d_u[i] * d_u[i] + 2 * d_v[i] * d_v[i] + d_w[i] * d_w[i] + d_u[i] * c1 + d_w[i] * c2;
-					else s = d_u[i] * d_u[i] + d_v[i] * d_v[i] + 2 * d_w[i] * d_w[i] + d_u[i] * c1 + d_v[i] * c2;
+					if (DIR == 0) s = 2 * du * du + dv * dv + dw * dw + dv * c1 + dw * c2;
+					else if (DIR == 1) s = du * du + 2 * dv * dv + dw * dw + du * c1 + dw * c2;
+					else s = du * du + dv * dv + 2 * dw * dw + du * c1 + dv * c2;
 					diss[i] = s;
 				}
 			}
 		}
 #pragma unroll
 		for (int i = 0; i < M; i++) {
-			const unsigned r = role[i];
+			const unsigned r = ROLE(i);
 			const bool is_int = r & R_INT, is_bc = r & (R_START | R_END), tfree = r & R_TFREE;
 			FT bd = FT(0);
-			if (is_bc && !tfree) bd = A.nodev[3][base + (long long)(r0 + i) * stride];
+			if (is_bc && !tfree) bd = A.nodev[3][off[i]];
 			const FT Vh = V[i] * K.inv2h;
 			const FT a = is_int ? -Vh - K.vis_T : ((r & R_END) && tfree ? FT(-1) : FT(0));
 			const FT c = is_int ? Vh - K.vis_T : ((r & R_START) && tfree ? FT(-1) : FT(0));
 			const FT b = is_int ? K.b_T : (is_bc && tfree ? FT(2) : FT(1));
 			const FT d = is_int ? cT[i] * K.c3dt + K.t_phi * diss[i] : bd;
-			if (i == M - 1) { lp[i] = a; cp[i] = c; b7 = b; dT[i] = d; }
-			else if (i == 0) { const FT rr = rcp<FT>(b); cp[0] = c * rr; lp[0] = a * rr; dT[0] = d * rr; }
-			else {
-				const FT rr = rcp<FT>(b - a * cp[i - 1]);
-				cp[i] = c * rr; lp[i] = -a * lp[i - 1] * rr; dT[i] = (d - a * dT[i - 1]) * rr;
-			}
+			CMC_ELIM_ROW(i, a, b, c)
+			if (i == M - 1) dT[i] = d;
+			else if (i == 0) dT[0] = d * rr;
+			else dT[i] = (d - a * dT[i - 1]) * rr;
 		}
 	}
+	CMC_MARK(4);   // phase T loads + elimination done
 	{
 		FT y0 = dT[M - 2], v0 = lp[M - 2], w0 = cp[M - 2];
 #pragma unroll
 		for (int i = M - 3; i >= 0; i--) { y0 = dT[i] - cp[i] * y0; v0 = lp[i] - cp[i] * v0; w0 = -cp[i] * w0; }
-		head[0 * stride_s + e] = y0; head[3 * stride_s + e] = v0; head[4 * stride_s + e] = w0;
+		head[0 * STR + e] = y0; head[3 * STR + e] = v0; head[4 * STR + e] = w0;
 		__syncthreads();
 		const bool has_next = g + 1 < GP;
-		const FT ny0 = has_next ? head[0 * stride_s + e_next] : FT(0);
-		const FT nv = has_next ? head[3 * stride_s + e_next] : FT(0), nw = has_next ? head[4 * stride_s + e_next] : FT(0);
+		const FT *hn = head + e + GS;
+		const FT ny0 = has_next ? hn[0 * STR] : FT(0), nv = has_next ? hn[3 * STR] : FT(0), nw = has_next ? hn[4 * STR] : FT(0);
 		const FT a7 = lp[M - 1], c7 = cp[M - 1];
-		const FT rr = rcp<FT>(b7 - a7 * cp[M - 2] - c7 * nv);
+		rr = rcp<FT>(b7 - a7 * cp[M - 2] - c7 * nv);
 		FT Rd[1] = {(dT[M - 1] - a7 * dT[M - 2] - c7 * ny0) * rr}, ET[1];
-		pcr_solve<FT, 1>(sys, GP, g, e, gstep, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, ET);
-		sol[e] = ET[0];
-		__syncthreads();
-		const FT El = g > 0 ? sol[e_prev] : FT(0);
+		reduced_solve<FT, 1, GP, GS, NL>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, ET);
+		CMC_MARK(5);   // phase T reduced solve done
+		const FT El = g > 0 ? sol[e - GS] : FT(0);
 		FT x[M], tq[M];
+		load8<FT, DIR>(A.temp[3], off, tq);
 		x[M - 1] = ET[0];
 #pragma unroll
 		for (int i = M - 2; i >= 0; i--) x[i] = dT[i] - lp[i] * El - cp[i] * x[i + 1];
-		if (chunk_ok) {
-			load8<FT, DIR>(A.temp[3], base, stride, r0, n, tq);
-			bool all_seg = true, hole = false;
+		if (holes) {
 #pragma unroll
-			for (int i = 0; i < M; i++) {
-				const bool seg = role[i] & R_SEG, in = role[i] & R_IN;
-				all_seg &= seg || (DIR == 2 && r0 + i >= n);
-				hole |= in && !seg;
-			}
-			if (hole) {
-#pragma unroll
-				for (int i = 0; i < M; i++)
-					if ((role[i] & R_IN) && !(role[i] & R_SEG)) x[i] = A.next[3][base + (long long)(r0 + i) * stride];
-			}
-#pragma unroll
-			for (int i = 0; i < M; i++) tq[i] = (role[i] & R_IN) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
-			store8<FT, DIR>(A.temp_out[3], base, stride, r0, n, tq);
-			if (all_seg) store8<FT, DIR>(A.next[3], base, stride, r0, n, x);
-			else {
-#pragma unroll
-				for (int i = 0; i < M; i++)
-					if (role[i] & R_SEG) A.next[3][base + (long long)(r0 + i) * stride] = x[i];
-			}
+			for (int i = 0; i < M; i++)
+				if (holes & (1u << i)) x[i] = A.next[3][off[i]];
 		}
+#pragma unroll
+		for (int i = 0; i < M; i++) tq[i] = (inmask & (1u << i)) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
+		store8<FT, DIR>(A.temp_out[3], off, full, tq);
+		store8<FT, DIR>(A.next[3], off, segfull, x);
 	}
+	CMC_MARK(6);
+#undef CMC_MARK
+#undef ROLE
 }
 
 template <typename FT>
-static size_t fast_smem_bytes(int GP) { return sizeof(FT) * (size_t)(2 * 5 * GP * NL + 5 * GP * NL + 3 * GP * NL); }
+static size_t fast_smem_bytes(int GP, int NL) { return sizeof(FT) * (size_t)(3 * 5 * GP * NL + 5 * GP * NL + 3 * GP * NL); }
+
+// lines per CTA: 8 (64-byte row segments in fp64) up to 256 threads per CTA; the 512-row case keeps 256 threads
+// (4 lines) so that one CTA per SM owns the whole register file: every load of a phase is in flight at once.
+constexpr int lines_per_cta(int GP) { return 8; }
+
+template <typename FT, int DIR, int GP>
+static unsigned launch_one(const SweepArgs<FT> &A, cudaStream_t s, long long *trace, bool dry)
+{
+	constexpr int NL = lines_per_cta(GP);
+	const Layout &L = A.L;
+	unsigned grid;
+	if (DIR == 0) grid = (unsigned)L.ny * (unsigned)((L.nz + NL - 1) / NL);
+	else if (DIR == 1) grid = (unsigned)L.nx * (unsigned)((L.nz + NL - 1) / NL);
+	else grid = (unsigned)L.nx * (unsigned)((L.ny + NL - 1) / NL);
+	if (dry) return grid;
+	static bool attr_set = false;
+	const size_t smem = fast_smem_bytes<FT>(GP, NL);
+	if (!attr_set) {
+		cudaFuncSetAttribute((const void *)k_fast_sweep<FT, DIR, GP, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		attr_set = true;
+	}
+	FastConst<FT> K; K.init(A, DIR);
+	k_fast_sweep<FT, DIR, GP, NL><<<grid, GP * NL, smem, s>>>(A, K, trace, 1);
+	return grid;
+}
+
+template <typename FT, int DIR>
+static unsigned launch_dir(int GP, const SweepArgs<FT> &A, cudaStream_t s, long long *trace, bool dry)
+{
+	switch (GP) {
+	case 4: return launch_one<FT, DIR, 4>(A, s, trace, dry);
+	case 8: return launch_one<FT, DIR, 8>(A, s, trace, dry);
+	case 16: return launch_one<FT, DIR, 16>(A, s, trace, dry);
+	case 32: return launch_one<FT, DIR, 32>(A, s, trace, dry);
+	default: return launch_one<FT, DIR, 64>(A, s, trace, dry);
+	}
+}
 
 template <typename FT>
 bool launch_fast_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches)
 {
 	const Layout &L = A.L;
 	const int n = dir == 0 ? L.nx : dir == 1 ? L.ny : L.nz;
+	if (n < M) return false;                              // clamped row offsets need at least one full chunk
+	if (L.total >= (1ll << 31)) return false;
 	const int G = (n + M - 1) / M;
-	int GP = 1;
+	int GP = 4;                                           // at least one warp per CTA
 	while (GP < G) GP <<= 1;
-	if (GP * NL > 512) return false;                      // lines longer than 512 rows: caller falls back
-	if (GP * NL < 32) GP = 32 / NL;                       // at least one warp
-	const size_t smem = fast_smem_bytes<FT>(GP);
-	const int threads = GP * NL;
-	unsigned grid;
-	if (dir == 0) grid = (unsigned)L.ny * (unsigned)((L.nz + NL - 1) / NL);
-	else if (dir == 1) grid = (unsigned)L.nx * (unsigned)((L.nz + NL - 1) / NL);
-	else grid = (unsigned)L.nx * (unsigned)((L.ny + NL - 1) / NL);
-	static bool attr_set[2][3] = {};
-	const int fi = sizeof(FT) == 4 ? 0 : 1;
-	auto set_attr = [&](const void *fn) {
-		if (!attr_set[fi][dir]) {
-			cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes<FT>(64));
-			attr_set[fi][dir] = true;
-		}
-	};
-	switch (dir) {
-	case 0: set_attr((const void *)k_fast_sweep<FT, 0>); k_fast_sweep<FT, 0><<<grid, threads, smem, s>>>(A, G, GP); break;
-	case 1: set_attr((const void *)k_fast_sweep<FT, 1>); k_fast_sweep<FT, 1><<<grid, threads, smem, s>>>(A, G, GP); break;
-	default: set_attr((const void *)k_fast_sweep<FT, 2>); k_fast_sweep<FT, 2><<<grid, threads, smem, s>>>(A, G, GP); break;
+	if (GP > 64) return false;                            // lines longer than 512 rows: caller falls back
+	const unsigned grid = dir == 0 ? launch_dir<FT, 0>(GP, A, s, nullptr, true) : dir == 1 ? launch_dir<FT, 1>(GP, A, s, nullptr, true)
+	                                                                                       : launch_dir<FT, 2>(GP, A, s, nullptr, true);
+	// debug facility: CMC_TRACE=1 records clock64() at the phase boundaries of every CTA and prints the mean phase
+	// durations (cycles) per direction.  Never enabled in tests or benchmarks.
+	static const bool tracing = getenv("CMC_TRACE") != nullptr;
+	long long *trace = nullptr;
+	if (tracing) { cudaMalloc((void **)&trace, (size_t)grid * 16 * sizeof(long long)); cudaMemset(trace, 0, (size_t)grid * 16 * sizeof(long long)); }
+	if (dir == 0) launch_dir<FT, 0>(GP, A, s, trace, false);
+	else if (dir == 1) launch_dir<FT, 1>(GP, A, s, trace, false);
+	else launch_dir<FT, 2>(GP, A, s, trace, false);
+	if (tracing) {
+		cudaStreamSynchronize(s);
+		std::vector<long long> h((size_t)grid * 16);
+		cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+		cudaFree(trace);
+		double acc[7] = {};
+		for (unsigned b = 0; b < grid; b++) for (int k = 1; k < 7; k++) acc[k] += (double)(h[(size_t)b * 16 + k] - h[(size_t)b * 16 + k - 1]);
+		fprintf(stderr, "[cmc trace] dir %d grid %u threads %d: mean cycles per CTA  loadV+elim %.0f | pcrV %.0f | storeV %.0f | loadT+elim %.0f | pcrT %.0f | storeT %.0f | total %.0f\n",
+		        dir, grid, GP * lines_per_cta(GP), acc[1] / grid, acc[2] / grid, acc[3] / grid, acc[4] / grid, acc[5] / grid, acc[6] / grid,
+		        (acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6]) / grid);
 	}
 	if (launches) (*launches)++;
 	return true;
@@ -524,46 +593,46 @@ bool launch_fast_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long lon
 template bool launch_fast_sweep<float>(int, const SweepArgs<float> &, cudaStream_t, long long *);
 template bool launch_fast_sweep<double>(int, const SweepArgs<double> &, cudaStream_t, long long *);
 
-// ---- standalone batched solver with the same partition + PCR machinery (unit tests) -------------------------
-// One CTA per NL systems; system-major host layout.
-template <typename FT>
-__global__ void __launch_bounds__(512, 1) k_pcr_batch(int nsys, int n, int GP, const FT *a, const FT *b, const FT *c, const FT *d, FT *x)
+// ---- standalone batched solver with the same partition + CR/PCR machinery (unit tests) --------------------------
+// One CTA per NLB systems; system-major host layout.
+template <typename FT, int GP>
+__global__ void __launch_bounds__(GP * NLB) k_pcr_batch(int nsys, int n, const FT *a, const FT *b, const FT *c, const FT *d, FT *x)
 {
+	constexpr int STR = GP * NLB;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	FT *sys = reinterpret_cast<FT *>(smem_raw);
-	FT *head = sys + 2 * 5 * GP * NL;
-	FT *sol = head + 5 * GP * NL;
+	FT *head = sys + 3 * 5 * STR;
+	FT *sol = head + 5 * STR;
 	const int t = threadIdx.x;
-	const int g = t % GP, l = t / GP;
-	const int sidx = blockIdx.x * NL + l;
+	const int l = t % NLB, g = t / NLB, e = t;
+	const int sidx = blockIdx.x * NLB + l;
 	const bool ok = sidx < nsys;
 	const size_t base = (size_t)(ok ? sidx : 0) * n;
-	const int r0 = g * M, e = g * NL + l, stride_s = GP * NL;
-	FT cp[M], lp[M], dp[M], b7 = FT(1);
+	const int r0 = g * M;
+	FT cp[M], lp[M], dp[M], b7 = FT(1), rr;
 #pragma unroll
 	for (int i = 0; i < M; i++) {
 		const int r = r0 + i;
 		FT ra = FT(0), rb = FT(1), rc = FT(0), rd = FT(0);
 		if (ok && r < n) { ra = r == 0 ? FT(0) : a[base + r]; rb = b[base + r]; rc = r == n - 1 ? FT(0) : c[base + r]; rd = d[base + r]; }
-		if (i == M - 1) { lp[i] = ra; cp[i] = rc; b7 = rb; dp[i] = rd; }
-		else if (i == 0) { const FT rr = rcp<FT>(rb); cp[0] = rc * rr; lp[0] = ra * rr; dp[0] = rd * rr; }
-		else { const FT rr = rcp<FT>(rb - ra * cp[i - 1]); cp[i] = rc * rr; lp[i] = -ra * lp[i - 1] * rr; dp[i] = (rd - ra * dp[i - 1]) * rr; }
+		CMC_ELIM_ROW(i, ra, rb, rc)
+		if (i == M - 1) dp[i] = rd;
+		else if (i == 0) dp[0] = rd * rr;
+		else dp[i] = (rd - ra * dp[i - 1]) * rr;
 	}
 	FT y0 = dp[M - 2], v0 = lp[M - 2], w0 = cp[M - 2];
 #pragma unroll
 	for (int i = M - 3; i >= 0; i--) { y0 = dp[i] - cp[i] * y0; v0 = lp[i] - cp[i] * v0; w0 = -cp[i] * w0; }
-	head[0 * stride_s + e] = y0; head[3 * stride_s + e] = v0; head[4 * stride_s + e] = w0;
+	head[0 * STR + e] = y0; head[3 * STR + e] = v0; head[4 * STR + e] = w0;
 	__syncthreads();
 	const bool has_next = g + 1 < GP;
-	const int en = e + NL;
-	const FT ny0 = has_next ? head[0 * stride_s + en] : FT(0), nv = has_next ? head[3 * stride_s + en] : FT(0), nw = has_next ? head[4 * stride_s + en] : FT(0);
+	const FT *hn = head + e + NLB;
+	const FT ny0 = has_next ? hn[0 * STR] : FT(0), nv = has_next ? hn[3 * STR] : FT(0), nw = has_next ? hn[4 * STR] : FT(0);
 	const FT a7 = lp[M - 1], c7 = cp[M - 1];
-	const FT rr = rcp<FT>(b7 - a7 * cp[M - 2] - c7 * nv);
+	rr = rcp<FT>(b7 - a7 * cp[M - 2] - c7 * nv);
 	FT Rd[1] = {(dp[M - 1] - a7 * dp[M - 2] - c7 * ny0) * rr}, E[1];
-	pcr_solve<FT, 1>(sys, GP, g, e, NL, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, E);
-	sol[e] = E[0];
-	__syncthreads();
-	const FT El = g > 0 ? sol[e - NL] : FT(0);
+	reduced_solve<FT, 1, GP, NLB, NLB>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, E);
+	const FT El = g > 0 ? sol[e - NLB] : FT(0);
 	FT xx[M];
 	xx[M - 1] = E[0];
 #pragma unroll
@@ -572,16 +641,28 @@ __global__ void __launch_bounds__(512, 1) k_pcr_batch(int nsys, int n, int GP, c
 	for (int i = 0; i < M; i++) if (ok && r0 + i < n) x[base + r0 + i] = xx[i];
 }
 
+template <typename FT, int GP>
+static void launch_batch_one(int nsys, int n, const FT *a, const FT *b, const FT *c, const FT *d, FT *x, cudaStream_t s)
+{
+	const size_t smem = fast_smem_bytes<FT>(GP, NLB);
+	cudaFuncSetAttribute((const void *)k_pcr_batch<FT, GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	k_pcr_batch<FT, GP><<<(nsys + NLB - 1) / NLB, GP * NLB, smem, s>>>(nsys, n, a, b, c, d, x);
+}
+
 template <typename FT>
 bool launch_pcr_batch(int nsys, int n, const FT *a, const FT *b, const FT *c, const FT *d, FT *x, cudaStream_t s)
 {
 	const int G = (n + M - 1) / M;
-	int GP = 1;
+	int GP = 4;
 	while (GP < G) GP <<= 1;
-	if (GP * NL > 512) return false;
-	if (GP * NL < 32) GP = 32 / NL;
-	cudaFuncSetAttribute((const void *)k_pcr_batch<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes<FT>(64));
-	k_pcr_batch<FT><<<(nsys + NL - 1) / NL, GP * NL, fast_smem_bytes<FT>(GP), s>>>(nsys, n, GP, a, b, c, d, x);
+	switch (GP) {
+	case 4: launch_batch_one<FT, 4>(nsys, n, a, b, c, d, x, s); break;
+	case 8: launch_batch_one<FT, 8>(nsys, n, a, b, c, d, x, s); break;
+	case 16: launch_batch_one<FT, 16>(nsys, n, a, b, c, d, x, s); break;
+	case 32: launch_batch_one<FT, 32>(nsys, n, a, b, c, d, x, s); break;
+	case 64: launch_batch_one<FT, 64>(nsys, n, a, b, c, d, x, s); break;
+	default: return false;
+	}
 	return true;
 }
 template bool launch_pcr_batch<float>(int, int, const float *, const float *, const float *, const float *, float *, cudaStream_t);
