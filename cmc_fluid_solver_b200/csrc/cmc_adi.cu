@@ -2,9 +2,16 @@
 //
 // Host-side restatement of AdiSolver3D::{Init, CreateSegments, UpdateBoundaries, TimeStep,
 // SolveDirection} (reference src/FluidSolver3D/AdiSolver3D.cpp:166-268, 286-391, 553-666) and
-// Solver3D::GetLayer (Solver3D.cpp:21-25) on top of the sm_100a kernels.  Everything is ordered on
-// ONE CUDA stream per handle; a time step does not synchronise with the host unless the caller
-// asks for the residual.  There is no CPU fallback anywhere in this file.
+// Solver3D::GetLayer (Solver3D.cpp:21-25) on top of the sm_100a kernels.
+//
+// A handle (Engine) owns one or more x-slabs of the grid (Slab: all device buffers of one slab):
+//   * single GPU            : one slab = the whole grid;
+//   * one process per GPU   : one slab per handle, neighbours reached through NCCL (dist.h);
+//   * emulated slabs        : N slabs of ONE device in one process, exchanging with device-to-device copies -
+//                             the same code path as the NCCL case, testable on a single GPU (the counterpart of
+//                             the reference's MGPU_EMU switch, src/Common/GPUplan.h:10-15).
+// The step logic is written once, in lockstep over the local slabs; every exchange is stream-ordered.  A time
+// step does not synchronise with the host unless the caller asks for the residual.  No CPU fallback anywhere.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -54,17 +61,16 @@ struct cmc_adi3d {
 	virtual int eval_div_error(int layer, double *err) = 0;
 
 	int device = 0, fp = 8;
-	int rank = 0, nranks = 1;
-	Layout L{}, G{};
+	int rank = 0, nranks = 1;       // position of this handle's (first) slab among all slabs of the grid
+	Layout L{}, G{};                // L: extent of the locally held planes [x0, x0 + nx); G: the whole grid
 	cudaStream_t stream = nullptr;
 	long long launches = 0;
 	long long dev_bytes = 0;
 	long long num_segs[3] = {0, 0, 0};
-	long long shared_free[3] = {0, 0, 0};   // cells shared by two segments with a BC_FREE row (fast solver falls back)
+	long long shared_free[3] = {0, 0, 0};   // cells shared by two segments with a BC_FREE row (informational)
 	int mode = CMC_MODE_FAST;
 	int fold_boundaries = 0;
 	bool have_nodes = false, have_lines = false;
-	DistContext *dist = nullptr;
 
 	// optional per-kernel-kind device timing (cmc_adi3d_set_option "profile"): CUDA event pairs on `stream`
 	int profile = 0;
@@ -102,44 +108,46 @@ namespace {
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// GPUplan::splitEven1D (reference GPUplan.cpp:122-141): dimx / n planes each, remainder spread over the first slabs
+static void split_even(int dimx, int n, int r, int &x0, int &nx)
+{
+	const int base = dimx / n, rem = dimx % n;
+	nx = base + (r < rem ? 1 : 0);
+	x0 = r * base + (r < rem ? r : rem);
+}
+
+// ---- one x-slab: every device buffer of the planes [x0, x0 + nx) ------------------------------------------------
 template <typename FT>
-struct Solver : cmc_adi3d {
-	FT *field[5][4] = {};        // physical buffers: four layers + the spare linearisation buffer
-	int slot[4] = {0, 1, 2, 3};  // logical layer (CMC_LAYER_*) -> physical buffer
+struct Slab {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	Layout L{}, G{};
+	int index = 0;                 // position among all slabs of the grid
+	FT *field[5][4] = {};          // physical buffers: four layers + the spare linearisation buffer
+	int slot[4] = {0, 1, 2, 3};    // logical layer (CMC_LAYER_*) -> physical buffer
 	int spare = 4;
 	FT *nodev[4] = {};
 	uint8_t *role[3] = {};
+	uint8_t *ncode = nullptr;      // whole-grid node codes (only until the line descriptors are built)
 	FT *cv = nullptr, *cT = nullptr;
-	double *d_partials = nullptr, *d_err2 = nullptr, *h_err2 = nullptr;
+	double *d_partials = nullptr, *d_err2 = nullptr;
 	unsigned long long *d_segcount = nullptr;
 	FT *d_outvel = nullptr;
 	double *d_outT = nullptr;
 	size_t out_cap = 0;
-	cmc_fluid_params params{};
-	double dx = 0, dy = 0, dz = 0;
-	double diffError = 0.0;
-	bool err_pending = false;
+	// partitioned x-sweep exchange buffers: [peer][16 | 8][lpo]
+	FT *xcoef_send = nullptr, *xcoef_recv = nullptr, *xbnd_send = nullptr, *xbnd_recv = nullptr;
+	long long bytes = 0;
 	static const int kMaxErrBlocks = 148 * 8;
 
-	~Solver() override
+	~Slab()
 	{
 		cudaSetDevice(device);
-		if (stream) cudaStreamSynchronize(stream);
-		spans_collect();
 		for (auto &l : field) for (auto &p : l) if (p) cudaFree(p);
 		for (auto &p : nodev) if (p) cudaFree(p);
 		for (auto &p : role) if (p) cudaFree(p);
-		if (cv) cudaFree(cv);
-		if (cT) cudaFree(cT);
-		if (d_partials) cudaFree(d_partials);
-		if (d_err2) cudaFree(d_err2);
-		if (h_err2) cudaFreeHost(h_err2);
-		if (d_segcount) cudaFree(d_segcount);
-		if (d_outvel) cudaFree(d_outvel);
-		if (d_outT) cudaFree(d_outT);
-		if (ncode) cudaFree(ncode);
-		if (dist) dist_destroy(dist);
-		if (stream) cudaStreamDestroy(stream);
+		void *misc[] = {cv, cT, d_partials, d_err2, d_segcount, d_outvel, d_outT, ncode, xcoef_send, xcoef_recv, xbnd_send, xbnd_recv};
+		for (void *p : misc) if (p) cudaFree(p);
 	}
 
 	template <typename T>
@@ -147,18 +155,13 @@ struct Solver : cmc_adi3d {
 	{
 		CU_TRY(cudaMalloc((void **)&p, count * sizeof(T)));
 		CU_TRY(cudaMemsetAsync(p, 0, count * sizeof(T), stream));
-		dev_bytes += (long long)(count * sizeof(T));
+		bytes += (long long)(count * sizeof(T));
 		return CMC_OK;
 	}
 
-	int init(const cmc_grid_desc *g, const cmc_fluid_params *p, int x0, int nx)
+	int init(const Layout &g, int x0, int nx, int dev, cudaStream_t s, int idx, int nslabs)
 	{
-		CU_TRY(cudaSetDevice(device));
-		CU_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-		params = *p;
-		dx = g->dx; dy = g->dy; dz = g->dz;
-		G.nx = g->dimx; G.ny = g->dimy; G.nz = g->dimz; G.gx = g->dimx; G.x0 = 0;
-		G.nzp = round_up(g->dimz, 16); G.plane = (long long)G.ny * G.nzp; G.total = (long long)(G.nx + 2) * G.plane;
+		device = dev; stream = s; G = g; index = idx;
 		L = G; L.nx = nx; L.x0 = x0; L.total = (long long)(nx + 2) * L.plane;
 		int rc;
 		for (int l = 0; l < 5; l++)
@@ -171,11 +174,17 @@ struct Solver : cmc_adi3d {
 		if ((rc = dalloc(d_partials, (size_t)2 * kMaxErrBlocks))) return rc;
 		if ((rc = dalloc(d_err2, 2))) return rc;
 		if ((rc = dalloc(d_segcount, 8))) return rc;
-		CU_TRY(cudaHostAlloc((void **)&h_err2, 2 * sizeof(double), cudaHostAllocDefault));
-		h_err2[0] = h_err2[1] = 0.0;
-		CU_TRY(cudaStreamSynchronize(stream));
+		if (nslabs > 1) {
+			const size_t lpo = lines_per_owner(nslabs);
+			if ((rc = dalloc(xcoef_send, lpo * 16 * nslabs))) return rc;
+			if ((rc = dalloc(xcoef_recv, lpo * 16 * nslabs))) return rc;
+			if ((rc = dalloc(xbnd_send, lpo * 8 * nslabs))) return rc;
+			if ((rc = dalloc(xbnd_recv, lpo * 8 * nslabs))) return rc;
+		}
 		return CMC_OK;
 	}
+
+	size_t lines_per_owner(int nslabs) const { return ((size_t)G.ny * G.nz + nslabs - 1) / nslabs; }
 
 	ConstLayerPtrs<FT> clayer(int logical) const
 	{
@@ -190,15 +199,138 @@ struct Solver : cmc_adi3d {
 		return r;
 	}
 
-	// dense host (global grid) <-> padded device slab
-	int upload_dense(FT *dst_field, const FT *src_global_dense)
+	// dense host (whole grid) -> padded device slab, plus the neighbour planes into the guard (halo) planes
+	int upload_nodes(const uint8_t *code, size_t N, const FT *const src[4])
 	{
-		const FT *src = src_global_dense + (size_t)L.x0 * L.ny * L.nz;
-		CU_TRY(cudaMemcpy2DAsync(dst_field + L.idx(0, 0, 0), sizeof(FT) * L.nzp, src, sizeof(FT) * L.nz,
-		                         sizeof(FT) * L.nz, (size_t)L.nx * L.ny, cudaMemcpyHostToDevice, stream));
+		if (ncode) { cudaFree(ncode); ncode = nullptr; }
+		CU_TRY(cudaMalloc((void **)&ncode, N));
+		CU_TRY(cudaMemcpyAsync(ncode, code, N, cudaMemcpyHostToDevice, stream));
+		const size_t rowb = sizeof(FT) * L.nz, pitch = sizeof(FT) * L.nzp, dense_plane = (size_t)L.ny * L.nz;
+		for (int q = 0; q < 4; q++) {
+			CU_TRY(cudaMemsetAsync(nodev[q], 0, sizeof(FT) * (size_t)L.total, stream));
+			const int p0 = L.x0 > 0 ? -1 : 0, p1 = L.x0 + L.nx < G.nx ? L.nx + 1 : L.nx;   // include the halo planes that exist
+			CU_TRY(cudaMemcpy2DAsync(nodev[q] + L.idx(p0, 0, 0), pitch, src[q] + (size_t)(L.x0 + p0) * dense_plane, rowb, rowb,
+			                         (size_t)(p1 - p0) * L.ny, cudaMemcpyHostToDevice, stream));
+		}
+		// cur = TimeLayer3D(grid) (TimeLayer3D.h:734-751); half/next/temp are uninitialised in the reference
+		// (TimeLayer3D.h:353) and are defined here as copies of cur (SURVEY N3/N5).
+		for (int l = 0; l < 5; l++)
+			for (int q = 0; q < 4; q++)
+				CU_TRY(cudaMemcpyAsync(field[l][q], nodev[q], sizeof(FT) * (size_t)L.total, cudaMemcpyDeviceToDevice, stream));
+		slot[0] = 0; slot[1] = 1; slot[2] = 2; slot[3] = 3; spare = 4;
+		return CMC_OK;
+	}
+};
+
+// ---- the handle ----------------------------------------------------------------------------------------------------
+template <typename FT>
+struct Engine : cmc_adi3d {
+	std::vector<Slab<FT> *> slabs;     // local slabs: 1 (single GPU / NCCL rank) or all of them (emulation)
+	NcclComm *nccl = nullptr;          // one process per GPU
+	int nslabs_total = 1;
+	cmc_fluid_params params{};
+	double dx = 0, dy = 0, dz = 0;
+	double diffError = 0.0;
+	bool err_pending = false;
+	double *h_err2 = nullptr;          // pinned: [2 * nlocal] (sum, count) per local slab
+
+	~Engine() override
+	{
+		cudaSetDevice(device);
+		if (stream) cudaStreamSynchronize(stream);
+		spans_collect();
+		for (auto *s : slabs) delete s;
+		if (h_err2) cudaFreeHost(h_err2);
+		if (nccl) nccl_destroy(nccl);
+		if (stream) cudaStreamDestroy(stream);
+	}
+
+	bool multi() const { return nslabs_total > 1; }
+
+	int init(const cmc_grid_desc *g, const cmc_fluid_params *p, int first_slab, int nlocal, int ntotal)
+	{
+		CU_TRY(cudaSetDevice(device));
+		CU_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+		params = *p;
+		dx = g->dx; dy = g->dy; dz = g->dz;
+		G.nx = g->dimx; G.ny = g->dimy; G.nz = g->dimz; G.gx = g->dimx; G.x0 = 0;
+		G.nzp = round_up(g->dimz, 16); G.plane = (long long)G.ny * G.nzp; G.total = (long long)(G.nx + 2) * G.plane;
+		nslabs_total = ntotal; rank = first_slab; nranks = ntotal;
+		int lo = 0, hi = 0;
+		for (int i = 0; i < nlocal; i++) {
+			int x0, nx;
+			split_even(G.nx, ntotal, first_slab + i, x0, nx);
+			if (i == 0) lo = x0;
+			hi = x0 + nx;
+			auto *s = new (std::nothrow) Slab<FT>();
+			if (!s) return fail(CMC_ERR_INVALID, "out of host memory");
+			slabs.push_back(s);
+			int rc = s->init(G, x0, nx, device, stream, first_slab + i, ntotal);
+			if (rc) return rc;
+			dev_bytes += s->bytes;
+		}
+		L = G; L.x0 = lo; L.nx = hi - lo; L.total = (long long)(L.nx + 2) * L.plane;
+		CU_TRY(cudaHostAlloc((void **)&h_err2, 2 * sizeof(double) * nlocal, cudaHostAllocDefault));
+		memset(h_err2, 0, 2 * sizeof(double) * nlocal);
+		CU_TRY(cudaStreamSynchronize(stream));
 		return CMC_OK;
 	}
 
+	// ------------------------------------------------------------------------------------------- exchanges
+	// boundary x-planes of the 4 fields of one logical layer -> the neighbours' guard planes
+	int halo_exchange(int logical)
+	{
+		if (!multi()) return CMC_OK;
+		span_begin(CMC_TIMING_COMM);
+		const size_t pb = sizeof(FT) * (size_t)G.plane;
+		if (nccl) {
+			Slab<FT> *s = slabs[0];
+			P2P ops[16]; int n = 0;
+			for (int q = 0; q < 4; q++) {
+				FT *f = s->field[s->slot[logical]][q];
+				if (rank > 0) ops[n++] = P2P{f + s->L.idx(0, 0, 0), f + s->L.idx(-1, 0, 0), pb, rank - 1};
+				if (rank + 1 < nranks) ops[n++] = P2P{f + s->L.idx(s->L.nx - 1, 0, 0), f + s->L.idx(s->L.nx, 0, 0), pb, rank + 1};
+			}
+			if (nccl_exchange(nccl, ops, n, stream)) return fail(CMC_ERR_COMM, nccl_error());
+			launches += 1;
+		} else {
+			for (size_t i = 0; i + 1 < slabs.size(); i++) {
+				Slab<FT> *a = slabs[i], *b = slabs[i + 1];
+				for (int q = 0; q < 4; q++) {
+					FT *fa = a->field[a->slot[logical]][q], *fb = b->field[b->slot[logical]][q];
+					CU_TRY(cudaMemcpyAsync(fb + b->L.idx(-1, 0, 0), fa + a->L.idx(a->L.nx - 1, 0, 0), pb, cudaMemcpyDeviceToDevice, stream));
+					CU_TRY(cudaMemcpyAsync(fa + a->L.idx(a->L.nx, 0, 0), fb + b->L.idx(0, 0, 0), pb, cudaMemcpyDeviceToDevice, stream));
+				}
+			}
+		}
+		span_end();
+		return CMC_OK;
+	}
+
+	// all-to-all of per-peer blocks: block p of `send` goes to slab p, which stores it as block <sender> of `recv`
+	int all_to_all(FT *Slab<FT>::*send, FT *Slab<FT>::*recv, size_t block_elems)
+	{
+		span_begin(CMC_TIMING_COMM);
+		const size_t bb = sizeof(FT) * block_elems;
+		if (nccl) {
+			Slab<FT> *s = slabs[0];
+			std::vector<P2P> ops;
+			for (int p = 0; p < nranks; p++) {
+				if (p == rank) { CU_TRY(cudaMemcpyAsync((s->*recv) + p * block_elems, (s->*send) + p * block_elems, bb, cudaMemcpyDeviceToDevice, stream)); continue; }
+				ops.push_back(P2P{(s->*send) + p * block_elems, (s->*recv) + p * block_elems, bb, p});
+			}
+			if (nccl_exchange(nccl, ops.data(), (int)ops.size(), stream)) return fail(CMC_ERR_COMM, nccl_error());
+			launches += 1;
+		} else {
+			for (size_t i = 0; i < slabs.size(); i++)
+				for (size_t j = 0; j < slabs.size(); j++)
+					CU_TRY(cudaMemcpyAsync((slabs[j]->*recv) + i * block_elems, (slabs[i]->*send) + j * block_elems, bb, cudaMemcpyDeviceToDevice, stream));
+		}
+		span_end();
+		return CMC_OK;
+	}
+
+	// ------------------------------------------------------------------------------------------- set up
 	int set_nodes(const int32_t *type, const int32_t *bc_vel, const int32_t *bc_temp,
 	              const void *vx, const void *vy, const void *vz, const void *T, size_t aos_stride) override
 	{
@@ -207,7 +339,6 @@ struct Solver : cmc_adi3d {
 		std::vector<uint8_t> code(N);
 		std::vector<FT> tmp[4];
 		const FT *src[4] = {(const FT *)vx, (const FT *)vy, (const FT *)vz, (const FT *)T};
-		long long face_in = 0;
 		if (aos_stride) {
 			// reference Node (Grid3D.h:73-88): {int type; int bc_vel; int bc_temp; FTYPE v[3]; FTYPE T}
 			const char *base = (const char *)type;
@@ -225,62 +356,54 @@ struct Solver : cmc_adi3d {
 				code[id] = (uint8_t)((type[id] & 3) | (bc_vel[id] == CMC_BC_FREE ? 4 : 0) | (bc_temp[id] == CMC_BC_FREE ? 8 : 0));
 			}
 		}
-		// NODE_IN cells on a domain face make the reference read out of bounds (stencils, EvalDivError):
-		// the guard planes / line padding keep our accesses in bounds, values there are unspecified.
-		for (int i = 0; i < G.nx; i++)
-			for (int j = 0; j < G.ny; j++)
-				for (int k = 0; k < G.nz; k++)
-					if (i == 0 || j == 0 || k == 0 || i == G.nx - 1 || j == G.ny - 1 || k == G.nz - 1)
-						if ((code[((size_t)i * G.ny + j) * G.nz + k] & 3) == CMC_NODE_IN) face_in++;
-		(void)face_in;
-		if (ncode) { cudaFree(ncode); ncode = nullptr; }
-		CU_TRY(cudaMalloc((void **)&ncode, N));
-		CU_TRY(cudaMemcpyAsync(ncode, code.data(), N, cudaMemcpyHostToDevice, stream));
-		int rc;
-		for (int q = 0; q < 4; q++) {
-			CU_TRY(cudaMemsetAsync(nodev[q], 0, sizeof(FT) * (size_t)L.total, stream));
-			if ((rc = upload_dense(nodev[q], src[q]))) return rc;
+		for (auto *s : slabs) {
+			int rc = s->upload_nodes(code.data(), N, src);
+			if (rc) return rc;
 		}
-		// halo planes of the node values (neighbour slabs) so that layers start with valid halos
-		if (nranks > 1) {
-			for (int q = 0; q < 4; q++) {
-				if (L.x0 > 0)
-					CU_TRY(cudaMemcpy2DAsync(nodev[q] + L.idx(-1, 0, 0), sizeof(FT) * L.nzp, src[q] + (size_t)(L.x0 - 1) * L.ny * L.nz,
-					                         sizeof(FT) * L.nz, sizeof(FT) * L.nz, (size_t)L.ny, cudaMemcpyHostToDevice, stream));
-				if (L.x0 + L.nx < G.nx)
-					CU_TRY(cudaMemcpy2DAsync(nodev[q] + L.idx(L.nx, 0, 0), sizeof(FT) * L.nzp, src[q] + (size_t)(L.x0 + L.nx) * L.ny * L.nz,
-					                         sizeof(FT) * L.nz, sizeof(FT) * L.nz, (size_t)L.ny, cudaMemcpyHostToDevice, stream));
-			}
-		}
-		// cur = TimeLayer3D(grid) (TimeLayer3D.h:734-751); half/next/temp are uninitialised in the reference
-		// (TimeLayer3D.h:353) and are defined here as copies of cur (SURVEY N3/N5).
-		for (int l = 0; l < 5; l++)
-			for (int q = 0; q < 4; q++)
-				CU_TRY(cudaMemcpyAsync(field[l][q], nodev[q], sizeof(FT) * (size_t)L.total, cudaMemcpyDeviceToDevice, stream));
-		slot[0] = 0; slot[1] = 1; slot[2] = 2; slot[3] = 3; spare = 4;
 		CU_TRY(cudaStreamSynchronize(stream));
 		have_nodes = true; have_lines = false;
 		diffError = 0.0; err_pending = false;
 		return CMC_OK;
 	}
-	uint8_t *ncode = nullptr;
 
 	int build_lines() override
 	{
 		if (!have_nodes) return fail(CMC_ERR_INVALID, "build_lines: call cmc_adi3d_set_nodes first");
 		CU_TRY(cudaSetDevice(device));
-		CU_TRY(cudaMemsetAsync(d_segcount, 0, 8 * sizeof(unsigned long long), stream));
-		for (int d = 0; d < 3; d++) CU_TRY(cudaMemsetAsync(role[d], 0, (size_t)L.total, stream));
-		launch_role_type_bits(G, ncode, L, role[0], role[1], role[2], stream, &launches);
-		for (int d = 0; d < 3; d++) launch_build_roles(d, G, ncode, L, role[d], d_segcount + d, stream, &launches);
-		unsigned long long h[8];
-		CU_TRY(cudaMemcpyAsync(h, d_segcount, sizeof h, cudaMemcpyDeviceToHost, stream));
-		CU_TRY(cudaStreamSynchronize(stream));
-		CU_TRY(cudaGetLastError());
-		for (int d = 0; d < 3; d++) { num_segs[d] = (long long)h[d]; shared_free[d] = (long long)h[4 + d]; }
-		if (nranks > 1 && dist) {
-			int rc = dist_sum_i64(dist, &num_segs[1], 2, stream);   // Y/Z counted per slab, X counted globally
-			if (rc) return fail(CMC_ERR_COMM, dist_error());
+		for (int d = 0; d < 3; d++) { num_segs[d] = 0; shared_free[d] = 0; }
+		for (auto *s : slabs) {
+			CU_TRY(cudaMemsetAsync(s->d_segcount, 0, 8 * sizeof(unsigned long long), stream));
+			for (int d = 0; d < 3; d++) CU_TRY(cudaMemsetAsync(s->role[d], 0, (size_t)s->L.total, stream));
+			launch_role_type_bits(G, s->ncode, s->L, s->role[0], s->role[1], s->role[2], stream, &launches);
+			for (int d = 0; d < 3; d++) launch_build_roles(d, G, s->ncode, s->L, s->role[d], s->d_segcount + d, stream, &launches);
+			unsigned long long h[8];
+			CU_TRY(cudaMemcpyAsync(h, s->d_segcount, sizeof h, cudaMemcpyDeviceToHost, stream));
+			CU_TRY(cudaStreamSynchronize(stream));
+			CU_TRY(cudaGetLastError());
+			// x-lines are scanned over the whole grid by every slab (same count everywhere); y/z-lines per slab
+			num_segs[0] = (long long)h[0]; shared_free[0] = (long long)h[4];
+			for (int d = 1; d < 3; d++) { num_segs[d] += (long long)h[d]; shared_free[d] += (long long)h[4 + d]; }
+			cudaFree(s->ncode); s->ncode = nullptr;          // the descriptors carry everything from here on
+		}
+		if (nccl) {      // y / z counts of the other ranks
+			double *tmp = slabs[0]->d_err2;
+			double v[2] = {(double)num_segs[1], (double)num_segs[2]}, w[2] = {(double)shared_free[1], (double)shared_free[2]};
+			for (int pass = 0; pass < 2; pass++) {
+				double *hv = pass == 0 ? v : w;
+				CU_TRY(cudaMemcpyAsync(tmp, hv, 2 * sizeof(double), cudaMemcpyHostToDevice, stream));
+				if (nccl_allreduce_sum_f64(nccl, tmp, 2, stream)) return fail(CMC_ERR_COMM, nccl_error());
+				CU_TRY(cudaMemcpyAsync(hv, tmp, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+				CU_TRY(cudaStreamSynchronize(stream));
+			}
+			num_segs[1] = (long long)v[0]; num_segs[2] = (long long)v[1];
+			shared_free[1] = (long long)w[0]; shared_free[2] = (long long)w[1];
+		}
+		if (multi()) {
+			for (auto *s : slabs)
+				if (s->L.nx % 8 != 0 || s->L.nx > 512 || s->L.nx < 8)
+					return fail(CMC_ERR_UNSUPPORTED, "slab-decomposed runs need 8 <= planes per slab <= 512 and a multiple of 8");
+			if (!fast_sweep_supported(slabs[0]->L, 1) || !fast_sweep_supported(slabs[0]->L, 2))
+				return fail(CMC_ERR_UNSUPPORTED, "slab-decomposed runs need 8 <= dimy, dimz <= 512");
 		}
 		have_lines = true;
 		return CMC_OK;
@@ -290,101 +413,139 @@ struct Solver : cmc_adi3d {
 	{
 		if (!have_lines) return fail(CMC_ERR_INVALID, "update_boundaries: call cmc_adi3d_build_lines first");
 		CU_TRY(cudaSetDevice(device));
-		ConstLayerPtrs<FT> nv; for (int q = 0; q < 4; q++) nv.f[q] = nodev[q];
 		span_begin(CMC_TIMING_BOUNDARY);
-		launch_update_boundaries<FT>(L, role[2], nv, layer(CMC_LAYER_CUR), stream, &launches);
+		for (auto *s : slabs) {
+			ConstLayerPtrs<FT> nv; for (int q = 0; q < 4; q++) nv.f[q] = s->nodev[q];
+			launch_update_boundaries<FT>(s->L, s->role[2], nv, s->layer(CMC_LAYER_CUR), stream, &launches);
+		}
 		span_end();
 		return CMC_OK;
 	}
 
-	SweepArgs<FT> sweep_args(int dir, FT dt, int cur_layer, int next_layer)
+	// ------------------------------------------------------------------------------------------- sweeps
+	SweepArgs<FT> sweep_args(Slab<FT> *s, int dir, FT dt, int cur_layer, int next_layer)
 	{
 		SweepArgs<FT> A;
-		A.L = L; A.dt = dt;
+		A.L = s->L; A.dt = dt;
 		A.h[0] = (FT)dx; A.h[1] = (FT)dy; A.h[2] = (FT)dz;
 		A.v_T = (FT)params.v_T; A.v_vis = (FT)params.v_vis; A.t_vis = (FT)params.t_vis; A.t_phi = (FT)params.t_phi;
-		A.role = role[dir];
+		A.role = s->role[dir];
 		for (int q = 0; q < 4; q++) {
-			A.cur[q] = field[slot[cur_layer]][q];
-			A.temp[q] = field[slot[CMC_LAYER_TEMP]][q];
-			A.next[q] = field[slot[next_layer]][q];
-			A.temp_out[q] = field[spare][q];
-			A.nodev[q] = nodev[q];
+			A.cur[q] = s->field[s->slot[cur_layer]][q];
+			A.temp[q] = s->field[s->slot[CMC_LAYER_TEMP]][q];
+			A.next[q] = s->field[s->slot[next_layer]][q];
+			A.temp_out[q] = s->field[s->spare][q];
+			A.nodev[q] = s->nodev[q];
 		}
-		A.cv = cv; A.cT = cT;
+		A.cv = s->cv; A.cT = s->cT;
+		A.xcoef = s->xcoef_send; A.xbnd = s->xbnd_recv; A.lpo = (int)s->lines_per_owner(nslabs_total);
+		A.extra_merge = 0;
 		return A;
 	}
 
+	bool fast_ok(int dir) const { return mode == CMC_MODE_FAST && fast_sweep_supported(slabs[0]->L, dir); }
+
 	// AdiSolver3D::SolveDirection (AdiSolver3D.cpp:564-666): num_local x { solve every line for u,v,w,T ; merge }
-	int solve_direction_impl(int dir, FT dt, int nl, int cur_layer, int next_layer)
+	// temp_is_cur: the linearisation layer still equals `cur` (first sweep of a step; the temp<-cur copy is folded
+	// away).  fold_post_merge: the last local iteration also applies the post-X MergeLayerTo (AdiSolver3D.cpp:354).
+	int solve_direction_impl(int dir, FT dt, int nl, int cur_layer, int next_layer, bool temp_is_cur = false, bool fold_post_merge = false)
 	{
 		for (int it = 0; it < nl; it++) {
-			if (nranks > 1) {
-				int rc = dist_halo_exchange<FT>(dist, L, field[slot[CMC_LAYER_TEMP]], stream, &launches);
-				if (rc) return fail(CMC_ERR_COMM, dist_error());
-			}
-			SweepArgs<FT> A = sweep_args(dir, dt, cur_layer, next_layer);
-			bool done = false;
-			if (nranks > 1 && dir == CMC_DIR_X) {
-				int rc = dist_sweep_x<FT>(dist, A, stream, &launches);
-				if (rc) return fail(CMC_ERR_COMM, dist_error());
-				std::swap(slot[CMC_LAYER_TEMP], spare);
-				done = true;
-			}
-			if (!done && mode == CMC_MODE_FAST && shared_free[dir] == 0) {
-				span_begin(CMC_TIMING_SWEEP_X + dir);
-				done = launch_fast_sweep<FT>(dir, A, stream, &launches);
+			const bool t_is_c = temp_is_cur && it == 0;
+			int rc = halo_exchange(t_is_c ? CMC_LAYER_CUR : CMC_LAYER_TEMP);   // x-stencils of the sweep read the neighbours' planes
+			if (rc) return rc;
+			const bool coupled = multi() && dir == CMC_DIR_X;
+			if (multi() && mode != CMC_MODE_FAST)
+				return fail(CMC_ERR_UNSUPPORTED, "slab-decomposed runs support CMC_MODE_FAST only");
+			if (coupled) {
+				// partitioned solve along the decomposed axis: spike pass -> all-to-all -> interface solve ->
+				// all-to-all -> coupled sweep.  (replaces LaunchSolveSegments_X, AdiSolver3D.cu:524-640)
+				span_begin(CMC_TIMING_SWEEP_X);
+				for (auto *s : slabs) {
+					SweepArgs<FT> A = sweep_args(s, dir, dt, cur_layer, next_layer);
+					if (!launch_x_spike<FT>(A, stream, &launches)) return fail(CMC_ERR_UNSUPPORTED, "x-spike pass: unsupported slab shape");
+				}
 				span_end();
-				if (done) std::swap(slot[CMC_LAYER_TEMP], spare);      // merged temp went to the other buffer
-				else if (profile) spans.pop_back();
-			}
-			if (!done) {
-				span_begin(CMC_TIMING_SWEEP_X + dir);
-				launch_exact_sweep<FT>(dir, A, stream, &launches);
+				const size_t lpo = slabs[0]->lines_per_owner(nslabs_total);
+				if ((rc = all_to_all(&Slab<FT>::xcoef_send, &Slab<FT>::xcoef_recv, lpo * 16))) return rc;
+				span_begin(CMC_TIMING_SWEEP_X);
+				const long long nlines = (long long)G.ny * G.nz;
+				for (auto *s : slabs) {
+					const long long first = (long long)s->index * (long long)lpo;
+					const int owned = (int)std::max(0ll, std::min((long long)lpo, nlines - first));
+					launch_x_interface<FT>(nslabs_total, (int)lpo, owned, s->xcoef_recv, s->xbnd_send, stream, &launches);
+				}
 				span_end();
-				span_begin(CMC_TIMING_MERGE);
-				launch_merge<FT>(L, role[dir], clayer(next_layer), layer(CMC_LAYER_TEMP), stream, &launches);
-				span_end();
+				if ((rc = all_to_all(&Slab<FT>::xbnd_send, &Slab<FT>::xbnd_recv, lpo * 8))) return rc;
 			}
+			span_begin(CMC_TIMING_SWEEP_X + dir);
+			for (auto *s : slabs) {
+				SweepArgs<FT> A = sweep_args(s, dir, dt, cur_layer, next_layer);
+				if (t_is_c)
+					for (int q = 0; q < 4; q++) A.temp[q] = s->field[s->slot[CMC_LAYER_CUR]][q];
+				A.extra_merge = (fold_post_merge && it == nl - 1) ? 1 : 0;
+				bool done = false;
+				if (coupled) {
+					if (!launch_x_coupled<FT>(A, stream, &launches)) return fail(CMC_ERR_UNSUPPORTED, "coupled x-sweep: unsupported slab shape");
+					done = true;
+				} else if (fast_ok(dir)) {
+					done = launch_fast_sweep<FT>(dir, A, stream, &launches);
+				}
+				if (done) std::swap(s->slot[CMC_LAYER_TEMP], s->spare);      // merged temp went to the other buffer
+				else {
+					launch_exact_sweep<FT>(dir, A, stream, &launches);
+					launch_merge<FT>(s->L, s->role[dir], s->clayer(next_layer), s->layer(CMC_LAYER_TEMP), stream, &launches);
+				}
+			}
+			span_end();
 		}
 		return CMC_OK;
 	}
 
-	int step_prologue() override
+	int step_prologue() override { return step_prologue_impl(true); }
+
+	int step_prologue_impl(bool copy_temp)
 	{
 		if (!have_lines) return fail(CMC_ERR_INVALID, "time_step: call cmc_adi3d_build_lines first");
 		CU_TRY(cudaSetDevice(device));
 		// cur -> next on BOUND and VALVE cells (AdiSolver3D.cpp:310-311); temp <- cur (:320)
 		span_begin(CMC_TIMING_COPY);
-		launch_copy_masked<FT>(L, role[2], R_BV, clayer(CMC_LAYER_CUR), layer(CMC_LAYER_NEXT), stream, &launches);
-		launch_copy_full<FT>(L, clayer(CMC_LAYER_CUR), layer(CMC_LAYER_TEMP), stream, &launches);
+		for (auto *s : slabs) {
+			launch_copy_masked<FT>(s->L, s->role[2], R_BV, s->clayer(CMC_LAYER_CUR), s->layer(CMC_LAYER_NEXT), stream, &launches);
+			if (copy_temp) launch_copy_full<FT>(s->L, s->clayer(CMC_LAYER_CUR), s->layer(CMC_LAYER_TEMP), stream, &launches);
+		}
 		span_end();
 		return CMC_OK;
 	}
 
 	int enqueue_div_error(int logical_layer)
 	{
-		if (nranks > 1) {
-			int rc = dist_halo_exchange<FT>(dist, L, field[slot[logical_layer]], stream, &launches);
-			if (rc) return fail(CMC_ERR_COMM, dist_error());
+		int rc = halo_exchange(logical_layer);       // the residual reads the i-1 plane (TimeLayer3D.h:614-621)
+		if (rc) return rc;
+		for (size_t i = 0; i < slabs.size(); i++) {
+			Slab<FT> *s = slabs[i];
+			const int l = s->slot[logical_layer];
+			launch_div_error<FT>(s->L, s->role[2], s->field[l][0], s->field[l][1], s->field[l][2], (FT)dx, (FT)dy, (FT)dz,
+			                     s->d_partials, Slab<FT>::kMaxErrBlocks, s->d_err2, stream, &launches);
+			if (nccl && nccl_allreduce_sum_f64(nccl, s->d_err2, 2, stream)) return fail(CMC_ERR_COMM, nccl_error());
+			CU_TRY(cudaMemcpyAsync(h_err2 + 2 * i, s->d_err2, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
 		}
-		const int l = slot[logical_layer];
-		launch_div_error<FT>(L, role[2], field[l][0], field[l][1], field[l][2], (FT)dx, (FT)dy, (FT)dz,
-		                     d_partials, kMaxErrBlocks, d_err2, stream, &launches);
-		if (nranks > 1) {
-			int rc = dist_allreduce_f64(dist, d_err2, 2, stream);
-			if (rc) return fail(CMC_ERR_COMM, dist_error());
-		}
-		CU_TRY(cudaMemcpyAsync(h_err2, d_err2, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
 		err_pending = true;
 		return CMC_OK;
+	}
+
+	double err_from_host() const
+	{
+		double e = 0.0, c = 0.0;
+		for (size_t i = 0; i < slabs.size(); i++) { e += h_err2[2 * i]; c += h_err2[2 * i + 1]; }
+		return e / c;           // err / count (TimeLayer3D.h:639); 0/0 = NaN like the reference
 	}
 
 	int fetch_error()
 	{
 		if (err_pending) {
 			CU_TRY(cudaStreamSynchronize(stream));
-			diffError = h_err2[0] / h_err2[1];      // err / count (TimeLayer3D.h:639); 0/0 = NaN like the reference
+			diffError = err_from_host();
 			err_pending = false;
 		}
 		return CMC_OK;
@@ -396,15 +557,23 @@ struct Solver : cmc_adi3d {
 		int rc;
 		if (ng < 0 || nl < 0) return fail(CMC_ERR_INVALID, "time_step: negative iteration count");
 		const FT dt = (FT)dt_in;                                   // FluidSolver3D.cpp:242 casts to FTYPE
-		if ((rc = step_prologue())) return rc;
+		// fast mode folds two full-field passes into the sweeps (identical arithmetic, fewer HBM round trips):
+		//  * temp <- cur (:320): the first Z sweep reads `cur` as its linearisation layer;
+		//  * the post-X MergeLayerTo (:354): the last X sweep of a global iteration relaxes twice.
+		const bool fold_copy = ng > 0 && nl > 0 && fast_ok(CMC_DIR_Z);
+		const bool fold_merge = nl > 0 && (multi() || fast_ok(CMC_DIR_X));
+		if ((rc = step_prologue_impl(!fold_copy))) return rc;
 		for (int it = 0; it < ng; it++) {                          // :335-358
-			if ((rc = solve_direction_impl(CMC_DIR_Z, dt, nl, CMC_LAYER_CUR, CMC_LAYER_NEXT))) return rc;
+			if ((rc = solve_direction_impl(CMC_DIR_Z, dt, nl, CMC_LAYER_CUR, CMC_LAYER_NEXT, fold_copy && it == 0))) return rc;
 			if ((rc = solve_direction_impl(CMC_DIR_Y, dt, nl, CMC_LAYER_NEXT, CMC_LAYER_HALF))) return rc;
-			if ((rc = solve_direction_impl(CMC_DIR_X, dt, nl, CMC_LAYER_HALF, CMC_LAYER_NEXT))) return rc;
-			// update non-linear layer once more (:354): temp = (temp + next) / 2 on NODE_IN
-			span_begin(CMC_TIMING_MERGE);
-			launch_merge<FT>(L, role[2], clayer(CMC_LAYER_NEXT), layer(CMC_LAYER_TEMP), stream, &launches);
-			span_end();
+			if ((rc = solve_direction_impl(CMC_DIR_X, dt, nl, CMC_LAYER_HALF, CMC_LAYER_NEXT, false, fold_merge))) return rc;
+			if (!fold_merge) {
+				// update non-linear layer once more (:354): temp = (temp + next) / 2 on NODE_IN
+				span_begin(CMC_TIMING_MERGE);
+				for (auto *s : slabs)
+					launch_merge<FT>(s->L, s->role[2], s->clayer(CMC_LAYER_NEXT), s->layer(CMC_LAYER_TEMP), stream, &launches);
+				span_end();
+			}
 		}
 		if (ce) {
 			span_begin(CMC_TIMING_RESIDUAL);
@@ -422,7 +591,7 @@ struct Solver : cmc_adi3d {
 				return fail(CMC_ERR_DIVERGED, buf);
 			}
 		}
-		std::swap(slot[CMC_LAYER_CUR], slot[CMC_LAYER_NEXT]);      // :388-390
+		for (auto *s : slabs) std::swap(s->slot[CMC_LAYER_CUR], s->slot[CMC_LAYER_NEXT]);      // :388-390
 		return CMC_OK;
 	}
 
@@ -463,7 +632,7 @@ struct Solver : cmc_adi3d {
 		if (rc) return rc;
 		CU_TRY(cudaStreamSynchronize(stream));
 		err_pending = false;
-		if (err) *err = h_err2[0] / h_err2[1];
+		if (err) *err = err_from_host();
 		return CMC_OK;
 	}
 
@@ -476,48 +645,81 @@ struct Solver : cmc_adi3d {
 		if (oy == 0) oy = G.ny;
 		if (oz == 0) oz = G.nz;
 		if (ox < 0 || oy < 0 || oz < 0) return fail(CMC_ERR_INVALID, "get_layer: negative output dims");
+		const size_t outN = (size_t)ox * oy * oz, rowN = (size_t)oy * oz;
 		span_begin(CMC_TIMING_READBACK);
-		launch_clear_out<FT>(L, role[2], layer(CMC_LAYER_NEXT), (FT)CMC_MISSING_VALUE, stream, &launches);
-		// output rows i whose source plane x = i*dimx/outdimx lies in this slab
-		int oi0 = ox, oi1 = 0;
-		for (int i = 0; i < ox; i++) {
-			const int x = (int)((long long)i * G.nx / ox);
-			if (x >= L.x0 && x < L.x0 + L.nx) { if (i < oi0) oi0 = i; if (i + 1 > oi1) oi1 = i + 1; }
-		}
-		const size_t outN = (size_t)ox * oy * oz;
-		if (outN > out_cap) {
-			if (d_outvel) cudaFree(d_outvel);
-			if (d_outT) cudaFree(d_outT);
-			d_outvel = nullptr; d_outT = nullptr;
-			CU_TRY(cudaMalloc((void **)&d_outvel, outN * 3 * sizeof(FT)));
-			CU_TRY(cudaMalloc((void **)&d_outT, outN * sizeof(double)));
-			out_cap = outN;
-		}
-		launch_filter<FT>(L, clayer(CMC_LAYER_NEXT), ox, oy, oz, oi0, oi1, d_outvel, d_outT, stream, &launches);
-		span_end();
-		if (oi1 > oi0) {
-			const size_t o0 = (size_t)oi0 * oy * oz, cnt = (size_t)(oi1 - oi0) * oy * oz;
-			if (nranks == 1 || rank == 0) {
-				CU_TRY(cudaMemcpyAsync((FT *)vel + 3 * o0, d_outvel + 3 * o0, cnt * 3 * sizeof(FT), cudaMemcpyDeviceToHost, stream));
-				CU_TRY(cudaMemcpyAsync(T + o0, d_outT + o0, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+		std::vector<int> lo(nslabs_total, ox), hi(nslabs_total, 0);
+		// output rows i whose source plane x = i*dimx/outdimx lies in slab r (TimeLayer3D.h:842-854)
+		for (int r = 0; r < nslabs_total; r++) {
+			int x0, nx;
+			split_even(G.nx, nslabs_total, r, x0, nx);
+			for (int i = 0; i < ox; i++) {
+				const int x = (int)((long long)i * G.nx / ox);
+				if (x >= x0 && x < x0 + nx) { if (i < lo[r]) lo[r] = i; if (i + 1 > hi[r]) hi[r] = i + 1; }
 			}
 		}
-		if (nranks > 1) {
-			int rc = dist_gather_layer<FT>(dist, G, ox, oy, oz, d_outvel, d_outT, oi0, oi1, (FT *)vel, T, stream);
-			if (rc) return fail(CMC_ERR_COMM, dist_error());
+		for (auto *s : slabs) {
+			launch_clear_out<FT>(s->L, s->role[2], s->layer(CMC_LAYER_NEXT), (FT)CMC_MISSING_VALUE, stream, &launches);
+			const size_t need = (nccl && rank == 0) ? outN : (size_t)std::max(0, hi[s->index] - lo[s->index]) * rowN;
+			if (need > s->out_cap) {
+				if (s->d_outvel) cudaFree(s->d_outvel);
+				if (s->d_outT) cudaFree(s->d_outT);
+				s->d_outvel = nullptr; s->d_outT = nullptr;
+				CU_TRY(cudaMalloc((void **)&s->d_outvel, need * 3 * sizeof(FT)));
+				CU_TRY(cudaMalloc((void **)&s->d_outT, need * sizeof(double)));
+				s->out_cap = need;
+			}
+			// slab-local output buffer starts at output row lo (rank 0 of an NCCL run: at row 0, it also receives)
+			const int oi0 = lo[s->index], oi1 = hi[s->index];
+			const size_t shift = (nccl && rank == 0) ? 0 : (size_t)std::max(oi0, 0) * rowN;
+			if (oi1 > oi0)
+				launch_filter<FT>(s->L, s->clayer(CMC_LAYER_NEXT), ox, oy, oz, oi0, oi1, s->d_outvel - 3 * shift, s->d_outT - shift, stream, &launches);
+		}
+		span_end();
+		if (nccl) {
+			Slab<FT> *s = slabs[0];
+			std::vector<P2P> ops;
+			if (rank == 0) {
+				for (int r = 1; r < nranks; r++)
+					if (hi[r] > lo[r]) {
+						const size_t o0 = (size_t)lo[r] * rowN, cnt = (size_t)(hi[r] - lo[r]) * rowN;
+						ops.push_back(P2P{nullptr, s->d_outvel + 3 * o0, cnt * 3 * sizeof(FT), r});
+						ops.push_back(P2P{nullptr, s->d_outT + o0, cnt * sizeof(double), r});
+					}
+			} else if (hi[rank] > lo[rank]) {
+				const size_t cnt = (size_t)(hi[rank] - lo[rank]) * rowN;
+				ops.push_back(P2P{s->d_outvel, nullptr, cnt * 3 * sizeof(FT), 0});
+				ops.push_back(P2P{s->d_outT, nullptr, cnt * sizeof(double), 0});
+			}
+			if (!ops.empty() && nccl_exchange(nccl, ops.data(), (int)ops.size(), stream)) return fail(CMC_ERR_COMM, nccl_error());
+			if (rank == 0) {
+				CU_TRY(cudaMemcpyAsync(vel, s->d_outvel, outN * 3 * sizeof(FT), cudaMemcpyDeviceToHost, stream));
+				CU_TRY(cudaMemcpyAsync(T, s->d_outT, outN * sizeof(double), cudaMemcpyDeviceToHost, stream));
+			}
+		} else {
+			for (auto *s : slabs) {
+				const int oi0 = lo[s->index], oi1 = hi[s->index];
+				if (oi1 <= oi0) continue;
+				const size_t o0 = (size_t)oi0 * rowN, cnt = (size_t)(oi1 - oi0) * rowN;
+				CU_TRY(cudaMemcpyAsync((FT *)vel + 3 * o0, s->d_outvel, cnt * 3 * sizeof(FT), cudaMemcpyDeviceToHost, stream));
+				CU_TRY(cudaMemcpyAsync(T + o0, s->d_outT, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+			}
 		}
 		CU_TRY(cudaStreamSynchronize(stream));
 		CU_TRY(cudaGetLastError());
 		return CMC_OK;
 	}
 
+	// dense host copy of the locally held planes (all local slabs, in x order)
 	int read_field(int logical, int var, void *dst) override
 	{
 		if (logical < 0 || logical > 3 || var < 0 || var > 3) return fail(CMC_ERR_INVALID, "read_field: bad layer/var");
 		CU_TRY(cudaSetDevice(device));
-		const FT *src = field[slot[logical]][var] + L.idx(0, 0, 0);
-		CU_TRY(cudaMemcpy2DAsync(dst, sizeof(FT) * L.nz, src, sizeof(FT) * L.nzp, sizeof(FT) * L.nz, (size_t)L.nx * L.ny,
-		                         cudaMemcpyDeviceToHost, stream));
+		for (auto *s : slabs) {
+			const FT *src = s->field[s->slot[logical]][var] + s->L.idx(0, 0, 0);
+			FT *d = (FT *)dst + (size_t)(s->L.x0 - L.x0) * G.ny * G.nz;
+			CU_TRY(cudaMemcpy2DAsync(d, sizeof(FT) * G.nz, src, sizeof(FT) * G.nzp, sizeof(FT) * G.nz, (size_t)s->L.nx * G.ny,
+			                         cudaMemcpyDeviceToHost, stream));
+		}
 		CU_TRY(cudaStreamSynchronize(stream));
 		return CMC_OK;
 	}
@@ -526,9 +728,12 @@ struct Solver : cmc_adi3d {
 	{
 		if (logical < 0 || logical > 3 || var < 0 || var > 3) return fail(CMC_ERR_INVALID, "write_field: bad layer/var");
 		CU_TRY(cudaSetDevice(device));
-		FT *dst = field[slot[logical]][var] + L.idx(0, 0, 0);
-		CU_TRY(cudaMemcpy2DAsync(dst, sizeof(FT) * L.nzp, src, sizeof(FT) * L.nz, sizeof(FT) * L.nz, (size_t)L.nx * L.ny,
-		                         cudaMemcpyHostToDevice, stream));
+		for (auto *s : slabs) {
+			FT *dst = s->field[s->slot[logical]][var] + s->L.idx(0, 0, 0);
+			const FT *sp = (const FT *)src + (size_t)(s->L.x0 - L.x0) * G.ny * G.nz;
+			CU_TRY(cudaMemcpy2DAsync(dst, sizeof(FT) * G.nzp, sp, sizeof(FT) * G.nz, sizeof(FT) * G.nz, (size_t)s->L.nx * G.ny,
+			                         cudaMemcpyHostToDevice, stream));
+		}
 		CU_TRY(cudaStreamSynchronize(stream));
 		return CMC_OK;
 	}
@@ -548,44 +753,40 @@ static int check_device(int device)
 	return CMC_OK;
 }
 
+// first_slab / nlocal / ntotal: which slabs of the x-split this handle holds
 static int create_impl(const cmc_grid_desc *grid, const cmc_fluid_params *params, int fp_bytes, int device,
-                       int rank, int nranks, const void *nccl_id, cmc_adi3d **out)
+                       int first_slab, int nlocal, int ntotal, const void *nccl_id, cmc_adi3d **out)
 {
 	if (!grid || !params || !out) return fail(CMC_ERR_INVALID, "create: null argument");
 	*out = nullptr;
 	if (fp_bytes != 4 && fp_bytes != 8) return fail(CMC_ERR_INVALID, "create: fp_bytes must be 4 or 8");
 	if (grid->dimx < 3 || grid->dimy < 3 || grid->dimz < 3) return fail(CMC_ERR_INVALID, "create: every grid dimension must be >= 3");
 	if (!(grid->dx > 0) || !(grid->dy > 0) || !(grid->dz > 0)) return fail(CMC_ERR_INVALID, "create: grid spacing must be positive");
-	if (nranks < 1 || rank < 0 || rank >= nranks) return fail(CMC_ERR_INVALID, "create: bad rank / nranks");
-	if (nranks > grid->dimx) return fail(CMC_ERR_INVALID, "create: more ranks than x-planes");
+	if (ntotal < 1 || ntotal > 16 || first_slab < 0 || nlocal < 1 || first_slab + nlocal > ntotal) return fail(CMC_ERR_INVALID, "create: bad slab / rank count (1..16)");
+	if (ntotal > grid->dimx) return fail(CMC_ERR_INVALID, "create: more slabs than x-planes");
 	int rc = check_device(device);
 	if (rc) return rc;
-	// GPUplan::splitEven1D (reference GPUplan.cpp:122-141): dimx / n planes each, remainder spread over the first ranks
-	int x0 = 0, nx = grid->dimx;
-	if (nranks > 1) {
-		const int base = grid->dimx / nranks, rem = grid->dimx % nranks;
-		nx = base + (rank < rem ? 1 : 0);
-		x0 = rank * base + (rank < rem ? rank : rem);
-	}
 	cmc_adi3d *h = nullptr;
+	NcclComm *comm = nullptr;
+	if (nccl_id) {
+		cudaSetDevice(device);
+		comm = nccl_create(first_slab, ntotal, nccl_id);
+		if (!comm) return fail(CMC_ERR_COMM, nccl_error());
+	}
 	if (fp_bytes == 4) {
-		auto *s = new (std::nothrow) Solver<float>();
+		auto *s = new (std::nothrow) Engine<float>();
 		if (!s) return fail(CMC_ERR_INVALID, "out of host memory");
-		s->device = device; s->fp = 4; s->rank = rank; s->nranks = nranks;
-		rc = s->init(grid, params, x0, nx);
+		s->device = device; s->fp = 4; s->nccl = comm;
+		rc = s->init(grid, params, first_slab, nlocal, ntotal);
 		h = s;
 	} else {
-		auto *s = new (std::nothrow) Solver<double>();
+		auto *s = new (std::nothrow) Engine<double>();
 		if (!s) return fail(CMC_ERR_INVALID, "out of host memory");
-		s->device = device; s->fp = 8; s->rank = rank; s->nranks = nranks;
-		rc = s->init(grid, params, x0, nx);
+		s->device = device; s->fp = 8; s->nccl = comm;
+		rc = s->init(grid, params, first_slab, nlocal, ntotal);
 		h = s;
 	}
 	if (rc) { delete h; return rc; }
-	if (nranks > 1) {
-		h->dist = dist_create(device, rank, nranks, nccl_id, h->L, fp_bytes, h->stream);
-		if (!h->dist) { delete h; return fail(CMC_ERR_COMM, dist_error()); }
-	}
 	*out = h;
 	return CMC_OK;
 }
@@ -608,13 +809,19 @@ int cmc_device_count(void)
 
 int cmc_adi3d_create(const cmc_grid_desc *grid, const cmc_fluid_params *params, int fp_bytes, int device, cmc_adi3d **out)
 {
-	return create_impl(grid, params, fp_bytes, device, 0, 1, nullptr, out);
+	return create_impl(grid, params, fp_bytes, device, 0, 1, 1, nullptr, out);
+}
+
+int cmc_adi3d_create_emulated(const cmc_grid_desc *grid, const cmc_fluid_params *params, int fp_bytes, int device,
+                              int n_slabs, cmc_adi3d **out)
+{
+	return create_impl(grid, params, fp_bytes, device, 0, n_slabs, n_slabs, nullptr, out);
 }
 
 int cmc_nccl_unique_id(void *id128)
 {
 	if (!id128) return fail(CMC_ERR_INVALID, "null id");
-	if (dist_unique_id(id128)) return fail(CMC_ERR_COMM, dist_error());
+	if (nccl_unique_id(id128)) return fail(CMC_ERR_COMM, nccl_error());
 	return CMC_OK;
 }
 
@@ -622,7 +829,7 @@ int cmc_adi3d_create_dist(const cmc_grid_desc *grid, const cmc_fluid_params *par
                           int rank, int nranks, const void *nccl_unique_id, cmc_adi3d **out)
 {
 	if (nranks > 1 && !nccl_unique_id) return fail(CMC_ERR_INVALID, "create_dist: nccl_unique_id required when nranks > 1");
-	return create_impl(grid, params, fp_bytes, device, rank, nranks, nccl_unique_id, out);
+	return create_impl(grid, params, fp_bytes, device, rank, 1, nranks, nranks > 1 ? nccl_unique_id : nullptr, out);
 }
 
 int cmc_adi3d_destroy(cmc_adi3d *h)
@@ -687,7 +894,7 @@ int cmc_adi3d_sync(cmc_adi3d *h, double *err) { H_CHECK(h); return h->sync(err);
 int cmc_adi3d_get_layer(cmc_adi3d *h, void *vel, double *T, int ox, int oy, int oz)
 {
 	H_CHECK(h);
-	if ((h->nranks == 1 || h->rank == 0) && (!vel || !T)) return fail(CMC_ERR_INVALID, "get_layer: null output");
+	if (h->rank == 0 && (!vel || !T)) return fail(CMC_ERR_INVALID, "get_layer: null output");
 	return h->get_layer(vel, T, ox, oy, oz);
 }
 

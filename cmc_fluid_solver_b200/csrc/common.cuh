@@ -38,7 +38,9 @@ enum : unsigned {
 	R_TFREE = 16u,   // node.bc_temp == BC_FREE (selects the boundary row of T)
 	R_IN    = 32u,   // node.type == NODE_IN    (merge mask)
 	R_BV    = 64u,   // node.type is NODE_BOUND or NODE_VALVE (boundary refresh / copy mask)
-	R_OUT   = 128u,  // node.type == NODE_OUT   (GetLayer writes 99999 here)
+	R_PRE   = 128u,  // interior row whose NEXT cell is shared by two segments (ends this one, starts the next): the
+	                 // shared cell's ApplyBC1 row is folded into this row and R_VFREE / R_TFREE describe THAT cell
+	                 // (NODE_OUT = neither R_IN nor R_BV: GetLayer writes 99999 there)
 	R_SEG   = R_INT | R_START | R_END
 };
 
@@ -55,6 +57,11 @@ struct SweepArgs {
 	FT *temp_out[4];         // merged linearisation layer (fast mode, double-buffered)
 	const FT *nodev[4];      // Node.v.x, v.y, v.z, Node.T (boundary row values)
 	FT *cv, *cT;             // exact mode: Thomas c' scratch (velocity matrix, temperature matrix)
+	// partitioned x-sweep of a slab-decomposed grid (kernels_fast.cu MODE 1 / 2, dist.h)
+	FT *xcoef;               // MODE 1 output: [owner][16][lpo] coefficients of the slab's first / last row
+	const FT *xbnd;          // MODE 2 input:  [owner][8][lpo] solutions of the neighbours' adjacent rows
+	int lpo;                 // lines per owner rank of the interface solve
+	int extra_merge;         // fast mode: apply the relaxation twice (folds the post-X MergeLayerTo, AdiSolver3D.cpp:354)
 };
 
 // elementwise helpers -----------------------------------------------------------------------

@@ -1,0 +1,218 @@
+// fast_core.cuh - building blocks shared by the fast sweep kernels (kernels_fast.cu) and the distributed
+// x-sweep kernels (kernels_dist.cu): reciprocal, sweep constants, the CR+PCR reduced solver, chunk I/O.
+#pragma once
+#include "kernels.h"
+
+namespace cmc {
+
+constexpr int M = 8;          // rows per chunk
+constexpr int NLB = 8;        // systems per CTA of the standalone batch solver
+
+// Reciprocal without the IEEE division slow path: hardware seed + Newton steps (fp64: MUFU.RCP64H seed, two
+// fused Newton iterations -> < 1 ulp for the well-scaled pivots of a diagonally dominant system).
+template <typename FT> __device__ __forceinline__ FT rcp(FT x);
+template <> __device__ __forceinline__ float rcp<float>(float x) { return __frcp_rn(x); }
+template <> __device__ __forceinline__ double rcp<double>(double x)
+{
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+	double e = fma(-x, r, 1.0);
+	r = fma(r, e, r);
+	e = fma(-x, r, 1.0);
+	r = fma(r, e, r);
+	return r;
+}
+
+// Division-free constants of one sweep (fast mode multiplies by reciprocals; exact mode keeps the reference's
+// divisions, see rows.cuh).
+template <typename FT>
+struct FastConst {
+	FT inv2h;            // 1 / (2 h_D)
+	FT inv2h1, inv2h2;   // 1 / (2 h) of the two cross directions
+	FT vis_v, vis_T, b_v, b_T;
+	FT c3dt;             // 3 / dt
+	FT v_T, t_phi;
+	__host__ __device__ __forceinline__ void init(const SweepArgs<FT> &A, int dir)
+	{
+		const FT h = A.h[dir];
+		inv2h = FT(1) / (2 * h);
+		inv2h1 = FT(1) / (2 * A.h[dir == 0 ? 1 : 0]);
+		inv2h2 = FT(1) / (2 * A.h[dir == 2 ? 1 : 2]);
+		vis_v = A.v_vis / (h * h); vis_T = A.t_vis / (h * h);
+		c3dt = 3 / A.dt;
+		b_v = c3dt + 2 * vis_v; b_T = c3dt + 2 * vis_T;
+		v_T = A.v_T; t_phi = A.t_phi;
+	}
+};
+
+// ---- reduced systems of a CTA: cyclic reduction + PCR hybrid in shared memory ----------------------------------
+// One thread per reduced row (chunk g of a line), rows normalised (B == 1).  GP = chunks per line rounded up to a
+// power of two (rows >= G are identity rows).  e = shared-memory element of this row, GS = element distance of
+// neighbouring chunks of the same line.
+//   forward : L levels of cyclic reduction - at level l (stride s = 2^l) every second surviving row is eliminated:
+//             it publishes (A, C, D) once and keeps them in registers; its two neighbours absorb it;
+//   middle  : PCR over the GP / 2^L surviving rows (<= 8: three steps);
+//   backward: eliminated rows recover x from their two (already solved) neighbours.
+// The solutions of ALL rows end up in sol[q * STR + e].  Fully unrolled: GP, GS are compile-time.
+template <typename FT, int NRHS, int GP, int GS, int NL>
+__device__ __forceinline__ void reduced_solve(FT *sys, FT *sol, int g, int e, FT Ain, FT Cin, const FT (&Din)[NRHS], FT (&X)[NRHS])
+{
+	constexpr int NR = 2 + NRHS;
+	constexpr int STR = GP * NL;
+	constexpr int L = GP > 8 ? (GP == 16 ? 1 : GP == 32 ? 2 : 3) : 0;
+	FT A = Ain, Cc = Cin, D[NRHS];
+#pragma unroll
+	for (int q = 0; q < NRHS; q++) D[q] = Din[q];
+	FT *crs = sys;                       // CR publications: NR arrays (each row publishes once, at its own element)
+	FT *pp = sys + NR * STR;             // PCR ping-pong: 2 * NR arrays (only surviving rows used)
+	int my_level = -1;                   // level at which this row was eliminated (-1: survives into the PCR)
+#pragma unroll
+	for (int lv = 0; lv < L; lv++) {
+		const int s = 1 << lv;
+		const bool alive = (g & (s - 1)) == 0 && my_level < 0;
+		const bool odd = alive && ((g >> lv) & 1);
+		if (odd) {
+			my_level = lv;
+			crs[0 * STR + e] = A; crs[1 * STR + e] = Cc;
+#pragma unroll
+			for (int q = 0; q < NRHS; q++) crs[(2 + q) * STR + e] = D[q];
+		}
+		__syncthreads();
+		if (alive && !odd) {
+			const bool lo = g - s >= 0, hi = g + s < GP;
+			const FT *l = crs + e - s * GS, *h = crs + e + s * GS;
+			const FT Al = lo ? l[0 * STR] : FT(0), Cl = lo ? l[1 * STR] : FT(0);
+			const FT Ah = hi ? h[0 * STR] : FT(0), Ch = hi ? h[1 * STR] : FT(0);
+			const FT r = rcp<FT>(FT(1) - A * Cl - Cc * Ah);
+#pragma unroll
+			for (int q = 0; q < NRHS; q++) {
+				const FT Dl = lo ? l[(2 + q) * STR] : FT(0), Dh = hi ? h[(2 + q) * STR] : FT(0);
+				D[q] = (D[q] - A * Dl - Cc * Dh) * r;
+			}
+			A = -A * Al * r;
+			Cc = -Cc * Ch * r;
+		}
+	}
+	const bool survivor = my_level < 0 && (g & ((1 << L) - 1)) == 0;
+#pragma unroll
+	for (int st = 0; (1 << (L + st)) < GP; st++) {
+		const int s = 1 << (L + st);
+		FT *w = pp + (st & 1) * NR * STR;
+		if (survivor) {
+			w[0 * STR + e] = A; w[1 * STR + e] = Cc;
+#pragma unroll
+			for (int q = 0; q < NRHS; q++) w[(2 + q) * STR + e] = D[q];
+		}
+		__syncthreads();
+		if (survivor) {
+			const bool lo = g - s >= 0, hi = g + s < GP;
+			const FT *l = w + e - s * GS, *h = w + e + s * GS;
+			const FT Al = lo ? l[0 * STR] : FT(0), Cl = lo ? l[1 * STR] : FT(0);
+			const FT Ah = hi ? h[0 * STR] : FT(0), Ch = hi ? h[1 * STR] : FT(0);
+			const FT r = rcp<FT>(FT(1) - A * Cl - Cc * Ah);
+#pragma unroll
+			for (int q = 0; q < NRHS; q++) {
+				const FT Dl = lo ? l[(2 + q) * STR] : FT(0), Dh = hi ? h[(2 + q) * STR] : FT(0);
+				D[q] = (D[q] - A * Dl - Cc * Dh) * r;
+			}
+			A = -A * Al * r;
+			Cc = -Cc * Ch * r;
+		}
+	}
+	if (survivor) {
+#pragma unroll
+		for (int q = 0; q < NRHS; q++) sol[q * STR + e] = D[q];
+	}
+	__syncthreads();
+#pragma unroll
+	for (int lv = L - 1; lv >= 0; lv--) {
+		const int s = 1 << lv;
+		if (my_level == lv) {
+			const bool lo = g - s >= 0, hi = g + s < GP;
+#pragma unroll
+			for (int q = 0; q < NRHS; q++) {
+				const FT xl = lo ? sol[q * STR + e - s * GS] : FT(0), xh = hi ? sol[q * STR + e + s * GS] : FT(0);
+				D[q] = D[q] - A * xl - Cc * xh;
+				sol[q * STR + e] = D[q];
+			}
+		}
+		__syncthreads();
+	}
+#pragma unroll
+	for (int q = 0; q < NRHS; q++) X[q] = D[q];
+}
+
+// ---- line I/O: 8 consecutive rows of this thread's chunk ----------------------------------------------------
+// X / Y sweeps: rows are `stride` apart, lanes of a warp sit on neighbouring k (coalesced 64-byte segments);
+// off[i] = element offset of row i (clamped into the line, computed once and shared by all fields).
+// Z sweep: the 8 rows are 8 contiguous elements (64 bytes in fp64) -> 128-bit vector accesses at off[0].
+template <typename FT> struct Vec16;
+template <> struct Vec16<double> { typedef double2 type; static constexpr int N = 2; };
+template <> struct Vec16<float> { typedef float4 type; static constexpr int N = 4; };
+
+template <typename FT, int DIR>
+__device__ __forceinline__ void load8(const FT *__restrict__ p, const int (&off)[M], FT (&o)[M])
+{
+	if (DIR == 2) {
+		typedef typename Vec16<FT>::type V;
+		constexpr int N = Vec16<FT>::N;
+		const V *q = reinterpret_cast<const V *>(p + off[0]);        // 64-byte aligned: r0 % 8 == 0, lines 128-byte aligned
+#pragma unroll
+		for (int v = 0; v < M / N; v++) {
+			const V t = q[v];
+			const FT *e = reinterpret_cast<const FT *>(&t);
+#pragma unroll
+			for (int k = 0; k < N; k++) o[v * N + k] = e[k];
+		}
+	} else {
+#pragma unroll
+		for (int i = 0; i < M; i++) o[i] = p[off[i]];
+	}
+}
+
+// store rows whose bit is set in `mask` (Z: whole chunk with vector stores when all 8 bits are set)
+template <typename FT, int DIR>
+__device__ __forceinline__ void store8(FT *__restrict__ p, const int (&off)[M], unsigned mask, const FT (&v)[M])
+{
+	if (DIR == 2) {
+		if (mask == 0xffu) {
+			typedef typename Vec16<FT>::type V;
+			constexpr int N = Vec16<FT>::N;
+			V *q = reinterpret_cast<V *>(p + off[0]);
+#pragma unroll
+			for (int w = 0; w < M / N; w++) {
+				V t;
+				FT *e = reinterpret_cast<FT *>(&t);
+#pragma unroll
+				for (int k = 0; k < N; k++) e[k] = v[w * N + k];
+				q[w] = t;
+			}
+		} else {
+#pragma unroll
+			for (int i = 0; i < M; i++)
+				if (mask & (1u << i)) p[off[0] + i] = v[i];
+		}
+	} else {
+#pragma unroll
+		for (int i = 0; i < M; i++)
+			if (mask & (1u << i)) p[off[i]] = v[i];
+	}
+}
+
+// central difference along the line for the 8 rows of a chunk (lo / hi = rows r0-1 and r0+8)
+template <typename FT>
+__device__ __forceinline__ FT cdiff(const FT (&f)[M], FT lo, FT hi, int i, FT inv2h)
+{
+	const FT m = i == 0 ? lo : f[i == 0 ? 0 : i - 1], p = i == M - 1 ? hi : f[i == M - 1 ? M - 1 : i + 1];
+	return (p - m) * inv2h;
+}
+
+// One chunk: eliminate the 7 interior rows of (a, b, c | d[NRHS]) given row by row, keep the separator raw.
+// cp/lp/dp hold c', the left spike and d' of the interior rows; entry M-1 holds the raw separator (lp = a, cp = c).
+#define CMC_ELIM_ROW(i, a, b, c)                                                   \
+	if ((i) == M - 1) { lp[i] = (a); cp[i] = (c); b7 = (b); }                      \
+	else if ((i) == 0) { rr = rcp<FT>(b); cp[0] = (c) * rr; lp[0] = (a) * rr; }    \
+	else { rr = rcp<FT>((b) - (a) * cp[(i) - 1]); cp[i] = (c) * rr; lp[i] = -(a) * lp[(i) - 1] * rr; }
+
+
+} // namespace cmc

@@ -13,8 +13,16 @@ void launch_thomas_batch(int nsys, int n, FT *a, FT *b, FT *c, FT *d, FT *x, cud
 // ---- kernels_fast.cu -----------------------------------------------------------------------------
 // Returns false when the fast path does not support this line length (caller falls back to exact sweeps
 // + merge kernel - still on the GPU; there is no CPU path).
+bool fast_sweep_supported(const Layout &L, int dir);
 template <typename FT>
 bool launch_fast_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
+// partitioned x-sweep (slab-decomposed grid): spike pass, interface solve, coupled sweep
+template <typename FT>
+bool launch_x_spike(const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
+template <typename FT>
+bool launch_x_coupled(const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
+template <typename FT>
+void launch_x_interface(int P, int lpo, int nlines, const FT *coef, FT *bnd, cudaStream_t s, long long *launches);
 template <typename FT>
 bool launch_pcr_batch(int nsys, int n, const FT *a, const FT *b, const FT *c, const FT *d, FT *x, cudaStream_t s);
 

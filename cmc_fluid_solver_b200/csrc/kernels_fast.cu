@@ -27,229 +27,29 @@
 #include <cstdlib>
 #include <vector>
 #include "kernels.h"
+#include "fast_core.cuh"
 
 namespace cmc {
 
-constexpr int M = 8;          // rows per chunk
-constexpr int NLB = 8;        // systems per CTA of the standalone batch solver
-
-// Reciprocal without the IEEE division slow path: hardware seed + Newton steps (fp64: MUFU.RCP64H seed, two
-// fused Newton iterations -> < 1 ulp for the well-scaled pivots of a diagonally dominant system).
-template <typename FT> __device__ __forceinline__ FT rcp(FT x);
-template <> __device__ __forceinline__ float rcp<float>(float x) { return __frcp_rn(x); }
-template <> __device__ __forceinline__ double rcp<double>(double x)
-{
-	double r;
-	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-	double e = fma(-x, r, 1.0);
-	r = fma(r, e, r);
-	e = fma(-x, r, 1.0);
-	r = fma(r, e, r);
-	return r;
-}
-
-// Division-free constants of one sweep (fast mode multiplies by reciprocals; exact mode keeps the reference's
-// divisions, see rows.cuh).
-template <typename FT>
-struct FastConst {
-	FT inv2h;            // 1 / (2 h_D)
-	FT inv2h1, inv2h2;   // 1 / (2 h) of the two cross directions
-	FT vis_v, vis_T, b_v, b_T;
-	FT c3dt;             // 3 / dt
-	FT v_T, t_phi;
-	__host__ __device__ __forceinline__ void init(const SweepArgs<FT> &A, int dir)
-	{
-		const FT h = A.h[dir];
-		inv2h = FT(1) / (2 * h);
-		inv2h1 = FT(1) / (2 * A.h[dir == 0 ? 1 : 0]);
-		inv2h2 = FT(1) / (2 * A.h[dir == 2 ? 1 : 2]);
-		vis_v = A.v_vis / (h * h); vis_T = A.t_vis / (h * h);
-		c3dt = 3 / A.dt;
-		b_v = c3dt + 2 * vis_v; b_T = c3dt + 2 * vis_T;
-		v_T = A.v_T; t_phi = A.t_phi;
-	}
-};
-
-// ---- reduced systems of a CTA: cyclic reduction + PCR hybrid in shared memory ----------------------------------
-// One thread per reduced row (chunk g of a line), rows normalised (B == 1).  GP = chunks per line rounded up to a
-// power of two (rows >= G are identity rows).  e = shared-memory element of this row, GS = element distance of
-// neighbouring chunks of the same line.
-//   forward : L levels of cyclic reduction - at level l (stride s = 2^l) every second surviving row is eliminated:
-//             it publishes (A, C, D) once and keeps them in registers; its two neighbours absorb it;
-//   middle  : PCR over the GP / 2^L surviving rows (<= 8: three steps);
-//   backward: eliminated rows recover x from their two (already solved) neighbours.
-// The solutions of ALL rows end up in sol[q * STR + e].  Fully unrolled: GP, GS are compile-time.
-template <typename FT, int NRHS, int GP, int GS, int NL>
-__device__ __forceinline__ void reduced_solve(FT *sys, FT *sol, int g, int e, FT Ain, FT Cin, const FT (&Din)[NRHS], FT (&X)[NRHS])
-{
-	constexpr int NR = 2 + NRHS;
-	constexpr int STR = GP * NL;
-	constexpr int L = GP > 8 ? (GP == 16 ? 1 : GP == 32 ? 2 : 3) : 0;
-	FT A = Ain, Cc = Cin, D[NRHS];
-#pragma unroll
-	for (int q = 0; q < NRHS; q++) D[q] = Din[q];
-	FT *crs = sys;                       // CR publications: NR arrays (each row publishes once, at its own element)
-	FT *pp = sys + NR * STR;             // PCR ping-pong: 2 * NR arrays (only surviving rows used)
-	int my_level = -1;                   // level at which this row was eliminated (-1: survives into the PCR)
-#pragma unroll
-	for (int lv = 0; lv < L; lv++) {
-		const int s = 1 << lv;
-		const bool alive = (g & (s - 1)) == 0 && my_level < 0;
-		const bool odd = alive && ((g >> lv) & 1);
-		if (odd) {
-			my_level = lv;
-			crs[0 * STR + e] = A; crs[1 * STR + e] = Cc;
-#pragma unroll
-			for (int q = 0; q < NRHS; q++) crs[(2 + q) * STR + e] = D[q];
-		}
-		__syncthreads();
-		if (alive && !odd) {
-			const bool lo = g - s >= 0, hi = g + s < GP;
-			const FT *l = crs + e - s * GS, *h = crs + e + s * GS;
-			const FT Al = lo ? l[0 * STR] : FT(0), Cl = lo ? l[1 * STR] : FT(0);
-			const FT Ah = hi ? h[0 * STR] : FT(0), Ch = hi ? h[1 * STR] : FT(0);
-			const FT r = rcp<FT>(FT(1) - A * Cl - Cc * Ah);
-#pragma unroll
-			for (int q = 0; q < NRHS; q++) {
-				const FT Dl = lo ? l[(2 + q) * STR] : FT(0), Dh = hi ? h[(2 + q) * STR] : FT(0);
-				D[q] = (D[q] - A * Dl - Cc * Dh) * r;
-			}
-			A = -A * Al * r;
-			Cc = -Cc * Ch * r;
-		}
-	}
-	const bool survivor = my_level < 0 && (g & ((1 << L) - 1)) == 0;
-#pragma unroll
-	for (int st = 0; (1 << (L + st)) < GP; st++) {
-		const int s = 1 << (L + st);
-		FT *w = pp + (st & 1) * NR * STR;
-		if (survivor) {
-			w[0 * STR + e] = A; w[1 * STR + e] = Cc;
-#pragma unroll
-			for (int q = 0; q < NRHS; q++) w[(2 + q) * STR + e] = D[q];
-		}
-		__syncthreads();
-		if (survivor) {
-			const bool lo = g - s >= 0, hi = g + s < GP;
-			const FT *l = w + e - s * GS, *h = w + e + s * GS;
-			const FT Al = lo ? l[0 * STR] : FT(0), Cl = lo ? l[1 * STR] : FT(0);
-			const FT Ah = hi ? h[0 * STR] : FT(0), Ch = hi ? h[1 * STR] : FT(0);
-			const FT r = rcp<FT>(FT(1) - A * Cl - Cc * Ah);
-#pragma unroll
-			for (int q = 0; q < NRHS; q++) {
-				const FT Dl = lo ? l[(2 + q) * STR] : FT(0), Dh = hi ? h[(2 + q) * STR] : FT(0);
-				D[q] = (D[q] - A * Dl - Cc * Dh) * r;
-			}
-			A = -A * Al * r;
-			Cc = -Cc * Ch * r;
-		}
-	}
-	if (survivor) {
-#pragma unroll
-		for (int q = 0; q < NRHS; q++) sol[q * STR + e] = D[q];
-	}
-	__syncthreads();
-#pragma unroll
-	for (int lv = L - 1; lv >= 0; lv--) {
-		const int s = 1 << lv;
-		if (my_level == lv) {
-			const bool lo = g - s >= 0, hi = g + s < GP;
-#pragma unroll
-			for (int q = 0; q < NRHS; q++) {
-				const FT xl = lo ? sol[q * STR + e - s * GS] : FT(0), xh = hi ? sol[q * STR + e + s * GS] : FT(0);
-				D[q] = D[q] - A * xl - Cc * xh;
-				sol[q * STR + e] = D[q];
-			}
-		}
-		__syncthreads();
-	}
-#pragma unroll
-	for (int q = 0; q < NRHS; q++) X[q] = D[q];
-}
-
-// ---- line I/O: 8 consecutive rows of this thread's chunk ----------------------------------------------------
-// X / Y sweeps: rows are `stride` apart, lanes of a warp sit on neighbouring k (coalesced 64-byte segments);
-// off[i] = element offset of row i (clamped into the line, computed once and shared by all fields).
-// Z sweep: the 8 rows are 8 contiguous elements (64 bytes in fp64) -> 128-bit vector accesses at off[0].
-template <typename FT> struct Vec16;
-template <> struct Vec16<double> { typedef double2 type; static constexpr int N = 2; };
-template <> struct Vec16<float> { typedef float4 type; static constexpr int N = 4; };
-
-template <typename FT, int DIR>
-__device__ __forceinline__ void load8(const FT *__restrict__ p, const int (&off)[M], FT (&o)[M])
-{
-	if (DIR == 2) {
-		typedef typename Vec16<FT>::type V;
-		constexpr int N = Vec16<FT>::N;
-		const V *q = reinterpret_cast<const V *>(p + off[0]);        // 64-byte aligned: r0 % 8 == 0, lines 128-byte aligned
-#pragma unroll
-		for (int v = 0; v < M / N; v++) {
-			const V t = q[v];
-			const FT *e = reinterpret_cast<const FT *>(&t);
-#pragma unroll
-			for (int k = 0; k < N; k++) o[v * N + k] = e[k];
-		}
-	} else {
-#pragma unroll
-		for (int i = 0; i < M; i++) o[i] = p[off[i]];
-	}
-}
-
-// store rows whose bit is set in `mask` (Z: whole chunk with vector stores when all 8 bits are set)
-template <typename FT, int DIR>
-__device__ __forceinline__ void store8(FT *__restrict__ p, const int (&off)[M], unsigned mask, const FT (&v)[M])
-{
-	if (DIR == 2) {
-		if (mask == 0xffu) {
-			typedef typename Vec16<FT>::type V;
-			constexpr int N = Vec16<FT>::N;
-			V *q = reinterpret_cast<V *>(p + off[0]);
-#pragma unroll
-			for (int w = 0; w < M / N; w++) {
-				V t;
-				FT *e = reinterpret_cast<FT *>(&t);
-#pragma unroll
-				for (int k = 0; k < N; k++) e[k] = v[w * N + k];
-				q[w] = t;
-			}
-		} else {
-#pragma unroll
-			for (int i = 0; i < M; i++)
-				if (mask & (1u << i)) p[off[0] + i] = v[i];
-		}
-	} else {
-#pragma unroll
-		for (int i = 0; i < M; i++)
-			if (mask & (1u << i)) p[off[i]] = v[i];
-	}
-}
-
-// central difference along the line for the 8 rows of a chunk (lo / hi = rows r0-1 and r0+8)
-template <typename FT>
-__device__ __forceinline__ FT cdiff(const FT (&f)[M], FT lo, FT hi, int i, FT inv2h)
-{
-	const FT m = i == 0 ? lo : f[i == 0 ? 0 : i - 1], p = i == M - 1 ? hi : f[i == M - 1 ? M - 1 : i + 1];
-	return (p - m) * inv2h;
-}
-
-// One chunk: eliminate the 7 interior rows of (a, b, c | d[NRHS]) given row by row, keep the separator raw.
-// cp/lp/dp hold c', the left spike and d' of the interior rows; entry M-1 holds the raw separator (lp = a, cp = c).
-#define CMC_ELIM_ROW(i, a, b, c)                                                   \
-	if ((i) == M - 1) { lp[i] = (a); cp[i] = (c); b7 = (b); }                      \
-	else if ((i) == 0) { rr = rcp<FT>(b); cp[0] = (c) * rr; lp[0] = (a) * rr; }    \
-	else { rr = rcp<FT>((b) - (a) * cp[(i) - 1]); cp[i] = (c) * rr; lp[i] = -(a) * lp[(i) - 1] * rr; }
-
-template <typename FT, int DIR, int GP, int NL>
+// MODE 0: the complete sweep of a slab whose lines do not leave the slab (Y, Z always; X on a single GPU).
+// x-sweep of a slab-decomposed grid (partitioned solve across GPUs, see dist.h):
+// MODE 1: "spike" pass - eliminate the slab's rows and emit, per line, how its first / last row depend on the
+//         neighbouring slabs' adjacent rows (16 coefficients); nothing is stored into the layers;
+// MODE 2: the complete sweep with the neighbours' (now known) adjacent-row solutions folded into the first /
+//         last row of the slab.
+template <typename FT, int DIR, int GP, int NL, int MODE>
 __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_sweep(const SweepArgs<FT> A, const FastConst<FT> K, long long *trace, const int one)
 {
+	static_assert(MODE == 0 || DIR == 0, "slab coupling exists along x only");
 #define CMC_MARK(k) do { if (trace) { __syncthreads(); if (threadIdx.x == 0) trace[(size_t)blockIdx.x * 16 + (k)] = clock64(); } } while (0)
 	CMC_MARK(0);
 	constexpr int STR = GP * NL;
 	constexpr int GS = DIR == 2 ? 1 : NL;          // shared-memory distance of neighbouring chunks of a line
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	FT *sys = reinterpret_cast<FT *>(smem_raw);    // 3 * 5 arrays (CR publications + PCR ping-pong)
-	FT *head = sys + 3 * 5 * STR;                  // 5 arrays: y0[3], v0, w0 of every chunk
-	FT *sol = head + 5 * STR;                      // 3 arrays: separator solutions
+	constexpr int NRMAX = MODE == 1 ? 7 : 5;       // matrix (2) + right-hand sides of the widest reduced solve
+	FT *sys = reinterpret_cast<FT *>(smem_raw);    // 3 * NRMAX arrays (CR publications + PCR ping-pong)
+	FT *head = sys + 3 * NRMAX * STR;              // 5 arrays: y0[3], v0, w0 of every chunk
+	FT *sol = head + 5 * STR;                      // NRMAX - 2 arrays: separator solutions
 
 	const Layout &L = A.L;
 	const int t = threadIdx.x;
@@ -276,6 +76,15 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 		line_ok = j < L.ny; n = L.nz; stride = 1; base = L.idx(i, line_ok ? j : 0, 0);
 	}
 	const int r0 = g * M;           // first row of this chunk
+	// slab-coupled x-lines: global line id, its owner rank for the interface solve, and the first / last chunk
+	int xo = 0;                     // element offset of this line's coefficients: (owner*NV + v)*lpo + line_in_owner
+	const int GL = (MODE != 0) ? A.L.nx / M : GP;    // chunks that hold real rows (nx % 8 == 0 is required)
+	if (MODE != 0) {
+		const int ktiles = (L.nz + NL - 1) / NL;
+		const int j = blockIdx.x / ktiles, k = min((blockIdx.x % ktiles) * NL + l, L.nz - 1);
+		const int line = j * L.nz + k, owner = line / A.lpo;
+		xo = owner * A.lpo * (MODE == 1 ? 16 : 8) + (line - owner * A.lpo);
+	}
 	// Row offsets, clamped into the line so that EVERY thread issues valid (if redundant) loads: threads of padding
 	// chunks / lines outside the grid see role 0 everywhere, compute identity rows and store nothing.
 	int off[M], off_lo, off_hi;      // 32-bit element offsets (launch_fast_sweep checks total < 2^31)
@@ -288,8 +97,9 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 	} else {
 #pragma unroll
 		for (int i = 0; i < M; i++) off[i] = (int)base + min(r0 + i, n - 1) * (int)stride;
-		off_lo = (int)base + max(r0 - 1, 0) * (int)stride;
-		off_hi = (int)base + min(r0 + M, n - 1) * (int)stride;
+		// rows -1 and n exist for a slab inside a decomposed grid (halo planes): its first / last row can be interior
+		off_lo = (int)base + max(r0 - 1, MODE != 0 ? -1 : 0) * (int)stride;
+		off_hi = (int)base + min(r0 + M, MODE != 0 ? n : n - 1) * (int)stride;
 	}
 	unsigned rowmask = 0;           // rows of this chunk that exist
 #pragma unroll
@@ -346,7 +156,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 				bd0 = A.nodev[0][off[i]]; bd1 = A.nodev[1][off[i]]; bd2 = A.nodev[2][off[i]];
 			}
 			const FT Vh = V[i] * K.inv2h;
-			const FT a = is_int ? -Vh - K.vis_v : ((r & R_END) && vfree ? FT(-1) : FT(0));
+			const FT a = is_int ? -Vh - K.vis_v : ((r & (R_END | R_START)) == R_END && vfree ? FT(-1) : FT(0));   // shared cell: start row only
 			const FT c = is_int ? Vh - K.vis_v : ((r & R_START) && vfree ? FT(-1) : FT(0));
 			const FT b = is_int ? K.b_v : (is_bc && vfree ? FT(2) : FT(1));
 			FT d[3];
@@ -354,13 +164,34 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 			d[1] = is_int ? dp[1][i] * K.c3dt : bd1;
 			d[2] = is_int ? dp[2][i] * K.c3dt : bd2;
 			if (is_int) d[DIR] -= K.v_T * cdiff<FT>(Tl, Tlo, Thi, i, K.inv2h);
-			CMC_ELIM_ROW(i, a, b, c)
+			FT aa = a, cc = c, bb = b;
+			if (r & R_PRE) {        // next cell ends this segment AND starts the next: fold its ApplyBC1 row in
+				if (vfree) bb = b + FT(0.5) * c;                       // -x[p-1] + 2 x[p] = 0
+				else {                                                  // x[p] = node value
+					const int idn = off[i] + (int)stride;
+					d[0] -= c * A.nodev[0][idn]; d[1] -= c * A.nodev[1][idn]; d[2] -= c * A.nodev[2][idn];
+				}
+				cc = FT(0);
+			}
+			if (MODE == 2) {        // neighbours' adjacent rows are known: move their terms to the right-hand side
+				if (i == 0 && g == 0) {
+#pragma unroll
+					for (int q = 0; q < 3; q++) d[q] -= a * A.xbnd[xo + q * A.lpo];
+					aa = FT(0);
+				}
+				if (i == M - 1 && g == GL - 1) {
+#pragma unroll
+					for (int q = 0; q < 3; q++) d[q] -= cc * A.xbnd[xo + (4 + q) * A.lpo];
+					cc = FT(0);
+				}
+			}
+			CMC_ELIM_ROW(i, aa, bb, cc)
 			if (i == M - 1) { dp[0][i] = d[0]; dp[1][i] = d[1]; dp[2][i] = d[2]; }
 			else if (i == 0) { dp[0][0] = d[0] * rr; dp[1][0] = d[1] * rr; dp[2][0] = d[2] * rr; }
 			else {
-				dp[0][i] = (d[0] - a * dp[0][i - 1]) * rr;
-				dp[1][i] = (d[1] - a * dp[1][i - 1]) * rr;
-				dp[2][i] = (d[2] - a * dp[2][i - 1]) * rr;
+				dp[0][i] = (d[0] - aa * dp[0][i - 1]) * rr;
+				dp[1][i] = (d[1] - aa * dp[1][i - 1]) * rr;
+				dp[2][i] = (d[2] - aa * dp[2][i - 1]) * rr;
 			}
 		}
 	}
@@ -388,12 +219,34 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 		Rd[0] = (dp[0][M - 1] - a7 * dp[0][M - 2] - c7 * ny0) * rr;
 		Rd[1] = (dp[1][M - 1] - a7 * dp[1][M - 2] - c7 * ny1) * rr;
 		Rd[2] = (dp[2][M - 1] - a7 * dp[2][M - 2] - c7 * ny2) * rr;
-		reduced_solve<FT, 3, GP, GS, NL>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, E);    // every row's solution -> sol[]
+		if (MODE == 1) {
+			// open-ended slab: E = Y - P*x_left - Q*x_right.  P, Q are two more right-hand sides: the left spike
+			// of chunk 0 and the last row's coupling c7 (its "next chunk" lives on the next slab).
+			FT Re[5] = {Rd[0], Rd[1], Rd[2], FT(0), FT(0)}, Xe[5];
+			FT Ra = -a7 * lp[M - 2] * rr;
+			if (g == 0) { Re[3] = Ra; Ra = FT(0); }
+			if (g == GL - 1) Re[4] = c7 * rr;        // nv == nw == 0 there: chunk GL is a padding (identity) chunk
+			reduced_solve<FT, 5, GP, GS, NL>(sys, sol, g, e, Ra, -c7 * nw * rr, Re, Xe);
+			if (line_ok && g == 0) {                 // first row: x = f - pf*x_left - qf*x_right
+#pragma unroll
+				for (int q = 0; q < 3; q++) A.xcoef[xo + q * A.lpo] = y0[q] - w0 * Xe[q];
+				A.xcoef[xo + 6 * A.lpo] = v0 - w0 * Xe[3];
+				A.xcoef[xo + 7 * A.lpo] = -w0 * Xe[4];
+			}
+			if (line_ok && g == GL - 1) {            // last row (= last separator): x = l - pl*x_left - ql*x_right
+#pragma unroll
+				for (int q = 0; q < 3; q++) A.xcoef[xo + (3 + q) * A.lpo] = Xe[q];
+				A.xcoef[xo + 8 * A.lpo] = Xe[3];
+				A.xcoef[xo + 9 * A.lpo] = Xe[4];
+			}
+			E[0] = E[1] = E[2] = FT(0);
+		} else
+			reduced_solve<FT, 3, GP, GS, NL>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, E);    // every row's solution -> sol[]
 	}
 	CMC_MARK(2);   // phase V reduced solve done
 	// back substitution, store u, v, w and the relaxed linearisation layer
 #pragma unroll
-	for (int q = 0; q < 3; q++) {
+	for (int q = 0; q < (MODE == 1 ? 0 : 3); q++) {
 		const FT El = g > 0 ? sol[q * STR + e - GS] : FT(0);
 		FT x[M], tq[M];
 		if (one) load8<FT, DIR>(A.temp[q], off, tq);
@@ -407,6 +260,10 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 		}
 #pragma unroll
 		for (int i = 0; i < M; i++) tq[i] = (inmask & (1u << i)) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
+		if (A.extra_merge) {
+#pragma unroll
+			for (int i = 0; i < M; i++) tq[i] = (inmask & (1u << i)) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
+		}
 		store8<FT, DIR>(A.temp_out[q], off, full, tq);
 		store8<FT, DIR>(A.next[q], off, segfull, x);
 	}
@@ -468,14 +325,24 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 			FT bd = FT(0);
 			if (is_bc && !tfree) bd = A.nodev[3][off[i]];
 			const FT Vh = V[i] * K.inv2h;
-			const FT a = is_int ? -Vh - K.vis_T : ((r & R_END) && tfree ? FT(-1) : FT(0));
+			const FT a = is_int ? -Vh - K.vis_T : ((r & (R_END | R_START)) == R_END && tfree ? FT(-1) : FT(0));
 			const FT c = is_int ? Vh - K.vis_T : ((r & R_START) && tfree ? FT(-1) : FT(0));
 			const FT b = is_int ? K.b_T : (is_bc && tfree ? FT(2) : FT(1));
-			const FT d = is_int ? cT[i] * K.c3dt + K.t_phi * diss[i] : bd;
-			CMC_ELIM_ROW(i, a, b, c)
+			FT d = is_int ? cT[i] * K.c3dt + K.t_phi * diss[i] : bd;
+			FT aa = a, cc = c, bb = b;
+			if (r & R_PRE) {
+				if (tfree) bb = b + FT(0.5) * c;
+				else d -= c * A.nodev[3][off[i] + (int)stride];
+				cc = FT(0);
+			}
+			if (MODE == 2) {
+				if (i == 0 && g == 0) { d -= a * A.xbnd[xo + 3 * A.lpo]; aa = FT(0); }
+				if (i == M - 1 && g == GL - 1) { d -= cc * A.xbnd[xo + 7 * A.lpo]; cc = FT(0); }
+			}
+			CMC_ELIM_ROW(i, aa, bb, cc)
 			if (i == M - 1) dT[i] = d;
 			else if (i == 0) dT[0] = d * rr;
-			else dT[i] = (d - a * dT[i - 1]) * rr;
+			else dT[i] = (d - aa * dT[i - 1]) * rr;
 		}
 	}
 	CMC_MARK(4);   // phase T loads + elimination done
@@ -491,6 +358,24 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 		const FT a7 = lp[M - 1], c7 = cp[M - 1];
 		rr = rcp<FT>(b7 - a7 * cp[M - 2] - c7 * nv);
 		FT Rd[1] = {(dT[M - 1] - a7 * dT[M - 2] - c7 * ny0) * rr}, ET[1];
+		if (MODE == 1) {
+			FT Re[3] = {Rd[0], FT(0), FT(0)}, Xe[3];
+			FT Ra = -a7 * lp[M - 2] * rr;
+			if (g == 0) { Re[1] = Ra; Ra = FT(0); }
+			if (g == GL - 1) Re[2] = c7 * rr;
+			reduced_solve<FT, 3, GP, GS, NL>(sys, sol, g, e, Ra, -c7 * nw * rr, Re, Xe);
+			if (line_ok && g == 0) {
+				A.xcoef[xo + 10 * A.lpo] = y0 - w0 * Xe[0];
+				A.xcoef[xo + 12 * A.lpo] = v0 - w0 * Xe[1];
+				A.xcoef[xo + 13 * A.lpo] = -w0 * Xe[2];
+			}
+			if (line_ok && g == GL - 1) {
+				A.xcoef[xo + 11 * A.lpo] = Xe[0];
+				A.xcoef[xo + 14 * A.lpo] = Xe[1];
+				A.xcoef[xo + 15 * A.lpo] = Xe[2];
+			}
+			return;
+		}
 		reduced_solve<FT, 1, GP, GS, NL>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, ET);
 		CMC_MARK(5);   // phase T reduced solve done
 		const FT El = g > 0 ? sol[e - GS] : FT(0);
@@ -506,6 +391,10 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 		}
 #pragma unroll
 		for (int i = 0; i < M; i++) tq[i] = (inmask & (1u << i)) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
+		if (A.extra_merge) {
+#pragma unroll
+			for (int i = 0; i < M; i++) tq[i] = (inmask & (1u << i)) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
+		}
 		store8<FT, DIR>(A.temp_out[3], off, full, tq);
 		store8<FT, DIR>(A.next[3], off, segfull, x);
 	}
@@ -515,13 +404,13 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 }
 
 template <typename FT>
-static size_t fast_smem_bytes(int GP, int NL) { return sizeof(FT) * (size_t)(3 * 5 * GP * NL + 5 * GP * NL + 3 * GP * NL); }
+static size_t fast_smem_bytes(int GP, int NL, int nrhs = 3) { return sizeof(FT) * (size_t)(3 * (2 + nrhs) * GP * NL + 5 * GP * NL + nrhs * GP * NL); }
 
 // lines per CTA: 8 (64-byte row segments in fp64) up to 256 threads per CTA; the 512-row case keeps 256 threads
 // (4 lines) so that one CTA per SM owns the whole register file: every load of a phase is in flight at once.
 constexpr int lines_per_cta(int GP) { return 8; }
 
-template <typename FT, int DIR, int GP>
+template <typename FT, int DIR, int GP, int MODE = 0>
 static unsigned launch_one(const SweepArgs<FT> &A, cudaStream_t s, long long *trace, bool dry)
 {
 	constexpr int NL = lines_per_cta(GP);
@@ -532,13 +421,13 @@ static unsigned launch_one(const SweepArgs<FT> &A, cudaStream_t s, long long *tr
 	else grid = (unsigned)L.nx * (unsigned)((L.ny + NL - 1) / NL);
 	if (dry) return grid;
 	static bool attr_set = false;
-	const size_t smem = fast_smem_bytes<FT>(GP, NL);
+	const size_t smem = fast_smem_bytes<FT>(GP, NL, MODE == 1 ? 5 : 3);
 	if (!attr_set) {
-		cudaFuncSetAttribute((const void *)k_fast_sweep<FT, DIR, GP, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaFuncSetAttribute((const void *)k_fast_sweep<FT, DIR, GP, NL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		attr_set = true;
 	}
 	FastConst<FT> K; K.init(A, DIR);
-	k_fast_sweep<FT, DIR, GP, NL><<<grid, GP * NL, smem, s>>>(A, K, trace, 1);
+	k_fast_sweep<FT, DIR, GP, NL, MODE><<<grid, GP * NL, smem, s>>>(A, K, trace, 1);
 	return grid;
 }
 
@@ -554,17 +443,23 @@ static unsigned launch_dir(int GP, const SweepArgs<FT> &A, cudaStream_t s, long 
 	}
 }
 
+bool fast_sweep_supported(const Layout &L, int dir)
+{
+	const int n = dir == 0 ? L.nx : dir == 1 ? L.ny : L.nz;
+	if (n < M) return false;                              // clamped row offsets need at least one full chunk
+	if (L.total >= (1ll << 31)) return false;             // 32-bit element offsets
+	return (n + M - 1) / M <= 64;                         // lines longer than 512 rows: caller falls back
+}
+
 template <typename FT>
 bool launch_fast_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches)
 {
 	const Layout &L = A.L;
+	if (!fast_sweep_supported(L, dir)) return false;
 	const int n = dir == 0 ? L.nx : dir == 1 ? L.ny : L.nz;
-	if (n < M) return false;                              // clamped row offsets need at least one full chunk
-	if (L.total >= (1ll << 31)) return false;
 	const int G = (n + M - 1) / M;
 	int GP = 4;                                           // at least one warp per CTA
 	while (GP < G) GP <<= 1;
-	if (GP > 64) return false;                            // lines longer than 512 rows: caller falls back
 	const unsigned grid = dir == 0 ? launch_dir<FT, 0>(GP, A, s, nullptr, true) : dir == 1 ? launch_dir<FT, 1>(GP, A, s, nullptr, true)
 	                                                                                       : launch_dir<FT, 2>(GP, A, s, nullptr, true);
 	// debug facility: CMC_TRACE=1 records clock64() at the phase boundaries of every CTA and prints the mean phase
@@ -589,6 +484,104 @@ bool launch_fast_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long lon
 	if (launches) (*launches)++;
 	return true;
 }
+
+// x-sweep passes of a slab (MODE 1 / MODE 2); nx must be a multiple of 8 and at most 512
+template <typename FT, int MODE>
+static bool launch_x_mode(const SweepArgs<FT> &A, cudaStream_t s)
+{
+	const Layout &L = A.L;
+	if (!fast_sweep_supported(L, 0) || L.nx % M != 0) return false;
+	int GP = 4;
+	while (GP < L.nx / M) GP <<= 1;
+	switch (GP) {
+	case 4: launch_one<FT, 0, 4, MODE>(A, s, nullptr, false); break;
+	case 8: launch_one<FT, 0, 8, MODE>(A, s, nullptr, false); break;
+	case 16: launch_one<FT, 0, 16, MODE>(A, s, nullptr, false); break;
+	case 32: launch_one<FT, 0, 32, MODE>(A, s, nullptr, false); break;
+	default: launch_one<FT, 0, 64, MODE>(A, s, nullptr, false); break;
+	}
+	return true;
+}
+template <typename FT>
+bool launch_x_spike(const SweepArgs<FT> &A, cudaStream_t s, long long *launches)
+{
+	if (!launch_x_mode<FT, 1>(A, s)) return false;
+	if (launches) (*launches)++;
+	return true;
+}
+template <typename FT>
+bool launch_x_coupled(const SweepArgs<FT> &A, cudaStream_t s, long long *launches)
+{
+	if (!launch_x_mode<FT, 2>(A, s)) return false;
+	if (launches) (*launches)++;
+	return true;
+}
+template bool launch_x_spike<float>(const SweepArgs<float> &, cudaStream_t, long long *);
+template bool launch_x_spike<double>(const SweepArgs<double> &, cudaStream_t, long long *);
+template bool launch_x_coupled<float>(const SweepArgs<float> &, cudaStream_t, long long *);
+template bool launch_x_coupled<double>(const SweepArgs<double> &, cudaStream_t, long long *);
+
+// ---- interface system of the partitioned x-sweep -------------------------------------------------------------------
+// One thread per OWNED line.  coef[(src * 16 + v) * lpo + line]: the 16 coefficients rank `src` emitted for the line
+// (k_fast_sweep MODE 1).  Unknowns per rank r: F_r (first row of its slab), L_r (last row):
+//     F_r + pf_r L_{r-1} + qf_r F_{r+1} = f_r ,   L_r + pl_r L_{r-1} + ql_r F_{r+1} = l_r .
+// Block-tridiagonal in Z_r = (L_r, F_{r+1}), r = 0..P-2, solved by block Thomas (2x2 blocks).  Writes, for every rank
+// r, the values of its neighbours' adjacent rows: bnd[(r * 8 + q) * lpo + line] = L_{r-1} (q < 4), F_{r+1} (q >= 4).
+constexpr int MAXP = 16;
+template <typename FT>
+__global__ void k_x_interface(int P, int lpo, int nlines, const FT *__restrict__ coef, FT *__restrict__ bnd)
+{
+	const int line = blockIdx.x * blockDim.x + threadIdx.x;
+	if (line >= nlines) return;
+#pragma unroll 1
+	for (int mat = 0; mat < 2; mat++) {
+		const int nr = mat == 0 ? 3 : 1;                 // right-hand sides: u, v, w | T
+		const int vf = mat == 0 ? 0 : 10, vl = mat == 0 ? 3 : 11, vp = mat == 0 ? 6 : 12;   // f, l, (pf, qf, pl, ql)
+		FT m01[MAXP], i00[MAXP], i01[MAXP], i10[MAXP], i11[MAXP], r0[3][MAXP], r1[3][MAXP];
+		auto C = [&](int src, int v) { return coef[((size_t)src * 16 + v) * lpo + line]; };
+		FT p_i00 = 0, p_i01 = 0;                         // inverse of the previous (eliminated) block
+		FT p_s[3] = {0, 0, 0};                           // i00 rhs0 + i01 rhs1 of the previous block
+		for (int r = 0; r + 1 < P; r++) {
+			const FT pl = C(r, vp + 2), ql = C(r, vp + 3), pf1 = C(r + 1, vp + 0), qf_r = C(r, vp + 1);
+			m01[r] = ql - pl * p_i01 * qf_r;             // (r == 0: pl == 0)
+			const FT det = FT(1) - m01[r] * pf1, id = FT(1) / det;
+			i00[r] = id; i01[r] = -m01[r] * id; i10[r] = -pf1 * id; i11[r] = id;
+			for (int q = 0; q < nr; q++) {
+				r0[q][r] = C(r, vl + q) - pl * p_s[q];
+				r1[q][r] = C(r + 1, vf + q);
+				p_s[q] = i00[r] * r0[q][r] + i01[r] * r1[q][r];
+			}
+			p_i00 = i00[r]; p_i01 = i01[r];
+		}
+		(void)p_i00;
+		for (int q = 0; q < nr; q++) {
+			FT Lr[MAXP], Fr1[MAXP];                      // L_r, F_{r+1}
+			FT nextF = FT(0);                            // F_{r+2} of the block above
+			for (int r = P - 2; r >= 0; r--) {
+				const FT qf1 = C(r + 1, vp + 1);
+				const FT b0 = r0[q][r], b1 = r1[q][r] - qf1 * nextF;
+				Lr[r] = i00[r] * b0 + i01[r] * b1;
+				Fr1[r] = i10[r] * b0 + i11[r] * b1;
+				nextF = Fr1[r];
+			}
+			const int qq = mat == 0 ? q : 3;
+			for (int r = 0; r < P; r++) {
+				bnd[((size_t)r * 8 + qq) * lpo + line] = r > 0 ? Lr[r - 1] : FT(0);
+				bnd[((size_t)r * 8 + 4 + qq) * lpo + line] = r + 1 < P ? Fr1[r] : FT(0);
+			}
+		}
+	}
+}
+
+template <typename FT>
+void launch_x_interface(int P, int lpo, int nlines, const FT *coef, FT *bnd, cudaStream_t s, long long *launches)
+{
+	if (nlines <= 0) return;
+	k_x_interface<FT><<<(nlines + 127) / 128, 128, 0, s>>>(P, lpo, nlines, coef, bnd);
+	if (launches) (*launches)++;
+}
+template void launch_x_interface<float>(int, int, int, const float *, float *, cudaStream_t, long long *);
+template void launch_x_interface<double>(int, int, int, const double *, double *, cudaStream_t, long long *);
 
 template bool launch_fast_sweep<float>(int, const SweepArgs<float> &, cudaStream_t, long long *);
 template bool launch_fast_sweep<double>(int, const SweepArgs<double> &, cudaStream_t, long long *);

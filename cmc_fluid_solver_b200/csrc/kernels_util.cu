@@ -59,7 +59,15 @@ __global__ void k_build_roles(const Layout G, const uint8_t *__restrict__ ncode,
 			}
 			// a cell that ends one segment and starts the next one holds TWO unknowns when its boundary row is
 			// BC_FREE; the whole-line fast solver cannot represent that (exact mode can) - count such cells
-			if (start == prev_end && (ncode[gbase + (long long)start * gstride] & 12u)) shared_free++;
+			if (start == prev_end) {
+				const unsigned sc = ncode[gbase + (long long)start * gstride];
+				if (sc & 12u) shared_free++;
+				// fast solver: one unknown per cell, so the earlier segment's last unknown (this cell) is eliminated
+				// into its last interior row (start - 1), which also records the shared cell's boundary kinds
+				const int q = start - 1;
+				if (!(DIR == 0 && (q < L.x0 || q >= L.x0 + L.nx)))
+					role[lbase + (long long)q * lstride] |= (uint8_t)(R_PRE | ((sc & 4u) ? R_VFREE : 0u) | ((sc & 8u) ? R_TFREE : 0u));
+			}
 			prev_end = end;
 			count++;
 			state = 0;
@@ -92,7 +100,7 @@ __global__ void k_role_type_bits(const Layout G, const uint8_t *__restrict__ nco
 		for (int k = threadIdx.x; k < L.nz; k += blockDim.x) {
 			const unsigned c = src[k];
 			const unsigned ty = code_type(c);
-			unsigned bits = (ty == 0u ? R_IN : 0u) | ((ty == 2u || ty == 3u) ? R_BV : 0u) | (ty == 1u ? R_OUT : 0u)
+			unsigned bits = (ty == 0u ? R_IN : 0u) | ((ty == 2u || ty == 3u) ? R_BV : 0u)
 			              | ((c & 4u) ? R_VFREE : 0u) | ((c & 8u) ? R_TFREE : 0u);
 			rx[dst + k] = (uint8_t)bits; ry[dst + k] = (uint8_t)bits; rz[dst + k] = (uint8_t)bits;
 		}
@@ -172,7 +180,7 @@ template <typename FT>
 __global__ void k_clear_out(const Layout L, const uint8_t *__restrict__ role, LayerPtrs<FT> layer, FT value)
 {
 	for_each_cell<FT>(L, [&](long long id) {
-		if (role[id] & R_OUT) { layer.f[0][id] = value; layer.f[1][id] = value; layer.f[2][id] = value; layer.f[3][id] = value; }
+		if (!(role[id] & (R_IN | R_BV))) { layer.f[0][id] = value; layer.f[1][id] = value; layer.f[2][id] = value; layer.f[3][id] = value; }
 	});
 }
 

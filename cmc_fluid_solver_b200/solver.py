@@ -68,7 +68,9 @@ class AdiSolver3D:
         self.rank, self.nranks = 0, 1
 
     # -- Solver3D::Init ------------------------------------------------------------------------------------
-    def Init(self, case: Case, device: int = 0, mode: str = "fast", rank: int = 0, nranks: int = 1, nccl_id: bytes = None):
+    def Init(self, case: Case, device: int = 0, mode: str = "fast", rank: int = 0, nranks: int = 1, nccl_id: bytes = None,
+             emulate_slabs: int = 0):
+        """rank/nranks/nccl_id: one x-slab per process (NCCL).  emulate_slabs=N: all N slabs in this handle, on one GPU."""
         lib = load_library()
         self.case = case
         self.fp = case.fp_bytes
@@ -76,7 +78,9 @@ class AdiSolver3D:
         g = GridDesc(case.dimx, case.dimy, case.dimz, case.dx, case.dy, case.dz)
         p = FluidParams(case.v_T, case.v_vis, case.t_vis, case.t_phi)
         h = C.c_void_p()
-        if nranks > 1:
+        if emulate_slabs > 1:
+            _check(lib.cmc_adi3d_create_emulated(C.byref(g), C.byref(p), self.fp, device, emulate_slabs, C.byref(h)))
+        elif nranks > 1:
             buf = C.create_string_buffer(nccl_id, 128)
             _check(lib.cmc_adi3d_create_dist(C.byref(g), C.byref(p), self.fp, device, rank, nranks, buf, C.byref(h)))
         else:

@@ -86,9 +86,14 @@ int cmc_nccl_unique_id(void *id128);
 int cmc_adi3d_create_dist(const cmc_grid_desc *grid, const cmc_fluid_params *params,
                           int fp_bytes, int device, int rank, int nranks,
                           const void *nccl_unique_id, cmc_adi3d **out);
+/* the same slab decomposition with all `n_slabs` slabs held by ONE handle on ONE device, exchanging halos and
+ * the reduced systems with device-to-device copies: exercises the multi-GPU code path on a single GPU (the
+ * counterpart of the reference's MGPU_EMU switch, src/Common/GPUplan.h:10-15). */
+int cmc_adi3d_create_emulated(const cmc_grid_desc *grid, const cmc_fluid_params *params,
+                              int fp_bytes, int device, int n_slabs, cmc_adi3d **out);
 int cmc_adi3d_destroy(cmc_adi3d *h);           /* ~AdiSolver3D (AdiSolver3D.cpp:153-158) */
 
-/* slab owned by this handle: global x range [x0, x0+nx) */
+/* planes held by this handle: global x range [x0, x0+nx) */
 int cmc_adi3d_slab(const cmc_adi3d *h, int *x0, int *nx);
 
 /* ---- grid nodes: replaces Grid3D::GetNodesCPU(), GetType, GetBC_vel, GetBC_temp, GetVel, GetT (Grid3D.h:114-124) ----

@@ -62,6 +62,21 @@ def max_rel(ref, got, mask=None):
     return linf, l2
 
 
+def layer_errors(ref4, got4):
+    """Tolerance metric of the parity tests (BASELINE.json north_star: relative L2 / L-inf per field, fp64 1e-10,
+    fp32 1e-5).  The three velocity components are ONE field - the velocity vector - so each component's error is
+    taken relative to the magnitude of the velocity field (a component that is ~0 everywhere, like v and w in a
+    straight channel, would otherwise turn rounding noise into an O(1) 'relative' error); T stands alone.
+    Returns (linf_vel, l2_vel, linf_T, l2_T)."""
+    r = [np.asarray(a, dtype=np.float64).ravel() for a in ref4]
+    g = [np.asarray(a, dtype=np.float64).ravel() for a in got4]
+    vmax = max(max(float(np.abs(a).max()) for a in r[:3]), 1e-300)
+    linf_v = max(float(np.abs(a - b).max()) for a, b in zip(r[:3], g[:3])) / vmax
+    l2_v = np.sqrt(sum(float(np.sum((a - b) ** 2)) for a, b in zip(r[:3], g[:3]))) / max(np.sqrt(sum(float(np.sum(a ** 2)) for a in r[:3])), 1e-300)
+    linf_T, l2_T = max_rel(r[3], g[3])
+    return linf_v, l2_v, linf_T, l2_T
+
+
 @pytest.fixture(scope="session")
 def oracle_mod():
     from oracle import oracle as O
