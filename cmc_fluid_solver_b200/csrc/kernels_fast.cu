@@ -147,51 +147,53 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 			load8<FT, DIR>(A.temp[3], off, Tl);
 			Tlo = A.temp[3][off_lo]; Thi = A.temp[3][off_hi];
 		}
+		// right-hand sides of interior rows, in place (rows that are not plain interior are patched below):
+		//   d = cur * 3/dt  ( - v_T * dT/dD for the velocity component along the sweep )
+#pragma unroll
+		for (int i = 0; i < M; i++) {
+			dp[0][i] *= K.c3dt; dp[1][i] *= K.c3dt; dp[2][i] *= K.c3dt;
+			dp[DIR][i] -= K.v_T * cdiff<FT>(Tl, Tlo, Thi, i, K.inv2h);
+		}
 #pragma unroll
 		for (int i = 0; i < M; i++) {
 			const unsigned r = ROLE(i);
-			const bool is_int = r & R_INT, is_bc = r & (R_START | R_END), vfree = r & R_VFREE;
-			FT bd0 = FT(0), bd1 = FT(0), bd2 = FT(0);
-			if (is_bc && !vfree) {        // no-slip boundary row: value of the node (rare: two rows per segment)
-				bd0 = A.nodev[0][off[i]]; bd1 = A.nodev[1][off[i]]; bd2 = A.nodev[2][off[i]];
-			}
 			const FT Vh = V[i] * K.inv2h;
-			const FT a = is_int ? -Vh - K.vis_v : ((r & (R_END | R_START)) == R_END && vfree ? FT(-1) : FT(0));   // shared cell: start row only
-			const FT c = is_int ? Vh - K.vis_v : ((r & R_START) && vfree ? FT(-1) : FT(0));
-			const FT b = is_int ? K.b_v : (is_bc && vfree ? FT(2) : FT(1));
-			FT d[3];
-			d[0] = is_int ? dp[0][i] * K.c3dt : bd0;
-			d[1] = is_int ? dp[1][i] * K.c3dt : bd1;
-			d[2] = is_int ? dp[2][i] * K.c3dt : bd2;
-			if (is_int) d[DIR] -= K.v_T * cdiff<FT>(Tl, Tlo, Thi, i, K.inv2h);
-			FT aa = a, cc = c, bb = b;
-			if (r & R_PRE) {        // next cell ends this segment AND starts the next: fold its ApplyBC1 row in
-				if (vfree) bb = b + FT(0.5) * c;                       // -x[p-1] + 2 x[p] = 0
-				else {                                                  // x[p] = node value
-					const int idn = off[i] + (int)stride;
-					d[0] -= c * A.nodev[0][idn]; d[1] -= c * A.nodev[1][idn]; d[2] -= c * A.nodev[2][idn];
-				}
-				cc = FT(0);
+			FT a = -Vh - K.vis_v, c = Vh - K.vis_v, b = K.b_v;
+			FT d0 = dp[0][i], d1 = dp[1][i], d2 = dp[2][i];
+			if ((r & (R_SEG | R_PRE)) != R_INT) {       // rare: boundary row, cell outside every segment, or shared-cell fold
+				const bool vfree = r & R_VFREE;
+				if (r & R_INT) {                        // R_PRE: the next cell ends this segment AND starts the next one -
+					if (vfree) b += FT(0.5) * c;        // fold its ApplyBC1 row in:  -x[p-1] + 2 x[p] = 0
+					else {                              //                            x[p] = node value
+						const int idn = off[i] + (int)stride;
+						d0 -= c * A.nodev[0][idn]; d1 -= c * A.nodev[1][idn]; d2 -= c * A.nodev[2][idn];
+					}
+					c = FT(0);
+				} else if (r & (R_START | R_END)) {     // ApplyBC0 / ApplyBC1 (a shared cell keeps its start row only)
+					a = ((r & (R_END | R_START)) == R_END && vfree) ? FT(-1) : FT(0);
+					c = ((r & R_START) && vfree) ? FT(-1) : FT(0);
+					b = vfree ? FT(2) : FT(1);
+					d0 = d1 = d2 = FT(0);
+					if (!vfree) { d0 = A.nodev[0][off[i]]; d1 = A.nodev[1][off[i]]; d2 = A.nodev[2][off[i]]; }
+				} else { a = FT(0); c = FT(0); b = FT(1); d0 = d1 = d2 = FT(0); }
 			}
 			if (MODE == 2) {        // neighbours' adjacent rows are known: move their terms to the right-hand side
 				if (i == 0 && g == 0) {
-#pragma unroll
-					for (int q = 0; q < 3; q++) d[q] -= a * A.xbnd[xo + q * A.lpo];
-					aa = FT(0);
+					d0 -= a * A.xbnd[xo]; d1 -= a * A.xbnd[xo + A.lpo]; d2 -= a * A.xbnd[xo + 2 * A.lpo];
+					a = FT(0);
 				}
 				if (i == M - 1 && g == GL - 1) {
-#pragma unroll
-					for (int q = 0; q < 3; q++) d[q] -= cc * A.xbnd[xo + (4 + q) * A.lpo];
-					cc = FT(0);
+					d0 -= c * A.xbnd[xo + 4 * A.lpo]; d1 -= c * A.xbnd[xo + 5 * A.lpo]; d2 -= c * A.xbnd[xo + 6 * A.lpo];
+					c = FT(0);
 				}
 			}
-			CMC_ELIM_ROW(i, aa, bb, cc)
-			if (i == M - 1) { dp[0][i] = d[0]; dp[1][i] = d[1]; dp[2][i] = d[2]; }
-			else if (i == 0) { dp[0][0] = d[0] * rr; dp[1][0] = d[1] * rr; dp[2][0] = d[2] * rr; }
+			CMC_ELIM_ROW(i, a, b, c)
+			if (i == M - 1) { dp[0][i] = d0; dp[1][i] = d1; dp[2][i] = d2; }
+			else if (i == 0) { dp[0][0] = d0 * rr; dp[1][0] = d1 * rr; dp[2][0] = d2 * rr; }
 			else {
-				dp[0][i] = (d[0] - aa * dp[0][i - 1]) * rr;
-				dp[1][i] = (d[1] - aa * dp[1][i - 1]) * rr;
-				dp[2][i] = (d[2] - aa * dp[2][i - 1]) * rr;
+				dp[0][i] = (d0 - a * dp[0][i - 1]) * rr;
+				dp[1][i] = (d1 - a * dp[1][i - 1]) * rr;
+				dp[2][i] = (d2 - a * dp[2][i - 1]) * rr;
 			}
 		}
 	}
@@ -321,28 +323,30 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 #pragma unroll
 		for (int i = 0; i < M; i++) {
 			const unsigned r = ROLE(i);
-			const bool is_int = r & R_INT, is_bc = r & (R_START | R_END), tfree = r & R_TFREE;
-			FT bd = FT(0);
-			if (is_bc && !tfree) bd = A.nodev[3][off[i]];
 			const FT Vh = V[i] * K.inv2h;
-			const FT a = is_int ? -Vh - K.vis_T : ((r & (R_END | R_START)) == R_END && tfree ? FT(-1) : FT(0));
-			const FT c = is_int ? Vh - K.vis_T : ((r & R_START) && tfree ? FT(-1) : FT(0));
-			const FT b = is_int ? K.b_T : (is_bc && tfree ? FT(2) : FT(1));
-			FT d = is_int ? cT[i] * K.c3dt + K.t_phi * diss[i] : bd;
-			FT aa = a, cc = c, bb = b;
-			if (r & R_PRE) {
-				if (tfree) bb = b + FT(0.5) * c;
-				else d -= c * A.nodev[3][off[i] + (int)stride];
-				cc = FT(0);
+			FT a = -Vh - K.vis_T, c = Vh - K.vis_T, b = K.b_T;
+			FT d = cT[i] * K.c3dt + K.t_phi * diss[i];
+			if ((r & (R_SEG | R_PRE)) != R_INT) {
+				const bool tfree = r & R_TFREE;
+				if (r & R_INT) {
+					if (tfree) b += FT(0.5) * c;
+					else d -= c * A.nodev[3][off[i] + (int)stride];
+					c = FT(0);
+				} else if (r & (R_START | R_END)) {
+					a = ((r & (R_END | R_START)) == R_END && tfree) ? FT(-1) : FT(0);
+					c = ((r & R_START) && tfree) ? FT(-1) : FT(0);
+					b = tfree ? FT(2) : FT(1);
+					d = tfree ? FT(0) : A.nodev[3][off[i]];
+				} else { a = FT(0); c = FT(0); b = FT(1); d = FT(0); }
 			}
 			if (MODE == 2) {
-				if (i == 0 && g == 0) { d -= a * A.xbnd[xo + 3 * A.lpo]; aa = FT(0); }
-				if (i == M - 1 && g == GL - 1) { d -= cc * A.xbnd[xo + 7 * A.lpo]; cc = FT(0); }
+				if (i == 0 && g == 0) { d -= a * A.xbnd[xo + 3 * A.lpo]; a = FT(0); }
+				if (i == M - 1 && g == GL - 1) { d -= c * A.xbnd[xo + 7 * A.lpo]; c = FT(0); }
 			}
-			CMC_ELIM_ROW(i, aa, bb, cc)
+			CMC_ELIM_ROW(i, a, b, c)
 			if (i == M - 1) dT[i] = d;
 			else if (i == 0) dT[0] = d * rr;
-			else dT[i] = (d - aa * dT[i - 1]) * rr;
+			else dT[i] = (d - a * dT[i - 1]) * rr;
 		}
 	}
 	CMC_MARK(4);   // phase T loads + elimination done
