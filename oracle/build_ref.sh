@@ -50,6 +50,15 @@ build3d() { # $1 = f32|f64
   )
   g++ -fopenmp -o "$OUT/ref_probe3d_$tag" "$dir"/*.o -L"$CUDA/lib64" -lcudart_static -ldl -lpthread -lrt
   echo "built $OUT/ref_probe3d_$tag"
+  # drop-in demonstration: the same driver + the reference's loader objects + our Solver3D adapter + libcmcadi.so
+  local pkg="$HERE/../cmc_fluid_solver_b200"
+  if [ -f "$pkg/libcmcadi.so" ]; then
+    $cxx -DWITH_B200 -I"$pkg/host" -I"$HERE/../include" -c "$HERE/ref_probe3d.cpp" -o "$dir/ref_probe3d.o"
+    $cxx -I"$pkg/host" -I"$HERE/../include" -c "$pkg/host/B200AdiSolver3D.cpp" -o "$dir/B200AdiSolver3D.o"
+    g++ -fopenmp -o "$OUT/dropin3d_$tag" "$dir"/*.o -L"$CUDA/lib64" -lcudart_static -ldl -lpthread -lrt \
+        -L"$pkg" -lcmcadi -Wl,-rpath,'$ORIGIN/../../cmc_fluid_solver_b200'
+    echo "built $OUT/dropin3d_$tag"
+  fi
 }
 
 build2d() { # fp32 only (BASELINE config 1 is the reference CPU case)

@@ -10,7 +10,11 @@
 // bench.py's cpu_baseline / --impl reference legs may execute the resulting binary.
 //
 // usage: ref_probe3d <data> <config> <out.bin|-> <nsteps> [align] [dump=every|last|none]
-//                    [getlayer] [dt=<v>] [sweep=<Z|Y|X>] [threads=<n>]
+//                    [getlayer] [dt=<v>] [sweep=<Z|Y|X>] [threads=<n>] [solver=cpu|b200|b200exact]
+//
+// Built with -DWITH_B200 (oracle/_ref/dropin3d_*) the same driver can put the reference's loader and Node[] in
+// front of the B200 solver through the Solver3D adapter (cmc_fluid_solver_b200/host/B200AdiSolver3D.*): that binary
+// is the drop-in demonstration - reference Grid3D/Grid2D/Config + our C ABI - and is exercised by the GPU tests.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -34,6 +38,10 @@
 #include "FluidSolver3D.h"
 #undef private
 #undef protected
+
+#ifdef WITH_B200
+#include "B200AdiSolver3D.h"
+#endif
 
 using namespace FluidSolver3D;
 using namespace Common;
@@ -67,7 +75,7 @@ int main(int argc, char **argv)
 		return 1;
 	}
 	bool align = false, getlayer = false;
-	std::string dump = "last", sweep = "";
+	std::string dump = "last", sweep = "", which = "cpu";
 	double dt_override = -1;
 	int nsteps = atoi(argv[4]);
 	for (int a = 5; a < argc; a++) {
@@ -77,6 +85,7 @@ int main(int argc, char **argv)
 		else if (!strncmp(argv[a], "dt=", 3)) dt_override = atof(argv[a] + 3);
 		else if (!strncmp(argv[a], "sweep=", 6)) sweep = argv[a] + 6;
 		else if (!strncmp(argv[a], "threads=", 8)) omp_set_num_threads(atoi(argv[a] + 8));
+		else if (!strncmp(argv[a], "solver=", 7)) which = argv[a] + 7;
 	}
 	try {
 		PARAplan *pplan = PARAplan::Instance();
@@ -107,8 +116,20 @@ int main(int argc, char **argv)
 		if (Config::useNormalizedParams) params = new FluidParams(Config::Re, Config::Pr, Config::lambda);
 		else params = new FluidParams(Config::viscosity, Config::density, Config::R_specific, Config::k, Config::cv);
 
-		AdiSolver3D *solver = new AdiSolver3D();
-		solver->Init(CPU, false, grid, *params, false, 1);
+		AdiSolver3D *solver = NULL;
+#ifdef WITH_B200
+		B200AdiSolver3D *b200 = NULL;
+		if (which != "cpu") {
+			b200 = new B200AdiSolver3D(which == "b200exact" ? CMC_MODE_EXACT : CMC_MODE_FAST, 0);
+			b200->Init(GPU, false, grid, *params, false, 1);
+		}
+#else
+		if (which != "cpu") throw std::runtime_error("probe: built without the B200 adapter");
+#endif
+		if (which == "cpu") {
+			solver = new AdiSolver3D();
+			solver->Init(CPU, false, grid, *params, false, 1);
+		}
 
 		int frames = grid->GetFramesNum();
 		double length = grid->GetCycleLength();
@@ -146,6 +167,40 @@ int main(int argc, char **argv)
 			for (size_t id = 0; id < N; id++) tf[id] = nodes[id].T;   put(tf.data(), N * sizeof(FTYPE));
 		}
 
+#ifdef WITH_B200
+		if (b200) {
+			// the drop-in path: reference loader + Node[] -> Solver3D adapter -> C ABI -> sm_100a kernels
+			b200->CreateSegments();
+			grid->Prepare(0);
+			size_t outN = (size_t)Config::outdimx * Config::outdimy * Config::outdimz;
+			Vec3D *resVel = getlayer ? new Vec3D[outN] : NULL;
+			double *resT = getlayer ? new double[outN] : NULL;
+			std::vector<FTYPE> buf(N);
+			double t_steps = 0.0;
+			for (int i = 0; i < nsteps; i++) {
+				bool computeError = (i % 10 == 0) || (i == nsteps - 1);
+				double t0 = omp_get_wtime();
+				b200->UpdateBoundaries();
+				b200->TimeStep((FTYPE)dt, Config::num_global, Config::num_local, computeError);
+				t_steps += omp_get_wtime() - t0;
+				if (getlayer && (i % Config::out_time_steps) == 0) {
+					b200->GetLayer(resVel, resT, Config::outdimx, Config::outdimy, Config::outdimz);
+					put_i32(i); put_i32(1); put_f64(b200->GetError());
+					put(resVel, outN * sizeof(Vec3D));
+					put(resT, outN * sizeof(double));
+				}
+				if (dump == "every" || (dump == "last" && i == nsteps - 1)) {
+					put_i32(i); put_i32(0); put_f64(b200->GetError());
+					for (int q = 0; q < 4; q++) { b200->ReadField(CMC_LAYER_CUR, q, buf.data()); put(buf.data(), N * sizeof(FTYPE)); }
+				}
+			}
+			printf("\nprobe: b200 steps %d, seconds %.6f, err %.10g\n", nsteps, t_steps, b200->GetError());
+			if (g_out) fclose(g_out);
+			delete b200;
+			fflush(stdout);
+			_Exit(0);
+		}
+#endif
 		// half/next/temp are allocated uninitialised by the reference (TimeLayer3D.h:353).
 		// Define their initial contents (= cur) so dumps are deterministic, OUT cells included.
 		solver->cur->CopyLayerTo(solver->next);

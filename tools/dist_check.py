@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Multi-GPU (one process per GPU, NCCL) check of the slab-decomposed ADI step:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+
+Every rank also runs the SAME case on its own GPU as a single slab and compares its planes (tolerance of the fast
+mode: fp64 1e-10 / fp32 1e-5), the residual and the GetLayer output on rank 0."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "tests"))
+from cmc_fluid_solver_b200 import AdiSolver3D  # noqa: E402
+from cmc_fluid_solver_b200.cases import channel_case  # noqa: E402
+from cmc_fluid_solver_b200.solver import nccl_unique_id  # noqa: E402
+from conftest import layer_errors  # noqa: E402
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    def fresh_id():          # one ncclUniqueId per communicator
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        return bytes(idt.cpu().numpy().tobytes())
+
+    ok = True
+    for fp, tol in ((8, 1e-10), (4, 1e-5)):
+        nid = fresh_id()
+        case = channel_case(16 * world * 2, 40, 48, fp_bytes=fp, depth_var=0.25)
+        case.outdims = (9, 7, 5)
+        one = AdiSolver3D().Init(case, device=lr, mode="fast"); one.CreateSegments()
+        many = AdiSolver3D().Init(case, device=lr, mode="fast", rank=rank, nranks=world, nccl_id=nid); many.CreateSegments()
+        assert [many.numSegs(d) for d in range(3)] == [one.numSegs(d) for d in range(3)], "segment counts differ"
+        for i in range(4):
+            one.UpdateBoundaries(); many.UpdateBoundaries()
+            e1 = one.TimeStep(case.dt, 4, 2, True)
+            e = many.TimeStep(case.dt, 4, 2, True)
+            assert abs(e - e1) <= (1e-5 if fp == 4 else 1e-9) * abs(e1), (e, e1)
+        v1, T1 = one.GetLayer(*case.outdims)
+        v, T = many.GetLayer(*case.outdims)
+        if rank == 0:
+            assert np.allclose(v, v1, rtol=0, atol=tol * 1e5) and np.allclose(T, T1, rtol=0, atol=tol * 1e5), "GetLayer differs"
+        sl = slice(many.x0, many.x0 + many.nx)
+        errs = layer_errors([one.read_field(0, q)[sl] for q in range(4)], [many.read_field(0, q) for q in range(4)])
+        good = max(errs) <= tol
+        ok &= good
+        print(f"rank {rank}/{world} fp{fp * 8}: planes [{many.x0},{many.x0 + many.nx}) err {e:.6e} (1 GPU {e1:.6e}) "
+              f"linf_vel {errs[0]:.2e} l2_vel {errs[1]:.2e} linf_T {errs[2]:.2e} l2_T {errs[3]:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+        one.close(); many.close()
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("DIST CHECK", "PASSED" if int(t.item()) else "FAILED")
+    sys.exit(0 if int(t.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
