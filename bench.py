@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--dims", default=None, help="X,Y,Z grid instead of --size^3 (experiments)")
     ap.add_argument("--fp", type=int, default=8, choices=[4, 8])
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -181,7 +182,8 @@ def main():
         nccl_id = bytes(idt.cpu().numpy().tobytes())
 
     S = args.size
-    case = channel_case(S, S, S, fp_bytes=args.fp, depth_var=0.2)
+    DX, DY, DZ = (int(v) for v in args.dims.split(",")) if args.dims else (S, S, S)
+    case = channel_case(DX, DY, DZ, fp_bytes=args.fp, depth_var=0.2)
     ncells = case.ncells
     fluid = case.n_in / ncells
     sol = AdiSolver3D().Init(case, device=local_rank, mode=args.mode, rank=rank, nranks=world, nccl_id=nccl_id)
@@ -304,7 +306,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if fpb == 8 else "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "grid": [S, S, S], "num_global": NUM_GLOBAL, "num_local": NUM_LOCAL,
+            "config": {"workload": workload_name(args), "grid": [DX, DY, DZ], "num_global": NUM_GLOBAL, "num_local": NUM_LOCAL,
                        "sweeps_per_step": NUM_GLOBAL * 3 * NUM_LOCAL, "fluid_fraction": round(fluid, 4), "mode": args.mode,
                        "parallelism": f"x-slab x{world}", "residual": "every 10th step (reference driver cadence)",
                        "l2": f"inputs larger than L2: each field {ncells * fpb / 1e9:.2f} GB, 20 resident fields"},

@@ -254,7 +254,7 @@ struct Engine : cmc_adi3d {
 		params = *p;
 		dx = g->dx; dy = g->dy; dz = g->dz;
 		G.nx = g->dimx; G.ny = g->dimy; G.nz = g->dimz; G.gx = g->dimx; G.x0 = 0;
-		G.nzp = round_up(g->dimz, 16); G.plane = (long long)G.ny * G.nzp; G.total = (long long)(G.nx + 2) * G.plane;
+		G.nzp = round_up(g->dimz, 16) + (getenv("CMC_PAD_Z") ? atoi(getenv("CMC_PAD_Z")) : 0); G.plane = (long long)G.ny * G.nzp; G.total = (long long)(G.nx + 2) * G.plane;
 		nslabs_total = ntotal; rank = first_slab; nranks = ntotal;
 		int lo = 0, hi = 0;
 		for (int i = 0; i < nlocal; i++) {
@@ -489,7 +489,14 @@ struct Engine : cmc_adi3d {
 					if (!launch_x_coupled<FT>(A, stream, &launches)) return fail(CMC_ERR_UNSUPPORTED, "coupled x-sweep: unsupported slab shape");
 					done = true;
 				} else if (fast_ok(dir)) {
-					done = launch_fast_sweep<FT>(dir, A, stream, &launches);
+					// two data-movement variants of the same arithmetic (kernels_ring.cu / kernels_fast.cu).  Measured on
+					// B200 at 512^3 fp64 (profiles/r01_variants.md): the cp.async ring wins along z (contiguous lines,
+					// 4.99 vs 5.77 ms), the direct-load kernel along y (5.00 vs 5.66 ms) and x (7.05 vs 8.2 ms: rows a
+					// whole plane apart).  CMC_RING=<subset of "xyz"> overrides.
+					static const char *ring_env = getenv("CMC_RING");
+					const bool ring = ring_env ? strchr(ring_env, "xyz"[dir]) != nullptr : dir == CMC_DIR_Z;
+					if (ring) done = launch_ring_sweep<FT>(dir, A, stream, &launches);
+					if (!done) done = launch_fast_sweep<FT>(dir, A, stream, &launches);
 				}
 				if (done) std::swap(s->slot[CMC_LAYER_TEMP], s->spare);      // merged temp went to the other buffer
 				else {

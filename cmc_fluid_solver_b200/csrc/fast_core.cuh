@@ -54,17 +54,25 @@ struct FastConst {
 //   middle  : PCR over the GP / 2^L surviving rows (<= 8: three steps);
 //   backward: eliminated rows recover x from their two (already solved) neighbours.
 // The solutions of ALL rows end up in sol[q * STR + e].  Fully unrolled: GP, GS are compile-time.
+// Shared-memory footprint (elements): crs = NR * STR (publications; `sol` may alias it - the publications are not
+// read again once the PCR starts), pp = 2 * NR * (STR >> L) (PCR ping-pong, surviving rows only, compacted).
+template <int GP> struct RedGeom { static constexpr int L = GP > 8 ? (GP == 16 ? 1 : GP == 32 ? 2 : 3) : 0; };
+template <int NRHS, int GP, int NL> __host__ __device__ constexpr int reduced_scratch_elems() { return (2 + NRHS) * GP * NL + 2 * (2 + NRHS) * ((GP * NL) >> RedGeom<GP>::L); }
+
 template <typename FT, int NRHS, int GP, int GS, int NL>
 __device__ __forceinline__ void reduced_solve(FT *sys, FT *sol, int g, int e, FT Ain, FT Cin, const FT (&Din)[NRHS], FT (&X)[NRHS])
 {
 	constexpr int NR = 2 + NRHS;
 	constexpr int STR = GP * NL;
-	constexpr int L = GP > 8 ? (GP == 16 ? 1 : GP == 32 ? 2 : 3) : 0;
+	constexpr int L = RedGeom<GP>::L;
+	constexpr int STRC = STR >> L;       // compacted stride of the PCR arrays
 	FT A = Ain, Cc = Cin, D[NRHS];
 #pragma unroll
 	for (int q = 0; q < NRHS; q++) D[q] = Din[q];
 	FT *crs = sys;                       // CR publications: NR arrays (each row publishes once, at its own element)
-	FT *pp = sys + NR * STR;             // PCR ping-pong: 2 * NR arrays (only surviving rows used)
+	FT *pp = sys + NR * STR;             // PCR ping-pong: 2 * NR compacted arrays (surviving rows only)
+	// compacted element of a surviving row (g a multiple of 2^L): chunk index g >> L
+	const int ec = GS == 1 ? ((e - g) >> L) + (g >> L) : (g >> L) * GS + (e - g * GS);
 	int my_level = -1;                   // level at which this row was eliminated (-1: survives into the PCR)
 #pragma unroll
 	for (int lv = 0; lv < L; lv++) {
@@ -96,23 +104,23 @@ __device__ __forceinline__ void reduced_solve(FT *sys, FT *sol, int g, int e, FT
 	const bool survivor = my_level < 0 && (g & ((1 << L) - 1)) == 0;
 #pragma unroll
 	for (int st = 0; (1 << (L + st)) < GP; st++) {
-		const int s = 1 << (L + st);
-		FT *w = pp + (st & 1) * NR * STR;
+		const int s = 1 << (L + st), sc = 1 << st;      // stride in chunks / in surviving rows
+		FT *w = pp + (st & 1) * NR * STRC;
 		if (survivor) {
-			w[0 * STR + e] = A; w[1 * STR + e] = Cc;
+			w[0 * STRC + ec] = A; w[1 * STRC + ec] = Cc;
 #pragma unroll
-			for (int q = 0; q < NRHS; q++) w[(2 + q) * STR + e] = D[q];
+			for (int q = 0; q < NRHS; q++) w[(2 + q) * STRC + ec] = D[q];
 		}
 		__syncthreads();
 		if (survivor) {
 			const bool lo = g - s >= 0, hi = g + s < GP;
-			const FT *l = w + e - s * GS, *h = w + e + s * GS;
-			const FT Al = lo ? l[0 * STR] : FT(0), Cl = lo ? l[1 * STR] : FT(0);
-			const FT Ah = hi ? h[0 * STR] : FT(0), Ch = hi ? h[1 * STR] : FT(0);
+			const FT *l = w + ec - sc * GS, *h = w + ec + sc * GS;
+			const FT Al = lo ? l[0 * STRC] : FT(0), Cl = lo ? l[1 * STRC] : FT(0);
+			const FT Ah = hi ? h[0 * STRC] : FT(0), Ch = hi ? h[1 * STRC] : FT(0);
 			const FT r = rcp<FT>(FT(1) - A * Cl - Cc * Ah);
 #pragma unroll
 			for (int q = 0; q < NRHS; q++) {
-				const FT Dl = lo ? l[(2 + q) * STR] : FT(0), Dh = hi ? h[(2 + q) * STR] : FT(0);
+				const FT Dl = lo ? l[(2 + q) * STRC] : FT(0), Dh = hi ? h[(2 + q) * STRC] : FT(0);
 				D[q] = (D[q] - A * Dl - Cc * Dh) * r;
 			}
 			A = -A * Al * r;

@@ -16,6 +16,9 @@ void launch_thomas_batch(int nsys, int n, FT *a, FT *b, FT *c, FT *d, FT *x, cud
 bool fast_sweep_supported(const Layout &L, int dir);
 template <typename FT>
 bool launch_fast_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
+// kernels_ring.cu: the same sweep as persistent CTAs fed by a cp.async shared-memory ring (MODE 0 lines only)
+template <typename FT>
+bool launch_ring_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
 // partitioned x-sweep (slab-decomposed grid): spike pass, interface solve, coupled sweep
 template <typename FT>
 bool launch_x_spike(const SweepArgs<FT> &A, cudaStream_t s, long long *launches);

@@ -38,7 +38,7 @@ namespace cmc {
 // MODE 2: the complete sweep with the neighbours' (now known) adjacent-row solutions folded into the first /
 //         last row of the slab.
 template <typename FT, int DIR, int GP, int NL, int MODE>
-__global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_sweep(const SweepArgs<FT> A, const FastConst<FT> K, long long *trace, const int one)
+__global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_sweep(const SweepArgs<FT> A, const FastConst<FT> K, long long *trace, const int one, const int pf_dist)
 {
 	static_assert(MODE == 0 || DIR == 0, "slab coupling exists along x only");
 #define CMC_MARK(k) do { if (trace) { __syncthreads(); if (threadIdx.x == 0) trace[(size_t)blockIdx.x * 16 + (k)] = clock64(); } } while (0)
@@ -100,6 +100,26 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 		// rows -1 and n exist for a slab inside a decomposed grid (halo planes): its first / last row can be interior
 		off_lo = (int)base + max(r0 - 1, MODE != 0 ? -1 : 0) * (int)stride;
 		off_hi = (int)base + min(r0 + M, MODE != 0 ? n : n - 1) * (int)stride;
+	}
+	// ---- L2 prefetch of the inputs of the CTA that will take this CTA's place in the next wave ------------------
+	// (CTAs are scheduled in blockIdx order; the CTA `pf_dist` ahead starts roughly when this one retires.)  The
+	// requests cost no registers or shared memory and keep HBM streaming while this CTA is in its solve phases.
+	if (pf_dist > 0 && blockIdx.x + pf_dist < gridDim.x) {
+		const unsigned fb = blockIdx.x + pf_dist;
+		long long fbase;
+		if (DIR == 0) { const int kt = (L.nz + NL - 1) / NL; fbase = L.idx(0, fb / kt, (int)(fb % kt) * NL); }
+		else if (DIR == 1) { const int kt = (L.nz + NL - 1) / NL; fbase = L.idx(fb / kt, 0, (int)(fb % kt) * NL); }
+		else { const int jt = (L.ny + NL - 1) / NL; fbase = L.idx(fb / jt, min((int)(fb % jt) * NL + l, L.ny - 1), 0); }
+		// one request per 64-byte row segment: Z - this thread's chunk; X, Y - lane l of a row group takes row l
+#pragma unroll
+		for (int rep = 0; rep < (DIR == 2 ? 1 : M / NL); rep++) {
+			const long long po = fbase + (DIR == 2 ? (long long)min(r0, L.nzp - M) : (long long)min(r0 + l + rep * NL, n - 1) * stride);
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(A.cur[q] + po));
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(A.temp[q] + po));
+			}
+		}
 	}
 	unsigned rowmask = 0;           // rows of this chunk that exist
 #pragma unroll
@@ -246,15 +266,20 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 			reduced_solve<FT, 3, GP, GS, NL>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, E);    // every row's solution -> sol[]
 	}
 	CMC_MARK(2);   // phase V reduced solve done
-	// back substitution, store u, v, w and the relaxed linearisation layer
+	// back substitution in place (dp[q] <- x: retires cp / lp early), then store u, v, w and the relaxed
+	// linearisation layer
 #pragma unroll
 	for (int q = 0; q < (MODE == 1 ? 0 : 3); q++) {
 		const FT El = g > 0 ? sol[q * STR + e - GS] : FT(0);
-		FT x[M], tq[M];
-		if (one) load8<FT, DIR>(A.temp[q], off, tq);
-		x[M - 1] = E[q];
+		dp[q][M - 1] = E[q];
 #pragma unroll
-		for (int i = M - 2; i >= 0; i--) x[i] = dp[q][i] - lp[i] * El - cp[i] * x[i + 1];
+		for (int i = M - 2; i >= 0; i--) dp[q][i] = dp[q][i] - lp[i] * El - cp[i] * dp[q][i + 1];
+	}
+#pragma unroll
+	for (int q = 0; q < (MODE == 1 ? 0 : 3); q++) {
+		FT (&x)[M] = dp[q];
+		FT tq[M];
+		if (one) load8<FT, DIR>(A.temp[q], off, tq);
 		if (holes) {                      // merge those with the OLD value of `next` (MergeFieldTo reads whatever is there)
 #pragma unroll
 			for (int i = 0; i < M; i++)
@@ -278,46 +303,55 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 		FT diss[M], V[M], cT[M];
 		load8<FT, DIR>(A.cur[3], off, cT);
 		{
-			// dissipation function of the sweep direction (TimeLayer3D.h:554-588): derivatives along the line of
-			// u, v, w plus the two cross-line derivatives of the component aligned with the sweep
+			// dissipation function of the sweep direction (TimeLayer3D.h:554-588), accumulated component by component:
 			//   X: 2 u_x^2 + v_x^2 + w_x^2 + v_x u_y + w_x u_z ; Y: u_y^2 + 2 v_y^2 + w_y^2 + u_y v_x + w_y v_z ;
 			//   Z: u_z^2 + v_z^2 + 2 w_z^2 + u_z w_x + v_z w_y
-			FT f[M], dd[3][M];
-#pragma unroll
-			for (int q = 0; q < 3; q++) {
-				load8<FT, DIR>(A.temp[q], off, f);
-				const FT lo = A.temp[q][off_lo], hi = A.temp[q][off_hi];
-#pragma unroll
-				for (int i = 0; i < M; i++) dd[q][i] = cdiff<FT>(f, lo, hi, i, K.inv2h);
-				if (q == DIR) {
-#pragma unroll
-					for (int i = 0; i < M; i++) V[i] = f[i];
-				}
-			}
-			// cross-line neighbours of temp[DIR]; lines next to an interior cell always exist, for everything else
-			// the (clamped, valid) addresses just deliver values that are never selected
+			// c1, c2: the two cross-line derivatives of temp[DIR]; c1 pairs with component QA, c2 with QB.  Lines next
+			// to an interior cell always exist, for everything else the (clamped, valid) addresses just deliver values
+			// that are never selected
+			constexpr int QA = DIR == 0 ? 1 : 0, QB = DIR == 2 ? 1 : 2;
 			const long long s1 = DIR == 0 ? L.nzp : L.plane, s2 = DIR == 2 ? L.nzp : 1;
 			const FT *tp = A.temp[DIR];
-			FT p1[M], m1[M], p2[M], m2[M];
-#pragma unroll
-			for (int i = 0; i < M; i++) diss[i] = FT(0);
-			if (any_int) {
+			FT c1[M], c2[M];
+			{
+				FT p1[M], m1[M];
 				load8<FT, DIR>(tp + s1, off, p1); load8<FT, DIR>(tp - s1, off, m1);
+#pragma unroll
+				for (int i = 0; i < M; i++) c1[i] = (p1[i] - m1[i]) * K.inv2h1;
+			}
+			{
+				FT p2[M], m2[M];
 				if (DIR == 2) { load8<FT, DIR>(tp + s2, off, p2); load8<FT, DIR>(tp - s2, off, m2); }
 				else {          // +-1 element along k: unaligned, scalar
 #pragma unroll
 					for (int i = 0; i < M; i++) { p2[i] = tp[off[i] + 1]; m2[i] = tp[off[i] - 1]; }
 				}
 #pragma unroll
+				for (int i = 0; i < M; i++) c2[i] = (p2[i] - m2[i]) * K.inv2h2;
+			}
+#pragma unroll
+			for (int i = 0; i < M; i++) diss[i] = FT(0);
+#pragma unroll
+			for (int q = 0; q < 3; q++) {
+				FT f[M];
+				load8<FT, DIR>(A.temp[q], off, f);
+				const FT lo = A.temp[q][off_lo], hi = A.temp[q][off_hi];
+#pragma unroll
 				for (int i = 0; i < M; i++) {
-					const FT c1 = (p1[i] - m1[i]) * K.inv2h1, c2 = (p2[i] - m2[i]) * K.inv2h2;
-					const FT du = dd[0][i], dv = dd[1][i], dw = dd[2][i];
-					FT s;
-					if (DIR == 0) s = 2 * du * du + dv * dv + dw * dw + dv * c1 + dw * c2;
-					else if (DIR == 1) s = du * du + 2 * dv * dv + dw * dw + du * c1 + dw * c2;
-					else s = du * du + dv * dv + 2 * dw * dw + du * c1 + dv * c2;
-					diss[i] = s;
+					const FT d = cdiff<FT>(f, lo, hi, i, K.inv2h);
+					FT w = q == DIR ? d + d : d;
+					if (q == QA) w += c1[i];
+					if (q == QB) w += c2[i];
+					diss[i] += d * w;
 				}
+				if (q == DIR) {
+#pragma unroll
+					for (int i = 0; i < M; i++) V[i] = f[i];
+				}
+			}
+			if (!any_int) {
+#pragma unroll
+				for (int i = 0; i < M; i++) diss[i] = FT(0);
 			}
 		}
 #pragma unroll
@@ -414,10 +448,9 @@ static size_t fast_smem_bytes(int GP, int NL, int nrhs = 3) { return sizeof(FT) 
 // (4 lines) so that one CTA per SM owns the whole register file: every load of a phase is in flight at once.
 constexpr int lines_per_cta(int GP) { return 8; }
 
-template <typename FT, int DIR, int GP, int MODE = 0>
+template <typename FT, int DIR, int GP, int MODE = 0, int NL = lines_per_cta(GP)>
 static unsigned launch_one(const SweepArgs<FT> &A, cudaStream_t s, long long *trace, bool dry)
 {
-	constexpr int NL = lines_per_cta(GP);
 	const Layout &L = A.L;
 	unsigned grid;
 	if (DIR == 0) grid = (unsigned)L.ny * (unsigned)((L.nz + NL - 1) / NL);
@@ -431,7 +464,34 @@ static unsigned launch_one(const SweepArgs<FT> &A, cudaStream_t s, long long *tr
 		attr_set = true;
 	}
 	FastConst<FT> K; K.init(A, DIR);
-	k_fast_sweep<FT, DIR, GP, NL, MODE><<<grid, GP * NL, smem, s>>>(A, K, trace, 1);
+	static const int pf_env = getenv("CMC_PF_DIST") ? atoi(getenv("CMC_PF_DIST")) : -1;
+	int pf = pf_env < 0 ? 0 : pf_env;     // off by default: measured slower (the SMs load in step; extra requests only queue up)
+	if (pf_env == -2) {      // CMC_PF_DIST=-2: one full wave of resident CTAs
+		static int per_sm = 0, sms = 0;
+		if (!per_sm) {
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_sweep<FT, DIR, GP, NL, MODE>, GP * NL, smem);
+			int dev = 0; cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+			if (per_sm < 1) per_sm = 1;
+		}
+		pf = per_sm * sms;
+	}
+	// x-lines: rows of a tile are a whole plane apart, so every 64-byte row segment is its own DRAM page visit; CTAs of
+	// a thread-block cluster are co-scheduled and walk neighbouring k-tiles in step, which turns those visits into
+	// 64 * cluster bytes per page (CMC_CLUSTER_X / _Y / _Z = 1, 2, 4, 8; experiments)
+	static const int cl_env[3] = {getenv("CMC_CLUSTER_X") ? atoi(getenv("CMC_CLUSTER_X")) : 1, getenv("CMC_CLUSTER_Y") ? atoi(getenv("CMC_CLUSTER_Y")) : 1,
+	                              getenv("CMC_CLUSTER_Z") ? atoi(getenv("CMC_CLUSTER_Z")) : 1};
+	const int cl = cl_env[DIR];
+	if (cl > 1 && grid % cl == 0) {
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GP * NL); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+		cudaLaunchAttribute at[1];
+		at[0].id = cudaLaunchAttributeClusterDimension;
+		at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+		cfg.attrs = at; cfg.numAttrs = 1;
+		cudaLaunchKernelEx(&cfg, k_fast_sweep<FT, DIR, GP, NL, MODE>, A, K, trace, 1, pf);
+	} else
+		k_fast_sweep<FT, DIR, GP, NL, MODE><<<grid, GP * NL, smem, s>>>(A, K, trace, 1, pf);
 	return grid;
 }
 
@@ -443,7 +503,10 @@ static unsigned launch_dir(int GP, const SweepArgs<FT> &A, cudaStream_t s, long 
 	case 8: return launch_one<FT, DIR, 8>(A, s, trace, dry);
 	case 16: return launch_one<FT, DIR, 16>(A, s, trace, dry);
 	case 32: return launch_one<FT, DIR, 32>(A, s, trace, dry);
-	default: return launch_one<FT, DIR, 64>(A, s, trace, dry);
+	default: {
+		static const bool nl4 = getenv("CMC_NL64") && atoi(getenv("CMC_NL64")) == 4;
+		return nl4 ? launch_one<FT, DIR, 64, 0, 4>(A, s, trace, dry) : launch_one<FT, DIR, 64>(A, s, trace, dry);
+	}
 	}
 }
 
