@@ -59,6 +59,7 @@ struct cmc_adi3d {
 	virtual int step_prologue() = 0;
 	virtual int solve_direction(int dir, double dt, int nl, int cur_layer, int next_layer) = 0;
 	virtual int eval_div_error(int layer, double *err) = 0;
+	virtual int exchange_kind() const = 0;
 
 	int device = 0, fp = 8;
 	int rank = 0, nranks = 1;       // position of this handle's (first) slab among all slabs of the grid
@@ -135,18 +136,24 @@ struct Slab {
 	FT *d_outvel = nullptr;
 	double *d_outT = nullptr;
 	size_t out_cap = 0;
-	// partitioned x-sweep exchange buffers: [peer][16 | 8][lpo]
+	// partitioned x-sweep exchange buffers: [peer][16 | 8][lpo].  The *_recv tables are filled by the other slabs'
+	// kernels directly (they live in the arena); the *_send staging buffers exist only for the NCCL transport.
 	FT *xcoef_send = nullptr, *xcoef_recv = nullptr, *xbnd_send = nullptr, *xbnd_recv = nullptr;
+	// exchange arena: everything another slab stores into - the 20 field buffers (guard planes), the two interface
+	// tables and the flag words - in ONE allocation with the same layout on every rank, so that one CUDA IPC mapping
+	// per peer makes all of it addressable over NVLink
+	char *arena = nullptr;
+	size_t arena_bytes = 0, flag_off = 0;
 	long long bytes = 0;
 	static const int kMaxErrBlocks = 148 * 8;
 
 	~Slab()
 	{
 		cudaSetDevice(device);
-		for (auto &l : field) for (auto &p : l) if (p) cudaFree(p);
+		if (arena) cudaFree(arena);
 		for (auto &p : nodev) if (p) cudaFree(p);
 		for (auto &p : role) if (p) cudaFree(p);
-		void *misc[] = {cv, cT, d_partials, d_err2, d_segcount, d_outvel, d_outT, ncode, xcoef_send, xcoef_recv, xbnd_send, xbnd_recv};
+		void *misc[] = {cv, cT, d_partials, d_err2, d_segcount, d_outvel, d_outT, ncode, xcoef_send, xbnd_send};
 		for (void *p : misc) if (p) cudaFree(p);
 	}
 
@@ -164,9 +171,22 @@ struct Slab {
 		device = dev; stream = s; G = g; index = idx;
 		L = G; L.nx = nx; L.x0 = x0; L.total = (long long)(nx + 2) * L.plane;
 		int rc;
-		for (int l = 0; l < 5; l++)
-			for (int q = 0; q < 4; q++)
-				if ((rc = dalloc(field[l][q], (size_t)L.total))) return rc;
+		{
+			auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+			const size_t fb = up(sizeof(FT) * (size_t)L.total), lpo = lines_per_owner(nslabs);
+			const size_t cb = nslabs > 1 ? up(sizeof(FT) * lpo * 16 * nslabs) : 0, bb = nslabs > 1 ? up(sizeof(FT) * lpo * 8 * nslabs) : 0;
+			flag_off = 20 * fb + cb + bb;
+			arena_bytes = flag_off + 256;
+			CU_TRY(cudaMalloc((void **)&arena, arena_bytes));
+			CU_TRY(cudaMemsetAsync(arena, 0, arena_bytes, stream));
+			bytes += (long long)arena_bytes;
+			for (int l = 0; l < 5; l++)
+				for (int q = 0; q < 4; q++) field[l][q] = reinterpret_cast<FT *>(arena + (size_t)(l * 4 + q) * fb);
+			if (nslabs > 1) {
+				xcoef_recv = reinterpret_cast<FT *>(arena + 20 * fb);
+				xbnd_recv = reinterpret_cast<FT *>(arena + 20 * fb + cb);
+			}
+		}
 		for (int q = 0; q < 4; q++) if ((rc = dalloc(nodev[q], (size_t)L.total))) return rc;
 		for (int d = 0; d < 3; d++) if ((rc = dalloc(role[d], (size_t)L.total))) return rc;
 		if ((rc = dalloc(cv, (size_t)L.total))) return rc;
@@ -177,9 +197,7 @@ struct Slab {
 		if (nslabs > 1) {
 			const size_t lpo = lines_per_owner(nslabs);
 			if ((rc = dalloc(xcoef_send, lpo * 16 * nslabs))) return rc;
-			if ((rc = dalloc(xcoef_recv, lpo * 16 * nslabs))) return rc;
 			if ((rc = dalloc(xbnd_send, lpo * 8 * nslabs))) return rc;
-			if ((rc = dalloc(xbnd_recv, lpo * 8 * nslabs))) return rc;
 		}
 		return CMC_OK;
 	}
@@ -233,12 +251,21 @@ struct Engine : cmc_adi3d {
 	double diffError = 0.0;
 	bool err_pending = false;
 	double *h_err2 = nullptr;          // pinned: [2 * nlocal] (sum, count) per local slab
+	// exchanges as stores into the other slabs' buffers (see SweepArgs::push_*): always when all slabs share this
+	// device (emulation), and between processes once every rank has mapped every other rank's arena (peer memory)
+	PeerMap pm;
+	bool p2p = false;
+	unsigned epoch = 0;                // ordering of peer stores: last epoch this rank has published
+	int *d_timeout = nullptr;
+	bool halos_dirty = true;           // the guard planes of `cur` may not match the neighbours' boundary planes
 
 	~Engine() override
 	{
 		cudaSetDevice(device);
 		if (stream) cudaStreamSynchronize(stream);
 		spans_collect();
+		if (p2p) peer_unmap(&pm);
+		if (d_timeout) cudaFree(d_timeout);
 		for (auto *s : slabs) delete s;
 		if (h_err2) cudaFreeHost(h_err2);
 		if (nccl) nccl_destroy(nccl);
@@ -246,6 +273,33 @@ struct Engine : cmc_adi3d {
 	}
 
 	bool multi() const { return nslabs_total > 1; }
+	int exchange_kind() const override { return !multi() ? 0 : !push_mode() ? 1 : nccl ? 3 : 2; }
+	bool push_mode() const { return multi() && (!nccl || p2p); }
+
+	// the address, in the slab that holds slab index `r`, of the buffer that is `mine` in slab `s`
+	FT *in_slab(Slab<FT> *s, int r, FT *mine) const
+	{
+		const size_t o = (size_t)((char *)mine - s->arena);
+		if (nccl) return reinterpret_cast<FT *>((char *)pm.base[r] + o);
+		return reinterpret_cast<FT *>(slabs[r]->arena + o);
+	}
+
+	// peer ordering (processes): publish `epoch` after this rank's kernel / wait for the ranks in `mask`
+	void publish()
+	{
+		if (!p2p) return;
+		epoch++;
+		peer_signal(pm, slabs[0]->flag_off, epoch, stream);
+		launches++;
+	}
+	void await(unsigned mask)
+	{
+		if (!p2p) return;
+		peer_wait(pm, slabs[0]->flag_off, mask, epoch, d_timeout, stream);
+		launches++;
+	}
+	unsigned neighbour_mask() const { return (rank > 0 ? 1u << (rank - 1) : 0u) | (rank + 1 < nranks ? 1u << (rank + 1) : 0u); }
+	unsigned all_mask() const { return (nranks >= 32 ? ~0u : (1u << nranks) - 1u) & ~(1u << rank); }
 
 	int init(const cmc_grid_desc *g, const cmc_fluid_params *p, int first_slab, int nlocal, int ntotal)
 	{
@@ -272,7 +326,14 @@ struct Engine : cmc_adi3d {
 		L = G; L.x0 = lo; L.nx = hi - lo; L.total = (long long)(L.nx + 2) * L.plane;
 		CU_TRY(cudaHostAlloc((void **)&h_err2, 2 * sizeof(double) * nlocal, cudaHostAllocDefault));
 		memset(h_err2, 0, 2 * sizeof(double) * nlocal);
+		CU_TRY(cudaMalloc((void **)&d_timeout, sizeof(int)));
+		CU_TRY(cudaMemsetAsync(d_timeout, 0, sizeof(int), stream));
 		CU_TRY(cudaStreamSynchronize(stream));
+		if (nccl) {
+			// peer memory needs the same arena layout on every rank (equal slabs); CMC_P2P=0 keeps the NCCL transport
+			const bool want = !(getenv("CMC_P2P") && atoi(getenv("CMC_P2P")) == 0) && G.nx % ntotal == 0;
+			if (want) p2p = peer_map_arenas(nccl, slabs[0]->arena, slabs[0]->arena_bytes, rank, nranks, &pm, stream) == 0;
+		}
 		return CMC_OK;
 	}
 
@@ -361,6 +422,7 @@ struct Engine : cmc_adi3d {
 			if (rc) return rc;
 		}
 		CU_TRY(cudaStreamSynchronize(stream));
+		halos_dirty = true;
 		have_nodes = true; have_lines = false;
 		diffError = 0.0; err_pending = false;
 		return CMC_OK;
@@ -440,6 +502,29 @@ struct Engine : cmc_adi3d {
 		A.cv = s->cv; A.cT = s->cT;
 		A.xcoef = s->xcoef_send; A.xbnd = s->xbnd_recv; A.lpo = (int)s->lines_per_owner(nslabs_total);
 		A.extra_merge = 0;
+		for (int q = 0; q < 4; q++) A.push_lo[q] = A.push_hi[q] = A.pushn_lo[q] = A.pushn_hi[q] = nullptr;
+		for (int r = 0; r < MAX_SLABS; r++) A.xcoef_to[r] = nullptr;
+		if (multi()) {
+			const size_t lpo = (size_t)A.lpo;
+			const int me = s->index;
+			if (push_mode()) {
+				// all slabs have the same shape here (emulation splits evenly or the caller's shapes are checked in build_lines)
+				const long long hi_plane = s->L.idx(s->L.nx, 0, 0), lo_plane = s->L.idx(-1, 0, 0);
+				for (int q = 0; q < 4; q++) {
+					if (me > 0) {
+						A.push_lo[q] = in_slab(s, me - 1, s->field[s->spare][q]) + hi_plane;
+						A.pushn_lo[q] = in_slab(s, me - 1, s->field[s->slot[next_layer]][q]) + hi_plane;
+					}
+					if (me + 1 < nslabs_total) {
+						A.push_hi[q] = in_slab(s, me + 1, s->field[s->spare][q]) + lo_plane;
+						A.pushn_hi[q] = in_slab(s, me + 1, s->field[s->slot[next_layer]][q]) + lo_plane;
+					}
+				}
+				for (int r = 0; r < nslabs_total; r++) A.xcoef_to[r] = in_slab(s, r, s->xcoef_recv) + (size_t)me * 16 * lpo;
+			} else {
+				for (int r = 0; r < nslabs_total; r++) A.xcoef_to[r] = s->xcoef_send + (size_t)r * 16 * lpo;
+			}
+		}
 		return A;
 	}
 
@@ -448,38 +533,54 @@ struct Engine : cmc_adi3d {
 	// AdiSolver3D::SolveDirection (AdiSolver3D.cpp:564-666): num_local x { solve every line for u,v,w,T ; merge }
 	// temp_is_cur: the linearisation layer still equals `cur` (first sweep of a step; the temp<-cur copy is folded
 	// away).  fold_post_merge: the last local iteration also applies the post-X MergeLayerTo (AdiSolver3D.cpp:354).
-	int solve_direction_impl(int dir, FT dt, int nl, int cur_layer, int next_layer, bool temp_is_cur = false, bool fold_post_merge = false)
+	// halos_ready: the guard planes the sweeps read are already valid (time_step in push mode: every sweep stores its
+	// boundary planes into the neighbours' guard planes itself)
+	int solve_direction_impl(int dir, FT dt, int nl, int cur_layer, int next_layer, bool temp_is_cur = false, bool fold_post_merge = false,
+	                         bool halos_ready = false)
 	{
 		for (int it = 0; it < nl; it++) {
 			const bool t_is_c = temp_is_cur && it == 0;
-			int rc = halo_exchange(t_is_c ? CMC_LAYER_CUR : CMC_LAYER_TEMP);   // x-stencils of the sweep read the neighbours' planes
-			if (rc) return rc;
+			int rc;
+			if (!(push_mode() && halos_ready))
+				if ((rc = halo_exchange(t_is_c ? CMC_LAYER_CUR : CMC_LAYER_TEMP))) return rc;   // x-stencils of the sweep read the neighbours' planes
 			const bool coupled = multi() && dir == CMC_DIR_X;
 			if (multi() && mode != CMC_MODE_FAST)
 				return fail(CMC_ERR_UNSUPPORTED, "slab-decomposed runs support CMC_MODE_FAST only");
+			// the neighbours have finished their previous sweep: their stores into this slab's guard planes are complete,
+			// and they no longer read the guard planes this sweep is about to overwrite on their side
+			await(neighbour_mask());
 			if (coupled) {
-				// partitioned solve along the decomposed axis: spike pass -> all-to-all -> interface solve ->
-				// all-to-all -> coupled sweep.  (replaces LaunchSolveSegments_X, AdiSolver3D.cu:524-640)
+				// partitioned solve along the decomposed axis: spike pass -> coefficients to the line owners -> interface
+				// solve -> neighbour values back -> coupled sweep.  (replaces LaunchSolveSegments_X, AdiSolver3D.cu:524-640)
 				span_begin(CMC_TIMING_SWEEP_X);
 				for (auto *s : slabs) {
 					SweepArgs<FT> A = sweep_args(s, dir, dt, cur_layer, next_layer);
+					if (t_is_c)
+						for (int q = 0; q < 4; q++) A.temp[q] = s->field[s->slot[CMC_LAYER_CUR]][q];
 					if (!launch_x_spike<FT>(A, stream, &launches)) return fail(CMC_ERR_UNSUPPORTED, "x-spike pass: unsupported slab shape");
 				}
 				span_end();
 				const size_t lpo = slabs[0]->lines_per_owner(nslabs_total);
-				if ((rc = all_to_all(&Slab<FT>::xcoef_send, &Slab<FT>::xcoef_recv, lpo * 16))) return rc;
+				if (push_mode()) { span_begin(CMC_TIMING_COMM); publish(); await(all_mask()); span_end(); }
+				else if ((rc = all_to_all(&Slab<FT>::xcoef_send, &Slab<FT>::xcoef_recv, lpo * 16))) return rc;
 				span_begin(CMC_TIMING_SWEEP_X);
 				const long long nlines = (long long)G.ny * G.nz;
 				for (auto *s : slabs) {
 					const long long first = (long long)s->index * (long long)lpo;
 					const int owned = (int)std::max(0ll, std::min((long long)lpo, nlines - first));
-					launch_x_interface<FT>(nslabs_total, (int)lpo, owned, s->xcoef_recv, s->xbnd_send, stream, &launches);
+					FT *to[MAX_SLABS] = {};
+					for (int r = 0; r < nslabs_total; r++)
+						to[r] = push_mode() ? in_slab(s, r, s->xbnd_recv) + (size_t)s->index * 8 * lpo : s->xbnd_send + (size_t)r * 8 * lpo;
+					launch_x_interface<FT>(nslabs_total, (int)lpo, owned, s->xcoef_recv, to, stream, &launches);
 				}
 				span_end();
-				if ((rc = all_to_all(&Slab<FT>::xbnd_send, &Slab<FT>::xbnd_recv, lpo * 8))) return rc;
+				if (push_mode()) { span_begin(CMC_TIMING_COMM); publish(); await(all_mask()); span_end(); }
+				else if ((rc = all_to_all(&Slab<FT>::xbnd_send, &Slab<FT>::xbnd_recv, lpo * 8))) return rc;
 			}
 			span_begin(CMC_TIMING_SWEEP_X + dir);
-			for (auto *s : slabs) {
+			std::vector<char> swapped(slabs.size(), 0);
+			for (size_t si = 0; si < slabs.size(); si++) {
+				Slab<FT> *s = slabs[si];
 				SweepArgs<FT> A = sweep_args(s, dir, dt, cur_layer, next_layer);
 				if (t_is_c)
 					for (int q = 0; q < 4; q++) A.temp[q] = s->field[s->slot[CMC_LAYER_CUR]][q];
@@ -498,13 +599,17 @@ struct Engine : cmc_adi3d {
 					if (ring) done = launch_ring_sweep<FT>(dir, A, stream, &launches);
 					if (!done) done = launch_fast_sweep<FT>(dir, A, stream, &launches);
 				}
-				if (done) std::swap(s->slot[CMC_LAYER_TEMP], s->spare);      // merged temp went to the other buffer
+				if (done) swapped[si] = 1;                               // merged temp went to the other buffer
 				else {
 					launch_exact_sweep<FT>(dir, A, stream, &launches);
 					launch_merge<FT>(s->L, s->role[dir], s->clayer(next_layer), s->layer(CMC_LAYER_TEMP), stream, &launches);
 				}
 			}
+			// (after ALL slabs are launched: the push targets above are computed from the neighbours' buffer roles)
+			for (size_t si = 0; si < slabs.size(); si++)
+				if (swapped[si]) std::swap(slabs[si]->slot[CMC_LAYER_TEMP], slabs[si]->spare);
 			span_end();
+			publish();
 		}
 		return CMC_OK;
 	}
@@ -525,10 +630,14 @@ struct Engine : cmc_adi3d {
 		return CMC_OK;
 	}
 
-	int enqueue_div_error(int logical_layer)
+	int enqueue_div_error(int logical_layer, bool halos_ready = false)
 	{
-		int rc = halo_exchange(logical_layer);       // the residual reads the i-1 plane (TimeLayer3D.h:614-621)
-		if (rc) return rc;
+		// the residual reads the i-1 plane (TimeLayer3D.h:614-621)
+		if (push_mode() && halos_ready) await(neighbour_mask());
+		else {
+			int rc = halo_exchange(logical_layer);
+			if (rc) return rc;
+		}
 		for (size_t i = 0; i < slabs.size(); i++) {
 			Slab<FT> *s = slabs[i];
 			const int l = s->slot[logical_layer];
@@ -570,10 +679,18 @@ struct Engine : cmc_adi3d {
 		const bool fold_copy = ng > 0 && nl > 0 && fast_ok(CMC_DIR_Z);
 		const bool fold_merge = nl > 0 && (multi() || fast_ok(CMC_DIR_X));
 		if ((rc = step_prologue_impl(!fold_copy))) return rc;
+		// push mode: every sweep stores its boundary planes into the neighbours' guard planes itself (temp' always,
+		// `next` by the x-sweep, which makes the guard planes of the next step's `cur` valid as well), so one explicit
+		// exchange is needed only when something else touched the layers (first step, write_field, GetLayer)
+		const bool pushing = push_mode() && fold_copy && fold_merge;
+		if (pushing && halos_dirty) {
+			if ((rc = halo_exchange(CMC_LAYER_CUR))) return rc;
+		}
+		halos_dirty = !pushing;
 		for (int it = 0; it < ng; it++) {                          // :335-358
-			if ((rc = solve_direction_impl(CMC_DIR_Z, dt, nl, CMC_LAYER_CUR, CMC_LAYER_NEXT, fold_copy && it == 0))) return rc;
-			if ((rc = solve_direction_impl(CMC_DIR_Y, dt, nl, CMC_LAYER_NEXT, CMC_LAYER_HALF))) return rc;
-			if ((rc = solve_direction_impl(CMC_DIR_X, dt, nl, CMC_LAYER_HALF, CMC_LAYER_NEXT, false, fold_merge))) return rc;
+			if ((rc = solve_direction_impl(CMC_DIR_Z, dt, nl, CMC_LAYER_CUR, CMC_LAYER_NEXT, fold_copy && it == 0, false, pushing))) return rc;
+			if ((rc = solve_direction_impl(CMC_DIR_Y, dt, nl, CMC_LAYER_NEXT, CMC_LAYER_HALF, false, false, pushing))) return rc;
+			if ((rc = solve_direction_impl(CMC_DIR_X, dt, nl, CMC_LAYER_HALF, CMC_LAYER_NEXT, false, fold_merge, pushing))) return rc;
 			if (!fold_merge) {
 				// update non-linear layer once more (:354): temp = (temp + next) / 2 on NODE_IN
 				span_begin(CMC_TIMING_MERGE);
@@ -584,7 +701,7 @@ struct Engine : cmc_adi3d {
 		}
 		if (ce) {
 			span_begin(CMC_TIMING_RESIDUAL);
-			rc = enqueue_div_error(CMC_LAYER_NEXT);
+			rc = enqueue_div_error(CMC_LAYER_NEXT, pushing);
 			span_end();
 			if (rc) return rc;
 		}
@@ -609,6 +726,11 @@ struct Engine : cmc_adi3d {
 		if (rc) return rc;
 		CU_TRY(cudaStreamSynchronize(stream));
 		CU_TRY(cudaGetLastError());
+		if (p2p) {
+			int t = 0;
+			CU_TRY(cudaMemcpy(&t, d_timeout, sizeof t, cudaMemcpyDeviceToHost));
+			if (t) return fail(CMC_ERR_COMM, "a peer rank did not publish its epoch within 10 s (peer_wait timed out)");
+		}
 		if (err) *err = diffError;
 		if (diffError > CMC_ERR_THRESHOLD) {
 			char buf[96];
@@ -624,6 +746,7 @@ struct Engine : cmc_adi3d {
 		if (dir < 0 || dir > 2 || cur_layer < 0 || cur_layer > 3 || next_layer < 0 || next_layer > 3 || cur_layer == next_layer)
 			return fail(CMC_ERR_INVALID, "solve_direction: bad direction or layers");
 		CU_TRY(cudaSetDevice(device));
+		halos_dirty = true;
 		int rc = solve_direction_impl(dir, (FT)dt, nl, cur_layer, next_layer);
 		if (rc) return rc;
 		CU_TRY(cudaStreamSynchronize(stream));
@@ -652,6 +775,7 @@ struct Engine : cmc_adi3d {
 		if (oy == 0) oy = G.ny;
 		if (oz == 0) oz = G.nz;
 		if (ox < 0 || oy < 0 || oz < 0) return fail(CMC_ERR_INVALID, "get_layer: negative output dims");
+		halos_dirty = true;                // Clear() below rewrites the NODE_OUT cells of a layer
 		const size_t outN = (size_t)ox * oy * oz, rowN = (size_t)oy * oz;
 		span_begin(CMC_TIMING_READBACK);
 		std::vector<int> lo(nslabs_total, ox), hi(nslabs_total, 0);
@@ -735,6 +859,7 @@ struct Engine : cmc_adi3d {
 	{
 		if (logical < 0 || logical > 3 || var < 0 || var > 3) return fail(CMC_ERR_INVALID, "write_field: bad layer/var");
 		CU_TRY(cudaSetDevice(device));
+		halos_dirty = true;
 		for (auto *s : slabs) {
 			FT *dst = s->field[s->slot[logical]][var] + s->L.idx(0, 0, 0);
 			const FT *sp = (const FT *)src + (size_t)(s->L.x0 - L.x0) * G.ny * G.nz;
@@ -931,6 +1056,7 @@ int cmc_adi3d_get_option(const cmc_adi3d *h, const char *key, int64_t *value)
 	if (!strcmp(key, "mode")) { *value = h->mode; return CMC_OK; }
 	if (!strcmp(key, "fold_boundaries")) { *value = h->fold_boundaries; return CMC_OK; }
 	if (!strcmp(key, "nzp")) { *value = h->L.nzp; return CMC_OK; }
+	if (!strcmp(key, "exchange")) { *value = h->exchange_kind(); return CMC_OK; }   // 0 none, 1 NCCL send/recv, 2 fused stores (same device), 3 fused stores (peer memory)
 	if (!strcmp(key, "shared_free_cells")) { *value = h->shared_free[0] + h->shared_free[1] + h->shared_free[2]; return CMC_OK; }
 	return fail(CMC_ERR_INVALID, std::string("get_option: unknown key ") + key);
 }

@@ -14,6 +14,8 @@
 
 namespace cmc {
 
+constexpr int MAX_SLABS = 16;   // slabs (GPUs) of one grid
+
 struct Layout {
 	int nx, ny, nz;       // cells of this slab (nx = local x-planes), reference dimx/dimy/dimz
 	int nzp;              // padded z-line length
@@ -62,6 +64,15 @@ struct SweepArgs {
 	const FT *xbnd;          // MODE 2 input:  [owner][8][lpo] solutions of the neighbours' adjacent rows
 	int lpo;                 // lines per owner rank of the interface solve
 	int extra_merge;         // fast mode: apply the relaxation twice (folds the post-X MergeLayerTo, AdiSolver3D.cpp:354)
+	// ---- slab-decomposed runs: exchanges fused into the sweeps as stores into the other slabs' buffers (peer memory
+	// over NVLink when the slabs live on different GPUs, see dist.h) --------------------------------------------------
+	// boundary x-planes of the sweep's outputs -> the x-neighbours' guard planes.  Each pointer addresses the target
+	// PLANE (element (j, k) at j * nzp + k); null = no neighbour on that side / nothing to push.
+	FT *push_lo[4], *push_hi[4];     // temp_out: plane 0 -> lower neighbour's plane nx, plane nx-1 -> upper neighbour's plane -1
+	FT *pushn_lo[4], *pushn_hi[4];   // the same for `next` (coupled x-sweep only: its output is the next sweep's / step's input)
+	// MODE 1: where the 16 coefficients of a line go: xcoef_to[owner] addresses the [16][lpo] block this slab owns in
+	// the owner's coefficient table
+	FT *xcoef_to[MAX_SLABS];
 };
 
 // elementwise helpers -----------------------------------------------------------------------

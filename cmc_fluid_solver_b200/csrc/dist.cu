@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 #include "dist.h"
 
 namespace cmc {
@@ -101,6 +102,119 @@ int nccl_allreduce_sum_f64(NcclComm *c, double *dev_buf, int n, cudaStream_t s)
 	if (!a || !c) { g_err = "NCCL not initialised"; return -1; }
 	NCCL_TRY(a->AllReduce(dev_buf, dev_buf, (size_t)n, kNcclFloat64, kNcclSum, c->comm, s));
 	return 0;
+}
+
+int nccl_allgather_bytes(NcclComm *c, const void *send_dev, void *recv_dev, size_t bytes, cudaStream_t s)
+{
+	Api *a = api();
+	if (!a || !c) { g_err = "NCCL not initialised"; return -1; }
+	if (cudaMemcpyAsync((char *)recv_dev + (size_t)c->rank * bytes, send_dev, bytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess) { g_err = "allgather: local copy failed"; return -1; }
+	NCCL_TRY(a->GroupStart());
+	for (int p = 0; p < c->nranks; p++) {
+		if (p == c->rank) continue;
+		NCCL_TRY(a->Send(send_dev, bytes, kNcclUint8, p, c->comm, s));
+		NCCL_TRY(a->Recv((char *)recv_dev + (size_t)p * bytes, bytes, kNcclUint8, p, c->comm, s));
+	}
+	NCCL_TRY(a->GroupEnd());
+	return 0;
+}
+
+// ---- peer memory ---------------------------------------------------------------------------------------------------
+int peer_map_arenas(NcclComm *c, void *arena, size_t arena_bytes, int rank, int nranks, PeerMap *pm, cudaStream_t s)
+{
+	(void)arena_bytes;
+	pm->rank = rank; pm->nranks = nranks;
+	for (int r = 0; r < 16; r++) { pm->base[r] = nullptr; pm->mapped[r] = false; }
+	pm->base[rank] = arena;
+	struct Msg { cudaIpcMemHandle_t h; int ok; int pad[15]; };
+	static_assert(sizeof(Msg) == 128, "message layout");
+	Msg mine;
+	memset(&mine, 0, sizeof mine);
+	mine.ok = cudaIpcGetMemHandle(&mine.h, arena) == cudaSuccess;
+	if (!mine.ok) cudaGetLastError();
+	Msg *d_all = nullptr, *d_mine = nullptr;
+	std::vector<Msg> all((size_t)nranks);
+	bool good = cudaMalloc((void **)&d_all, sizeof(Msg) * nranks) == cudaSuccess && cudaMalloc((void **)&d_mine, sizeof(Msg)) == cudaSuccess;
+	if (good) good = cudaMemcpyAsync(d_mine, &mine, sizeof mine, cudaMemcpyHostToDevice, s) == cudaSuccess;
+	// the collective must run on every rank even if this one already failed locally
+	if (nccl_allgather_bytes(c, d_mine, d_all, sizeof(Msg), s)) good = false;
+	if (good) good = cudaMemcpyAsync(all.data(), d_all, sizeof(Msg) * nranks, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+	if (cudaStreamSynchronize(s) != cudaSuccess) good = false;
+	if (good) {
+		for (int r = 0; r < nranks && good; r++) {
+			if (!all[r].ok) { good = false; break; }
+			if (r == rank) continue;
+			void *p = nullptr;
+			if (cudaIpcOpenMemHandle(&p, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = false; break; }
+			pm->base[r] = p; pm->mapped[r] = true;
+		}
+	}
+	// agree: everybody maps everybody, or nobody uses peer memory
+	double *d_ok = reinterpret_cast<double *>(d_all);
+	double v = good ? 1.0 : 0.0;
+	bool agreed = false;
+	if (d_all && cudaMemcpyAsync(d_ok, &v, sizeof v, cudaMemcpyHostToDevice, s) == cudaSuccess && nccl_allreduce_sum_f64(c, d_ok, 1, s) == 0 &&
+	    cudaMemcpyAsync(&v, d_ok, sizeof v, cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess)
+		agreed = v > nranks - 0.5;
+	if (d_all) cudaFree(d_all);
+	if (d_mine) cudaFree(d_mine);
+	if (!agreed) { peer_unmap(pm); g_err = "peer mapping of the exchange arenas failed on at least one rank"; return -1; }
+	return 0;
+}
+
+void peer_unmap(PeerMap *pm)
+{
+	for (int r = 0; r < 16; r++)
+		if (pm->mapped[r] && pm->base[r]) { cudaIpcCloseMemHandle(pm->base[r]); pm->base[r] = nullptr; pm->mapped[r] = false; }
+}
+
+struct FlagTargets { unsigned *p[16]; };
+
+__global__ void k_peer_signal(const FlagTargets ft, int nranks, int me, unsigned epoch)
+{
+	// everything this rank stored into peer memory before this kernel (stream order) becomes visible system-wide
+	// before the flag does
+	__threadfence_system();
+	const int r = threadIdx.x;
+	if (r < nranks && r != me && ft.p[r]) {
+		volatile unsigned *f = ft.p[r] + me;
+		*f = epoch;
+	}
+	__threadfence_system();
+}
+
+__global__ void k_peer_wait(const volatile unsigned *flags, int nranks, unsigned src_mask, unsigned epoch, int *timeout_flag)
+{
+	const int r = threadIdx.x;
+	if (r < nranks && (src_mask >> r & 1u)) {
+		unsigned long long t0;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+		for (;;) {
+			unsigned v;
+			asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+			if ((int)(v - epoch) >= 0) break;
+			__nanosleep(200);
+			unsigned long long t1;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+			if (t1 - t0 > 10000000000ull) { if (timeout_flag) atomicExch(timeout_flag, 1); break; }    // 10 s: a peer died
+		}
+	}
+	__threadfence_system();
+}
+
+void peer_signal(const PeerMap &pm, size_t flag_off, unsigned epoch, cudaStream_t s)
+{
+	FlagTargets ft;
+	for (int r = 0; r < 16; r++) ft.p[r] = (r < pm.nranks && pm.base[r]) ? reinterpret_cast<unsigned *>((char *)pm.base[r] + flag_off) : nullptr;
+	k_peer_signal<<<1, 32, 0, s>>>(ft, pm.nranks, pm.rank, epoch);
+}
+
+void peer_wait(const PeerMap &pm, size_t flag_off, unsigned src_mask, unsigned epoch, int *timeout_flag, cudaStream_t s)
+{
+	src_mask &= ~(1u << pm.rank);
+	if (!src_mask) return;
+	const volatile unsigned *flags = reinterpret_cast<const volatile unsigned *>((char *)pm.base[pm.rank] + flag_off);
+	k_peer_wait<<<1, 32, 0, s>>>(flags, pm.nranks, src_mask, epoch, timeout_flag);
 }
 
 } // namespace cmc

@@ -207,6 +207,34 @@ __device__ __forceinline__ void store8(FT *__restrict__ p, const int (&off)[M], 
 	}
 }
 
+// Slab-decomposed runs: the boundary x-planes of a sweep's outputs also go straight into the x-neighbours' guard
+// planes (SweepArgs::push_*: the neighbour slab's buffer, in peer memory when it lives on another GPU), so that no
+// separate halo exchange follows the sweep.  y / z lines: the CTAs of planes 0 and nx-1 repeat their stores; x lines
+// (coupled sweep, MODE 2): the first row of chunk 0 and the last row of the last chunk.
+template <typename FT, int DIR, int MODE>
+__device__ __forceinline__ void push_planes(const SweepArgs<FT> &A, int q, int pi, int g, int GL, const int (&off)[M],
+                                            unsigned full, unsigned segfull, const FT (&tq)[M], const FT (&x)[M])
+{
+	const Layout &L = A.L;
+	if (DIR != 0) {
+		if (MODE != 0) return;
+		// `off` holds slab offsets (pi + 1) * plane + j * nzp + k: shift the plane pointers accordingly
+		if (pi == 0 && A.push_lo[q]) store8<FT, DIR>(A.push_lo[q] - L.plane, off, full, tq);
+		if (pi == L.nx - 1 && A.push_hi[q]) store8<FT, DIR>(A.push_hi[q] - (long long)L.nx * L.plane, off, full, tq);
+	} else if (MODE == 2) {
+		if (g == 0) {
+			const long long o = off[0] - L.plane;
+			if (A.push_lo[q] && (full & 1u)) A.push_lo[q][o] = tq[0];
+			if (A.pushn_lo[q] && (segfull & 1u)) A.pushn_lo[q][o] = x[0];
+		}
+		if (g == GL - 1) {
+			const long long o = off[M - 1] - (long long)L.nx * L.plane;
+			if (A.push_hi[q] && (full & 0x80u)) A.push_hi[q][o] = tq[M - 1];
+			if (A.pushn_hi[q] && (segfull & 0x80u)) A.pushn_hi[q][o] = x[M - 1];
+		}
+	}
+}
+
 // central difference along the line for the 8 rows of a chunk (lo / hi = rows r0-1 and r0+8)
 template <typename FT>
 __device__ __forceinline__ FT cdiff(const FT (&f)[M], FT lo, FT hi, int i, FT inv2h)

@@ -25,7 +25,8 @@ bool launch_x_spike(const SweepArgs<FT> &A, cudaStream_t s, long long *launches)
 template <typename FT>
 bool launch_x_coupled(const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
 template <typename FT>
-void launch_x_interface(int P, int lpo, int nlines, const FT *coef, FT *bnd, cudaStream_t s, long long *launches);
+// bnd_to[r]: the [8][lpo] block of rank r's interface table that this owner fills
+void launch_x_interface(int P, int lpo, int nlines, const FT *coef, FT *const *bnd_to, cudaStream_t s, long long *launches);
 template <typename FT>
 bool launch_pcr_batch(int nsys, int n, const FT *a, const FT *b, const FT *c, const FT *d, FT *x, cudaStream_t s);
 

@@ -76,14 +76,19 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 		line_ok = j < L.ny; n = L.nz; stride = 1; base = L.idx(i, line_ok ? j : 0, 0);
 	}
 	const int r0 = g * M;           // first row of this chunk
+	int pi = 0;                     // y / z lines: the x-plane this CTA works in
+	if (DIR == 1) pi = blockIdx.x / ((L.nz + NL - 1) / NL);
+	if (DIR == 2) pi = blockIdx.x / ((L.ny + NL - 1) / NL);
 	// slab-coupled x-lines: global line id, its owner rank for the interface solve, and the first / last chunk
-	int xo = 0;                     // element offset of this line's coefficients: (owner*NV + v)*lpo + line_in_owner
+	int xo = 0;                     // element offset of this line's interface values: owner * 8 * lpo + line_in_owner
+	FT *cto = nullptr;              // MODE 1: this line's slot in its owner's coefficient table
 	const int GL = (MODE != 0) ? A.L.nx / M : GP;    // chunks that hold real rows (nx % 8 == 0 is required)
 	if (MODE != 0) {
 		const int ktiles = (L.nz + NL - 1) / NL;
 		const int j = blockIdx.x / ktiles, k = min((blockIdx.x % ktiles) * NL + l, L.nz - 1);
 		const int line = j * L.nz + k, owner = line / A.lpo;
-		xo = owner * A.lpo * (MODE == 1 ? 16 : 8) + (line - owner * A.lpo);
+		xo = owner * A.lpo * 8 + (line - owner * A.lpo);
+		if (MODE == 1) cto = A.xcoef_to[owner] + (line - owner * A.lpo);
 	}
 	// Row offsets, clamped into the line so that EVERY thread issues valid (if redundant) loads: threads of padding
 	// chunks / lines outside the grid see role 0 everywhere, compute identity rows and store nothing.
@@ -251,15 +256,15 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 			reduced_solve<FT, 5, GP, GS, NL>(sys, sol, g, e, Ra, -c7 * nw * rr, Re, Xe);
 			if (line_ok && g == 0) {                 // first row: x = f - pf*x_left - qf*x_right
 #pragma unroll
-				for (int q = 0; q < 3; q++) A.xcoef[xo + q * A.lpo] = y0[q] - w0 * Xe[q];
-				A.xcoef[xo + 6 * A.lpo] = v0 - w0 * Xe[3];
-				A.xcoef[xo + 7 * A.lpo] = -w0 * Xe[4];
+				for (int q = 0; q < 3; q++) cto[q * A.lpo] = y0[q] - w0 * Xe[q];
+				cto[6 * A.lpo] = v0 - w0 * Xe[3];
+				cto[7 * A.lpo] = -w0 * Xe[4];
 			}
 			if (line_ok && g == GL - 1) {            // last row (= last separator): x = l - pl*x_left - ql*x_right
 #pragma unroll
-				for (int q = 0; q < 3; q++) A.xcoef[xo + (3 + q) * A.lpo] = Xe[q];
-				A.xcoef[xo + 8 * A.lpo] = Xe[3];
-				A.xcoef[xo + 9 * A.lpo] = Xe[4];
+				for (int q = 0; q < 3; q++) cto[(3 + q) * A.lpo] = Xe[q];
+				cto[8 * A.lpo] = Xe[3];
+				cto[9 * A.lpo] = Xe[4];
 			}
 			E[0] = E[1] = E[2] = FT(0);
 		} else
@@ -293,6 +298,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 		}
 		store8<FT, DIR>(A.temp_out[q], off, full, tq);
 		store8<FT, DIR>(A.next[q], off, segfull, x);
+		push_planes<FT, DIR, MODE>(A, q, pi, g, GL, off, full, segfull, tq, x);
 	}
 	CMC_MARK(3);   // phase V stores issued
 
@@ -403,14 +409,14 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 			if (g == GL - 1) Re[2] = c7 * rr;
 			reduced_solve<FT, 3, GP, GS, NL>(sys, sol, g, e, Ra, -c7 * nw * rr, Re, Xe);
 			if (line_ok && g == 0) {
-				A.xcoef[xo + 10 * A.lpo] = y0 - w0 * Xe[0];
-				A.xcoef[xo + 12 * A.lpo] = v0 - w0 * Xe[1];
-				A.xcoef[xo + 13 * A.lpo] = -w0 * Xe[2];
+				cto[10 * A.lpo] = y0 - w0 * Xe[0];
+				cto[12 * A.lpo] = v0 - w0 * Xe[1];
+				cto[13 * A.lpo] = -w0 * Xe[2];
 			}
 			if (line_ok && g == GL - 1) {
-				A.xcoef[xo + 11 * A.lpo] = Xe[0];
-				A.xcoef[xo + 14 * A.lpo] = Xe[1];
-				A.xcoef[xo + 15 * A.lpo] = Xe[2];
+				cto[11 * A.lpo] = Xe[0];
+				cto[14 * A.lpo] = Xe[1];
+				cto[15 * A.lpo] = Xe[2];
 			}
 			return;
 		}
@@ -435,6 +441,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 		}
 		store8<FT, DIR>(A.temp_out[3], off, full, tq);
 		store8<FT, DIR>(A.next[3], off, segfull, x);
+		push_planes<FT, DIR, MODE>(A, 3, pi, g, GL, off, full, segfull, tq, x);
 	}
 	CMC_MARK(6);
 #undef CMC_MARK
@@ -594,9 +601,11 @@ template bool launch_x_coupled<double>(const SweepArgs<double> &, cudaStream_t, 
 //     F_r + pf_r L_{r-1} + qf_r F_{r+1} = f_r ,   L_r + pl_r L_{r-1} + ql_r F_{r+1} = l_r .
 // Block-tridiagonal in Z_r = (L_r, F_{r+1}), r = 0..P-2, solved by block Thomas (2x2 blocks).  Writes, for every rank
 // r, the values of its neighbours' adjacent rows: bnd[(r * 8 + q) * lpo + line] = L_{r-1} (q < 4), F_{r+1} (q >= 4).
-constexpr int MAXP = 16;
+constexpr int MAXP = MAX_SLABS;
+template <typename FT> struct BndTargets { FT *p[MAXP]; };    // per rank: the [8][lpo] block this owner fills in its table
+
 template <typename FT>
-__global__ void k_x_interface(int P, int lpo, int nlines, const FT *__restrict__ coef, FT *__restrict__ bnd)
+__global__ void k_x_interface(int P, int lpo, int nlines, const FT *__restrict__ coef, const BndTargets<FT> bnd)
 {
 	const int line = blockIdx.x * blockDim.x + threadIdx.x;
 	if (line >= nlines) return;
@@ -633,22 +642,24 @@ __global__ void k_x_interface(int P, int lpo, int nlines, const FT *__restrict__
 			}
 			const int qq = mat == 0 ? q : 3;
 			for (int r = 0; r < P; r++) {
-				bnd[((size_t)r * 8 + qq) * lpo + line] = r > 0 ? Lr[r - 1] : FT(0);
-				bnd[((size_t)r * 8 + 4 + qq) * lpo + line] = r + 1 < P ? Fr1[r] : FT(0);
+				bnd.p[r][(size_t)qq * lpo + line] = r > 0 ? Lr[r - 1] : FT(0);
+				bnd.p[r][(size_t)(4 + qq) * lpo + line] = r + 1 < P ? Fr1[r] : FT(0);
 			}
 		}
 	}
 }
 
 template <typename FT>
-void launch_x_interface(int P, int lpo, int nlines, const FT *coef, FT *bnd, cudaStream_t s, long long *launches)
+void launch_x_interface(int P, int lpo, int nlines, const FT *coef, FT *const *bnd_to, cudaStream_t s, long long *launches)
 {
 	if (nlines <= 0) return;
-	k_x_interface<FT><<<(nlines + 127) / 128, 128, 0, s>>>(P, lpo, nlines, coef, bnd);
+	BndTargets<FT> bt;
+	for (int r = 0; r < MAXP; r++) bt.p[r] = r < P ? bnd_to[r] : nullptr;
+	k_x_interface<FT><<<(nlines + 127) / 128, 128, 0, s>>>(P, lpo, nlines, coef, bt);
 	if (launches) (*launches)++;
 }
-template void launch_x_interface<float>(int, int, int, const float *, float *, cudaStream_t, long long *);
-template void launch_x_interface<double>(int, int, int, const double *, double *, cudaStream_t, long long *);
+template void launch_x_interface<float>(int, int, int, const float *, float *const *, cudaStream_t, long long *);
+template void launch_x_interface<double>(int, int, int, const double *, double *const *, cudaStream_t, long long *);
 
 template bool launch_fast_sweep<float>(int, const SweepArgs<float> &, cudaStream_t, long long *);
 template bool launch_fast_sweep<double>(int, const SweepArgs<double> &, cudaStream_t, long long *);

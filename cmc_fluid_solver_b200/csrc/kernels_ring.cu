@@ -50,17 +50,18 @@ struct Tile {
 	long long stride;    // along the line
 	int n;               // rows of a line
 	int lines;           // lines of the tile that exist (1..NL)
+	int pi;              // y / z lines: the x-plane of the tile
 	__device__ __forceinline__ void set(const Layout &L, int tile)
 	{
 		if (DIR == 0) {
 			const int kt = (L.nz + NL - 1) / NL, j = tile / kt, k0 = (tile - j * kt) * NL;
-			tbase = L.idx(0, j, k0); stride = L.plane; n = L.nx; lines = min(NL, L.nz - k0);
+			tbase = L.idx(0, j, k0); stride = L.plane; n = L.nx; lines = min(NL, L.nz - k0); pi = 0;
 		} else if (DIR == 1) {
 			const int kt = (L.nz + NL - 1) / NL, i = tile / kt, k0 = (tile - i * kt) * NL;
-			tbase = L.idx(i, 0, k0); stride = L.nzp; n = L.ny; lines = min(NL, L.nz - k0);
+			tbase = L.idx(i, 0, k0); stride = L.nzp; n = L.ny; lines = min(NL, L.nz - k0); pi = i;
 		} else {
 			const int jt = (L.ny + NL - 1) / NL, i = tile / jt, j0 = (tile - i * jt) * NL;
-			tbase = L.idx(i, j0, 0); stride = 1; n = L.nz; lines = min(NL, L.ny - j0);
+			tbase = L.idx(i, j0, 0); stride = 1; n = L.nz; lines = min(NL, L.ny - j0); pi = i;
 		}
 	}
 };
@@ -355,6 +356,7 @@ __global__ void __launch_bounds__(GP * NL, 1) k_ring_sweep(const SweepArgs<FT> A
 			}
 			store8<FT, DIR>(A.temp_out[q], off, full, tq);
 			store8<FT, DIR>(A.next[q], off, segfull, x);
+			push_planes<FT, DIR, 0>(A, q, T.pi, g, GP, off, full, segfull, tq, x);
 		}
 
 		// ======================================= phase T ==================================================
@@ -484,6 +486,7 @@ __global__ void __launch_bounds__(GP * NL, 1) k_ring_sweep(const SweepArgs<FT> A
 			}
 			store8<FT, DIR>(A.temp_out[3], off, full, tT);
 			store8<FT, DIR>(A.next[3], off, segfull, x);
+			push_planes<FT, DIR, 0>(A, 3, T.pi, g, GP, off, full, segfull, tT, x);
 		}
 		// (head / sol are next written two barriers into the next tile)
 	}

@@ -205,6 +205,11 @@ class AdiSolver3D:
             out[name] = (ms.value, n.value)
         return out
 
+    def exchange_kind(self) -> str:
+        v = C.c_int64(0)
+        _check(load_library().cmc_adi3d_get_option(self._h, b"exchange", C.byref(v)))
+        return ("none", "nccl", "fused-stores", "fused-stores-peer-memory")[v.value]
+
     def device_bytes(self) -> int:
         n = C.c_int64(0)
         _check(load_library().cmc_adi3d_device_bytes(self._h, C.byref(n)))

@@ -45,7 +45,9 @@ def test_reference_driver_with_b200_solver(oracle_mod, tmp_path, fp):
             g = gs[key]
             if key[1] == 0:          # raw current layer after the step
                 if tol == 0.0:
-                    assert g["err"] == r["err"]
+                    # the fields are bit-identical; the residual is a sum over all cells (serial on the CPU, a block
+                    # reduction on the device): equal up to summation order
+                    assert abs(g["err"] - r["err"]) <= 1e-12 * abs(r["err"])
                     for n in "uvwT":
                         assert np.array_equal(g[n], r[n]), f"{solver} fp{fp * 8} step {key[0]} field {n}"
                 else:
