@@ -453,9 +453,11 @@ static size_t fast_smem_bytes(int GP, int NL, int nrhs = 3) { return sizeof(FT) 
 
 // lines per CTA: 8 (64-byte row segments in fp64) up to 256 threads per CTA; the 512-row case keeps 256 threads
 // (4 lines) so that one CTA per SM owns the whole register file: every load of a phase is in flight at once.
-constexpr int lines_per_cta(int GP) { return 8; }
+// x / y lines: short lines take more of them per CTA, which widens the row segments a warp touches (8 lines = 64 bytes
+// in fp64, 32 lines = 256 bytes) at the same CTA size; z lines are contiguous anyway.
+constexpr int lines_per_cta(int GP, int DIR = 2) { return DIR == 2 ? 8 : GP <= 16 ? 32 : GP == 32 ? 16 : 8; }
 
-template <typename FT, int DIR, int GP, int MODE = 0, int NL = lines_per_cta(GP)>
+template <typename FT, int DIR, int GP, int MODE = 0, int NL = lines_per_cta(GP, DIR)>
 static unsigned launch_one(const SweepArgs<FT> &A, cudaStream_t s, long long *trace, bool dry)
 {
 	const Layout &L = A.L;
@@ -552,7 +554,7 @@ bool launch_fast_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long lon
 		double acc[7] = {};
 		for (unsigned b = 0; b < grid; b++) for (int k = 1; k < 7; k++) acc[k] += (double)(h[(size_t)b * 16 + k] - h[(size_t)b * 16 + k - 1]);
 		fprintf(stderr, "[cmc trace] dir %d grid %u threads %d: mean cycles per CTA  loadV+elim %.0f | pcrV %.0f | storeV %.0f | loadT+elim %.0f | pcrT %.0f | storeT %.0f | total %.0f\n",
-		        dir, grid, GP * lines_per_cta(GP), acc[1] / grid, acc[2] / grid, acc[3] / grid, acc[4] / grid, acc[5] / grid, acc[6] / grid,
+		        dir, grid, GP * lines_per_cta(GP, dir), acc[1] / grid, acc[2] / grid, acc[3] / grid, acc[4] / grid, acc[5] / grid, acc[6] / grid,
 		        (acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6]) / grid);
 	}
 	if (launches) (*launches)++;
