@@ -251,3 +251,127 @@ def solve_tridiagonal(a, b, c, d):
     x = np.zeros_like(a)
     f(*[v.ctypes.data_as(P) for v in (a, b, c, d, x)], len(a))
     return x
+
+
+# ----------------------------------------------------------------------------------------------- 2D ADI (A16)
+def read_probe2d(path) -> dict:
+    """Parse a dump written by oracle/_ref/ref_probe2d_f32 (format: oracle/ref_probe2d.cpp)."""
+    data = Path(path).read_bytes()
+    assert data[:8] == b"CMCPRB2D", "not a 2D probe dump"
+    off = 8
+    ver, fpb, dimx, dimy, ng, nl, nsteps, ox, oy, out_every = struct.unpack_from("<10i", data, off)
+    off += 40
+    dx, dy, dt, v_T, v_vis, t_vis, t_phi, startT, _ = struct.unpack_from("<9d", data, off)
+    off += 72
+    N, outN, ft = dimx * dimy, ox * oy, _np_ft(fpb)
+
+    def take(dtype, count):
+        nonlocal off
+        a = np.frombuffer(data, dtype=dtype, count=count, offset=off).copy()
+        off += a.nbytes
+        return a
+
+    out = dict(fp_bytes=fpb, dimx=dimx, dimy=dimy, dx=dx, dy=dy, dt=dt, v_T=v_T, v_vis=v_vis, t_vis=t_vis, t_phi=t_phi, startT=startT,
+               num_global=ng, num_local=nl, outdims=(ox, oy), out_every=out_every, grids={}, layers={}, outputs={}, errs={})
+    while off < len(data):
+        step, kind = struct.unpack_from("<2i", data, off)
+        off += 8
+        if kind == 2:       # grid arrays seen by the solver in this step
+            out["grids"][step] = dict(type=take(np.int32, N), bc=take(np.int32, N), vx=take(ft, N), vy=take(ft, N), T=take(ft, N))
+            continue
+        (err,) = struct.unpack_from("<d", data, off)
+        off += 12
+        if kind == 0:       # current layer after the step (step -1: the initial layer)
+            out["layers"][step] = [take(ft, N) for _ in range(3)]
+            out["errs"][step] = err
+        else:               # GetLayer output
+            out["outputs"][step] = (take(ft, 2 * outN).reshape(outN, 2), take(np.float64, outN))
+    return out
+
+
+def ref2d_binary() -> Path:
+    return REF_DIR / "ref_probe2d_f32"
+
+
+def run_ref2d(data_file, config_file, out_file, nsteps=0, dump="every", timeout=600):
+    cmd = [str(ref2d_binary()), str(data_file), str(config_file), str(out_file), str(int(nsteps)), f"dump={dump}"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError(f"reference 2D probe failed ({r.returncode}): {r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+    return r.stdout
+
+
+class Oracle2D:
+    """oracle/adi2d_oracle.c driven like the reference's AdiSolver2D behind Solver2D (Solver2D.h:24-45)."""
+
+    def __init__(self, dimx, dimy, dx, dy, v_T, v_vis, t_vis, t_phi, startT, fp_bytes=4):
+        self.fp, self.ft = fp_bytes, _np_ft(fp_bytes)
+        self.suf = "_f32" if fp_bytes == 4 else "_f64"
+        self.dimx, self.dimy = dimx, dimy
+        f = self._fn("oracle2d_create")
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_int, C.c_int] + [C.c_double] * 7
+        self.h = C.c_void_p(f(dimx, dimy, dx, dy, v_T, v_vis, t_vis, t_phi, startT))
+        self._FP = C.POINTER(C.c_float if fp_bytes == 4 else C.c_double)
+
+    def _fn(self, name):
+        return getattr(lib(), name + self.suf)
+
+    def close(self):
+        if self.h:
+            f = self._fn("oracle2d_destroy")
+            f.argtypes = [C.c_void_p]
+            f(self.h)
+            self.h = None
+
+    def set_grid(self, type_, bc, vx, vy, T):
+        f = self._fn("oracle2d_set_grid")
+        IP = C.POINTER(C.c_int)
+        f.argtypes = [C.c_void_p, IP, IP, self._FP, self._FP, self._FP]
+        ai = [np.ascontiguousarray(a, dtype=np.int32) for a in (type_, bc)]
+        af = [np.ascontiguousarray(a, dtype=self.ft) for a in (vx, vy, T)]
+        f(self.h, *[a.ctypes.data_as(IP) for a in ai], *[a.ctypes.data_as(self._FP) for a in af])
+
+    def init_layer(self):
+        f = self._fn("oracle2d_init_layer")
+        f.argtypes = [C.c_void_p]
+        f(self.h)
+
+    def update_boundaries(self):
+        f = self._fn("oracle2d_update_boundaries")
+        f.argtypes = [C.c_void_p]
+        f(self.h)
+
+    def time_step(self, dt, num_global, num_local):
+        f = self._fn("oracle2d_time_step")
+        f.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        f.restype = C.c_int
+        e = C.c_double(0)
+        rc = f(self.h, float(dt), num_global, num_local, C.byref(e))
+        if rc:
+            raise RuntimeError("Exceeded max number of iterations" if rc == 1 else "Error is too big!")
+        return e.value
+
+    def iters(self):
+        f = self._fn("oracle2d_iters")
+        f.argtypes = [C.c_void_p]
+        f.restype = C.c_int
+        return f(self.h)
+
+    def field(self, layer, var):
+        f = self._fn("oracle2d_field")
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        f.restype = C.c_void_p
+        p = f(self.h, layer, var)
+        n = self.dimx * self.dimy
+        buf = (C.c_float if self.fp == 4 else C.c_double) * n
+        return np.frombuffer(buf.from_address(p), dtype=self.ft)
+
+    def get_layer(self, ox=0, oy=0):
+        ox, oy = ox or self.dimx, oy or self.dimy
+        vel = np.zeros((ox * oy, 2), dtype=self.ft)
+        T = np.zeros(ox * oy, dtype=np.float64)
+        f = self._fn("oracle2d_get_layer")
+        f.argtypes = [C.c_void_p, self._FP, C.POINTER(C.c_double), C.c_int, C.c_int]
+        f(self.h, vel.ctypes.data_as(self._FP), T.ctypes.data_as(C.POINTER(C.c_double)), ox, oy)
+        return vel, T
