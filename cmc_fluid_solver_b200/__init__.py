@@ -6,6 +6,6 @@ reference src/FluidSolver3D/Solver3D.h:24-49, AdiSolver3D.h:52-61) over the C AB
 fallback: creating a solver without the CUDA library or without a GPU raises.
 """
 from .cases import Case  # noqa: F401
-from .solver import AdiSolver3D, CmcError, DivergedError, lib_path, load_library  # noqa: F401
+from .solver import AdiSolver2D, AdiSolver3D, CmcError, DivergedError, lib_path, load_library  # noqa: F401
 
-__all__ = ["AdiSolver3D", "Case", "CmcError", "DivergedError", "lib_path", "load_library"]
+__all__ = ["AdiSolver2D", "AdiSolver3D", "Case", "CmcError", "DivergedError", "lib_path", "load_library"]

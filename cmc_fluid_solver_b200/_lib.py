@@ -17,6 +17,8 @@ SYMBOLS = [
     "cmc_adi3d_read_field", "cmc_adi3d_write_field", "cmc_adi3d_step_prologue", "cmc_adi3d_solve_direction",
     "cmc_adi3d_eval_div_error", "cmc_adi3d_time_step_async", "cmc_adi3d_sync", "cmc_adi3d_stream",
     "cmc_adi3d_launch_count", "cmc_adi3d_get_timing", "cmc_adi3d_device_bytes", "cmc_solve_tridiagonal_batch",
+    "cmc_adi2d_create", "cmc_adi2d_destroy", "cmc_adi2d_set_grid", "cmc_adi2d_init_layer", "cmc_adi2d_update_boundaries",
+    "cmc_adi2d_time_step", "cmc_adi2d_get_layer", "cmc_adi2d_read_field", "cmc_adi2d_write_field", "cmc_adi2d_launch_count",
 ]
 
 
@@ -76,6 +78,16 @@ def load_library() -> C.CDLL:
         "cmc_adi3d_get_timing": [vp, i32, P(dbl), P(i64)],
         "cmc_adi3d_device_bytes": [vp, P(i64)],
         "cmc_solve_tridiagonal_batch": [i32, i32, i32, i32, vp, vp, vp, vp, vp],
+        "cmc_adi2d_create": [i32, i32, dbl, dbl, P(FluidParams), dbl, i32, i32, P(vp)],
+        "cmc_adi2d_destroy": [vp],
+        "cmc_adi2d_set_grid": [vp, vp, vp, vp, vp, vp],
+        "cmc_adi2d_init_layer": [vp],
+        "cmc_adi2d_update_boundaries": [vp],
+        "cmc_adi2d_time_step": [vp, dbl, i32, i32, P(dbl), P(i32)],
+        "cmc_adi2d_get_layer": [vp, vp, vp, i32, i32],
+        "cmc_adi2d_read_field": [vp, i32, i32, vp],
+        "cmc_adi2d_write_field": [vp, i32, i32, vp],
+        "cmc_adi2d_launch_count": [vp, P(i64)],
     }
     for name, argtypes in sig.items():
         f = getattr(lib, name)

@@ -925,6 +925,10 @@ static int create_impl(const cmc_grid_desc *grid, const cmc_fluid_params *params
 
 } // namespace
 
+// shared with cmc_adi2d.cu
+int cmc_set_error(int code, const std::string &msg) { return fail(code, msg); }
+int cmc_check_device(int device) { return check_device(device); }
+
 // =================================================== C ABI ===================================================
 extern "C" {
 

@@ -216,6 +216,88 @@ class AdiSolver3D:
         return n.value
 
 
+class AdiSolver2D:
+    """B200 drop-in for the reference's 2D AdiSolver2D behind Solver2D (reference src/FluidSolver2D/Solver2D.h:24-45,
+    AdiSolver2D.h:40-64; driver call sequence FluidSolver2D.cpp:60-152):
+
+        solver = AdiSolver2D().Init(dimx, dimy, dx, dy, params, startT)      # Solver2D::Init(grid, params)
+        loop: solver.set_grid(...)            # what grid.Prepare(t) changed: Grid2D::GetType / GetData per cell
+              solver.UpdateBoundaries(); solver.TimeStep(dt, num_global, num_local)
+              solver.GetLayer(outdimx, outdimy)
+
+    Results are bit-identical with the reference CPU solver (GPU only, no CPU fallback)."""
+
+    def __init__(self):
+        self._h = None
+        self.err = 0.0
+        self.iters = 0
+
+    def Init(self, dimx, dimy, dx, dy, v_T, v_vis, t_vis, t_phi, startT, fp_bytes=4, device=0):
+        lib = load_library()
+        self.dimx, self.dimy, self.fp = dimx, dimy, fp_bytes
+        self.ft = np.float32 if fp_bytes == 4 else np.float64
+        p = FluidParams(v_T, v_vis, t_vis, t_phi)
+        h = C.c_void_p()
+        _check(lib.cmc_adi2d_create(dimx, dimy, float(dx), float(dy), C.byref(p), float(startT), fp_bytes, device, C.byref(h)))
+        self._h = h
+        return self
+
+    def close(self):
+        if self._h:
+            load_library().cmc_adi2d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_grid(self, type_, bc, vx, vy, T):
+        ai = [np.ascontiguousarray(a, dtype=np.int32) for a in (type_, bc)]
+        af = [np.ascontiguousarray(a, dtype=self.ft) for a in (vx, vy, T)]
+        _check(load_library().cmc_adi2d_set_grid(self._h, *[_ptr(a) for a in ai], *[_ptr(a) for a in af]))
+
+    def init_layer(self):
+        _check(load_library().cmc_adi2d_init_layer(self._h))
+
+    def UpdateBoundaries(self):
+        _check(load_library().cmc_adi2d_update_boundaries(self._h))
+
+    def TimeStep(self, dt, num_global, num_local):
+        e, it = C.c_double(0.0), C.c_int(0)
+        rc = load_library().cmc_adi2d_time_step(self._h, float(dt), int(num_global), int(num_local), C.byref(e), C.byref(it))
+        self.err, self.iters = e.value, it.value
+        _check(rc)
+        return self.err
+
+    def GetLayer(self, outdimx=0, outdimy=0):
+        ox, oy = outdimx or self.dimx, outdimy or self.dimy
+        vel = np.empty((ox * oy, 2), dtype=self.ft)
+        T = np.empty(ox * oy, dtype=np.float64)
+        _check(load_library().cmc_adi2d_get_layer(self._h, _ptr(vel), _ptr(T), ox, oy))
+        return vel, T
+
+    def read_field(self, layer, var):
+        out = np.empty(self.dimx * self.dimy, dtype=self.ft)
+        _check(load_library().cmc_adi2d_read_field(self._h, layer, var, _ptr(out)))
+        return out
+
+    def write_field(self, layer, var, a):
+        a = np.ascontiguousarray(a, dtype=self.ft)
+        assert a.size == self.dimx * self.dimy
+        _check(load_library().cmc_adi2d_write_field(self._h, layer, var, _ptr(a)))
+
+    def launch_count(self):
+        n = C.c_int64(0)
+        _check(load_library().cmc_adi2d_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # lower-case aliases (the 2D test driver uses either spelling)
+    update_boundaries = UpdateBoundaries
+    time_step = TimeStep
+
+
 def solve_tridiagonal_batch(a, b, c, d, mode="exact"):
     """Batched line solve on the GPU: rows of a,b,c,d are independent systems (Common::SolveTridiagonal)."""
     ft = a.dtype

@@ -170,6 +170,38 @@ int cmc_adi3d_device_bytes(const cmc_adi3d *h, int64_t *n);
 int cmc_solve_tridiagonal_batch(int fp_bytes, int mode, int nsys, int n,
                                 const void *a, const void *b, const void *c, const void *d, void *x);
 
+/* =====================================================================================================================
+ * 2D ADI solver: replaces FluidSolver2D::AdiSolver2D behind FluidSolver2D::Solver2D (src/FluidSolver2D/Solver2D.h:24-45,
+ * AdiSolver2D.h:40-64).  Host arrays use the reference's layout idx = i * dimy + j (TimeLayer2D.h:27-40).  The arithmetic
+ * is the reference's, operation by operation (bit-identical results, including the data-dependent number of outer
+ * iterations).  Layers: CMC_LAYER_CUR / _HALF / _NEXT / _TEMP; variables: 0 = u, 1 = v, 2 = T.
+ * ===================================================================================================================== */
+typedef struct cmc_adi2d cmc_adi2d;
+
+/* `new AdiSolver2D` + the allocations of AdiSolver2D::Init (AdiSolver2D.cpp:21-35); dx, dy, startT = Grid2D::dx, dy, startT */
+int cmc_adi2d_create(int dimx, int dimy, double dx, double dy, const cmc_fluid_params *params, double startT,
+                     int fp_bytes, int device, cmc_adi2d **out);
+int cmc_adi2d_destroy(cmc_adi2d *h);
+/* what the solver reads through Grid2D::GetType / GetData (src/FluidSolver2D/Grid2D.h:52-54): node type, CondData2D::type
+ * (CMC_BC_*), CondData2D::vel.x / .y / .T per cell.  The reference driver refreshes the grid before every step
+ * (grid.Prepare(t), FluidSolver2D.cpp:129), so call this before every cmc_adi2d_update_boundaries / _time_step. */
+int cmc_adi2d_set_grid(cmc_adi2d *h, const int32_t *type, const int32_t *bc_type, const void *vx, const void *vy, const void *T);
+/* cur <- grid data in every cell: the second half of AdiSolver2D::Init (AdiSolver2D.cpp:36-50) */
+int cmc_adi2d_init_layer(cmc_adi2d *h);
+/* Solver2D::UpdateBoundaries (Solver2D.cpp:48-62) */
+int cmc_adi2d_update_boundaries(cmc_adi2d *h);
+/* AdiSolver2D::TimeStep (AdiSolver2D.cpp:279-323): iterates until it >= num_global AND the residual <= 0.1.  *err_out = the
+ * residual the reference prints, *iters_out = outer iterations done.  CMC_ERR_DIVERGED where the reference exits
+ * ("Exceeded max number of iterations", "Error is too big!"). */
+int cmc_adi2d_time_step(cmc_adi2d *h, double dt, int num_global, int num_local, double *err_out, int *iters_out);
+/* Solver2D::GetLayer (Solver2D.cpp:20-34): nearest-lower downsample of `next`; vel_xy = Vec2D[ox*oy] (2 x FTYPE), T = double[] */
+int cmc_adi2d_get_layer(cmc_adi2d *h, void *vel_xy, double *T, int outdimx, int outdimy);
+/* dense host copy of one field of one layer (Solver2D::SetGridBoundaries, Solver2D.cpp:64-71, reads cur.u / cur.v this
+ * way; Solver2D::SetLayer, :36-46, writes cur) */
+int cmc_adi2d_read_field(cmc_adi2d *h, int layer, int var, void *dst);
+int cmc_adi2d_write_field(cmc_adi2d *h, int layer, int var, const void *src);
+int cmc_adi2d_launch_count(const cmc_adi2d *h, int64_t *n);
+
 #ifdef __cplusplus
 }
 #endif

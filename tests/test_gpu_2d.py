@@ -1,0 +1,86 @@
+"""2D ADI on the GPU through the C ABI (cmc_adi2d_*): bit-for-bit against the golden vectors of the
+reference's 2D solver on its own data/2D/box_pipe case (all 49 steps: fields, residual, iteration counts via the
+residual, GetLayer output), and against the CPU oracle in fp64 and on a synthetic case with a free outflow."""
+import numpy as np
+import pytest
+
+from test_oracle2d import golden_grid, load_golden2d
+
+
+@pytest.mark.gpu
+def test_box_pipe_2d_matches_reference_bitwise():
+    from cmc_fluid_solver_b200 import AdiSolver2D
+    z = load_golden2d()
+    dimx, dimy = (int(v) for v in z["dims"])
+    s = AdiSolver2D().Init(dimx, dimy, *[float(v) for v in z["spacing"]], *[float(v) for v in z["params"]], float(z["startT"]), 4)
+    for q in range(3):
+        s.write_field(0, q, z["layer_init"][q])
+    keep = {int(k): i for i, k in enumerate(z["keep"])}
+    outs = {int(k): i for i, k in enumerate(z["out_steps"])}
+    for step in range(int(z["steps"])):
+        s.set_grid(*golden_grid(z, step))
+        s.UpdateBoundaries()
+        err = s.TimeStep(float(z["dt"]), int(z["iters"][0]), int(z["iters"][1]))
+        assert err == z["err"][step], f"residual differs at step {step}"
+        for q in range(3):
+            f = s.read_field(0, q)
+            assert float(np.sum(f.astype(np.float64))) == z["sums"][step, q], f"step {step} field {q}"
+            if step in keep:
+                assert np.array_equal(f, z["layers"][keep[step], q])
+        if step in outs:
+            vel, T = s.GetLayer(*[int(v) for v in z["outdims"]])
+            assert np.array_equal(vel, z["out_vel"][outs[step]]) and np.array_equal(T, z["out_T"][outs[step]])
+    assert s.launch_count() >= 2 * int(z["steps"])
+    s.close()
+
+
+def synthetic_2d(dimx, dimy, free_outflow=True):
+    """Channel with an inflow valve on the left, (free) outflow on the right, a wall-attached block; OUT rim."""
+    ty = np.ones((dimx, dimy), dtype=np.int32)          # NODE_OUT
+    ty[2:dimx - 2, 2:dimy - 2] = 0                      # NODE_IN
+    ty[1, 1:dimy - 1] = 3; ty[dimx - 2, 1:dimy - 1] = 3                 # valves
+    ty[1:dimx - 1, 1] = 2; ty[1:dimx - 1, dimy - 2] = 2                 # walls
+    ty[dimx // 3:dimx // 3 + 6, 2:dimy // 2] = 2                        # block attached to the lower wall
+    bc = np.zeros((dimx, dimy), dtype=np.int32)
+    vx = np.zeros((dimx, dimy)); vy = np.zeros((dimx, dimy)); T = np.ones((dimx, dimy))
+    vx[1, 2:dimy - 2] = 1.0
+    if free_outflow:
+        bc[dimx - 2, 2:dimy - 2] = 1
+    return ty.ravel(), bc.ravel(), vx.ravel(), vy.ravel(), T.ravel()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fp", [4, 8])
+def test_synthetic_2d_against_oracle(oracle_mod, fp):
+    from cmc_fluid_solver_b200 import AdiSolver2D
+    O = oracle_mod
+    dimx, dimy, h = 61, 47, 0.02
+    par = (1.0, 0.05, 0.07, 0.002)
+    ft = np.float32 if fp == 4 else np.float64
+    g = synthetic_2d(dimx, dimy)
+    o = O.Oracle2D(dimx, dimy, h, h, *par, 1.0, fp)
+    s = AdiSolver2D().Init(dimx, dimy, h, h, *par, 1.0, fp)
+    for solver in (o, s):
+        solver.set_grid(*g)
+        solver.init_layer()
+    for step in range(6):
+        e_ref = (o.update_boundaries(), o.time_step(0.05, 3, 2))[1]
+        e = (s.UpdateBoundaries(), s.TimeStep(0.05, 3, 2))[1]
+        assert e == e_ref and s.iters == o.iters()
+        for q in range(3):
+            assert np.array_equal(s.read_field(0, q), o.field(0, q).astype(ft)), f"fp{fp * 8} step {step} field {q}"
+    v, T = s.GetLayer(10, 9)
+    vo, To = o.get_layer(10, 9)
+    assert np.array_equal(v, vo) and np.array_equal(T, To)
+    o.close(); s.close()
+
+
+@pytest.mark.gpu
+def test_2d_argument_errors():
+    from cmc_fluid_solver_b200 import AdiSolver2D, CmcError
+    with pytest.raises(CmcError):
+        AdiSolver2D().Init(2, 10, 1, 1, 1, 1, 1, 1, 1)
+    s = AdiSolver2D().Init(8, 8, 1, 1, 1, 1, 1, 1, 1)
+    with pytest.raises(CmcError):
+        s.TimeStep(0.1, 1, 1)           # no grid yet
+    s.close()
