@@ -54,6 +54,9 @@ struct FastConst {
 //   middle  : PCR over the GP / 2^L surviving rows (<= 8: three steps);
 //   backward: eliminated rows recover x from their two (already solved) neighbours.
 // The solutions of ALL rows end up in sol[q * STR + e].  Fully unrolled: GP, GS are compile-time.
+// Precondition: the first row of a line enters with A == 0 and the last one with C == 0 (exact zeros: boundary and
+// identity rows have a = 0 / c = 0, the slab-coupled modes zero them explicitly).  Elimination keeps them zero, which is
+// why a row may read an arbitrary (finite) published row in place of a neighbour that does not exist.
 // Shared-memory footprint (elements): crs = NR * STR (publications; `sol` may alias it - the publications are not
 // read again once the PCR starts), pp = 2 * NR * (STR >> L) (PCR ping-pong, surviving rows only, compacted).
 template <int GP> struct RedGeom { static constexpr int L = GP > 8 ? (GP == 16 ? 1 : GP == 32 ? 2 : 3) : 0; };
@@ -87,14 +90,16 @@ __device__ __forceinline__ void reduced_solve(FT *sys, FT *sol, int g, int e, FT
 		}
 		__syncthreads();
 		if (alive && !odd) {
+			// a row without a lower (upper) neighbour has A == 0 (C == 0) exactly - see the header comment - so it may
+			// read ANY published row in its place: no bounds predicates, no zero fills
 			const bool lo = g - s >= 0, hi = g + s < GP;
-			const FT *l = crs + e - s * GS, *h = crs + e + s * GS;
-			const FT Al = lo ? l[0 * STR] : FT(0), Cl = lo ? l[1 * STR] : FT(0);
-			const FT Ah = hi ? h[0 * STR] : FT(0), Ch = hi ? h[1 * STR] : FT(0);
+			const FT *l = crs + (lo ? e - s * GS : e + s * GS), *h = crs + (hi ? e + s * GS : e - s * GS);
+			const FT Al = l[0 * STR], Cl = l[1 * STR];
+			const FT Ah = h[0 * STR], Ch = h[1 * STR];
 			const FT r = rcp<FT>(FT(1) - A * Cl - Cc * Ah);
 #pragma unroll
 			for (int q = 0; q < NRHS; q++) {
-				const FT Dl = lo ? l[(2 + q) * STR] : FT(0), Dh = hi ? h[(2 + q) * STR] : FT(0);
+				const FT Dl = l[(2 + q) * STR], Dh = h[(2 + q) * STR];
 				D[q] = (D[q] - A * Dl - Cc * Dh) * r;
 			}
 			A = -A * Al * r;
@@ -114,13 +119,13 @@ __device__ __forceinline__ void reduced_solve(FT *sys, FT *sol, int g, int e, FT
 		__syncthreads();
 		if (survivor) {
 			const bool lo = g - s >= 0, hi = g + s < GP;
-			const FT *l = w + ec - sc * GS, *h = w + ec + sc * GS;
-			const FT Al = lo ? l[0 * STRC] : FT(0), Cl = lo ? l[1 * STRC] : FT(0);
-			const FT Ah = hi ? h[0 * STRC] : FT(0), Ch = hi ? h[1 * STRC] : FT(0);
+			const FT *l = w + (lo ? ec - sc * GS : ec + sc * GS), *h = w + (hi ? ec + sc * GS : ec - sc * GS);
+			const FT Al = l[0 * STRC], Cl = l[1 * STRC];
+			const FT Ah = h[0 * STRC], Ch = h[1 * STRC];
 			const FT r = rcp<FT>(FT(1) - A * Cl - Cc * Ah);
 #pragma unroll
 			for (int q = 0; q < NRHS; q++) {
-				const FT Dl = lo ? l[(2 + q) * STRC] : FT(0), Dh = hi ? h[(2 + q) * STRC] : FT(0);
+				const FT Dl = l[(2 + q) * STRC], Dh = h[(2 + q) * STRC];
 				D[q] = (D[q] - A * Dl - Cc * Dh) * r;
 			}
 			A = -A * Al * r;
@@ -137,9 +142,10 @@ __device__ __forceinline__ void reduced_solve(FT *sys, FT *sol, int g, int e, FT
 		const int s = 1 << lv;
 		if (my_level == lv) {
 			const bool lo = g - s >= 0, hi = g + s < GP;
+			const int el = lo ? e - s * GS : e + s * GS, eh = hi ? e + s * GS : e - s * GS;
 #pragma unroll
 			for (int q = 0; q < NRHS; q++) {
-				const FT xl = lo ? sol[q * STR + e - s * GS] : FT(0), xh = hi ? sol[q * STR + e + s * GS] : FT(0);
+				const FT xl = sol[q * STR + el], xh = sol[q * STR + eh];
 				D[q] = D[q] - A * xl - Cc * xh;
 				sol[q * STR + e] = D[q];
 			}
@@ -158,19 +164,39 @@ template <typename FT> struct Vec16;
 template <> struct Vec16<double> { typedef double2 type; static constexpr int N = 2; };
 template <> struct Vec16<float> { typedef float4 type; static constexpr int N = 4; };
 
+// 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256): a z-chunk of 8 fp64 values is two of them (one
+// for fp32), and every access covers whole 32-byte sectors even though neighbouring lanes are a chunk apart
+__device__ __forceinline__ void ldg256(const double *p, double (&o)[4])
+{
+	asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(double *p, const double (&v)[4])
+{
+	asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+__device__ __forceinline__ void ldg256(const float *p, float (&o)[8])
+{
+	asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(float *p, const float (&v)[8])
+{
+	asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
+	             "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 template <typename FT, int DIR>
 __device__ __forceinline__ void load8(const FT *__restrict__ p, const int (&off)[M], FT (&o)[M])
 {
 	if (DIR == 2) {
-		typedef typename Vec16<FT>::type V;
-		constexpr int N = Vec16<FT>::N;
-		const V *q = reinterpret_cast<const V *>(p + off[0]);        // 64-byte aligned: r0 % 8 == 0, lines 128-byte aligned
+		constexpr int N = 32 / (int)sizeof(FT);                        // elements per 256-bit access
+		const FT *q = p + off[0];                                       // 64-byte aligned: r0 % 8 == 0, lines 128-byte aligned
 #pragma unroll
 		for (int v = 0; v < M / N; v++) {
-			const V t = q[v];
-			const FT *e = reinterpret_cast<const FT *>(&t);
+			FT t[N];
+			ldg256(q + v * N, t);
 #pragma unroll
-			for (int k = 0; k < N; k++) o[v * N + k] = e[k];
+			for (int k = 0; k < N; k++) o[v * N + k] = t[k];
 		}
 	} else {
 #pragma unroll
@@ -184,16 +210,14 @@ __device__ __forceinline__ void store8(FT *__restrict__ p, const int (&off)[M], 
 {
 	if (DIR == 2) {
 		if (mask == 0xffu) {
-			typedef typename Vec16<FT>::type V;
-			constexpr int N = Vec16<FT>::N;
-			V *q = reinterpret_cast<V *>(p + off[0]);
+			constexpr int N = 32 / (int)sizeof(FT);
+			FT *q = p + off[0];
 #pragma unroll
 			for (int w = 0; w < M / N; w++) {
-				V t;
-				FT *e = reinterpret_cast<FT *>(&t);
+				FT t[N];
 #pragma unroll
-				for (int k = 0; k < N; k++) e[k] = v[w * N + k];
-				q[w] = t;
+				for (int k = 0; k < N; k++) t[k] = v[w * N + k];
+				stg256(q + w * N, t);
 			}
 		} else {
 #pragma unroll

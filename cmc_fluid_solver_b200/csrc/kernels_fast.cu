@@ -38,7 +38,7 @@ namespace cmc {
 // MODE 2: the complete sweep with the neighbours' (now known) adjacent-row solutions folded into the first /
 //         last row of the slab.
 template <typename FT, int DIR, int GP, int NL, int MODE>
-__global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_sweep(const SweepArgs<FT> A, const FastConst<FT> K, long long *trace, const int one, const int pf_dist)
+__global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_sweep(const SweepArgs<FT> A, const FastConst<FT> K, long long *trace, const int one, const int pf_dist, const int pf_self)
 {
 	static_assert(MODE == 0 || DIR == 0, "slab coupling exists along x only");
 #define CMC_MARK(k) do { if (trace) { __syncthreads(); if (threadIdx.x == 0) trace[(size_t)blockIdx.x * 16 + (k)] = clock64(); } } while (0)
@@ -171,6 +171,18 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 			load8<FT, DIR>(A.cur[2], off, dp[2]);
 			load8<FT, DIR>(A.temp[3], off, Tl);
 			Tlo = A.temp[3][off_lo]; Thi = A.temp[3][off_hi];
+			// x / y lines: ask L2 for what this CTA reads AFTER the u,v,w solve (the other two temp components, cur.T,
+			// the first cross-line neighbours of temp[DIR]) - the requests cost no registers and HBM keeps streaming while
+			// the SM eliminates and solves.  One request per 64-byte row segment: lane l of a row group takes row l.
+			if (DIR != 2 && pf_self && l < M) {
+				const long long ro = base - l + (long long)min(r0 + l, n - 1) * stride;
+				const long long s1 = DIR == 0 ? L.nzp : L.plane;
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(A.temp[DIR == 0 ? 1 : 0] + ro));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(A.temp[DIR == 2 ? 1 : 2] + ro));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cur[3] + ro));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(A.temp[DIR] + ro + s1));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(A.temp[DIR] + ro - s1));
+			}
 		}
 		// right-hand sides of interior rows, in place (rows that are not plain interior are patched below):
 		//   d = cur * 3/dt  ( - v_T * dT/dD for the velocity component along the sweep )
@@ -491,6 +503,7 @@ static unsigned launch_one(const SweepArgs<FT> &A, cudaStream_t s, long long *tr
 	static const int cl_env[3] = {getenv("CMC_CLUSTER_X") ? atoi(getenv("CMC_CLUSTER_X")) : 1, getenv("CMC_CLUSTER_Y") ? atoi(getenv("CMC_CLUSTER_Y")) : 1,
 	                              getenv("CMC_CLUSTER_Z") ? atoi(getenv("CMC_CLUSTER_Z")) : 1};
 	const int cl = cl_env[DIR];
+	static const int pfs = getenv("CMC_PF_SELF") ? atoi(getenv("CMC_PF_SELF")) : 0;   // measured: neutral on y, -20 % on x (the x-sweep is bound by the number of row requests)
 	if (cl > 1 && grid % cl == 0) {
 		cudaLaunchConfig_t cfg = {};
 		cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GP * NL); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -498,9 +511,9 @@ static unsigned launch_one(const SweepArgs<FT> &A, cudaStream_t s, long long *tr
 		at[0].id = cudaLaunchAttributeClusterDimension;
 		at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
 		cfg.attrs = at; cfg.numAttrs = 1;
-		cudaLaunchKernelEx(&cfg, k_fast_sweep<FT, DIR, GP, NL, MODE>, A, K, trace, 1, pf);
+		cudaLaunchKernelEx(&cfg, k_fast_sweep<FT, DIR, GP, NL, MODE>, A, K, trace, 1, pf, pfs);
 	} else
-		k_fast_sweep<FT, DIR, GP, NL, MODE><<<grid, GP * NL, smem, s>>>(A, K, trace, 1, pf);
+		k_fast_sweep<FT, DIR, GP, NL, MODE><<<grid, GP * NL, smem, s>>>(A, K, trace, 1, pf, pfs);
 	return grid;
 }
 
