@@ -245,9 +245,16 @@ def main():
     sweep_n = sum(timings[k][1] for k in ("sweep_x", "sweep_y", "sweep_z"))
     achieved = sweep_bytes * sweep_n / (sweep_ms * 1e-3) / 1e9 if sweep_ms else None
     step_bytes = local_cells * (NUM_GLOBAL * 3 * NUM_LOCAL * (16 * fpb + 1) + NUM_GLOBAL * 12 * fpb + 8 * fpb)   # BASELINE.md B_step
+    # measured DRAM traffic per launch of the dominant kernel: one ncu --set full capture, committed under profiles/
+    traffic = None
+    tp = ROOT / "profiles" / "r01_ncu_traffic.json"
+    key = f"{DX}x{DY}x{DZ}_f{fpb * 8}"
+    if tp.exists() and world == 1 and dom:
+        traffic = json.loads(tp.read_text()).get(key, {}).get(dom, {}).get("dram_bytes")
     roofline = {
         "bound": "hbm", "kernel": "k_fast_sweep<%s,X|Y|Z> (all three directions, %d launches)" % ("double" if fpb == 8 else "float", sweep_n),
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None,
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic,
+        "traffic_source": "profiles/r01_ncu_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch of the dominant kernel)" if traffic else None,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": sweep_bytes,
         "per_direction": per_dir, "dominant": dom,
         "sweep_share_of_step": sweep_ms / (ms if world == 1 else max(ms, 1e-9)),

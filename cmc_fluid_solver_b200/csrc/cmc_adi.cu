@@ -169,7 +169,7 @@ struct Slab {
 	int init(const Layout &g, int x0, int nx, int dev, cudaStream_t s, int idx, int nslabs)
 	{
 		device = dev; stream = s; G = g; index = idx;
-		L = G; L.nx = nx; L.x0 = x0; L.total = (long long)(nx + 2) * L.plane;
+		L = G; L.x0 = x0; L.shape(nx, G.ny, G.nz, G.nzp, G.jbs);
 		int rc;
 		{
 			auto up = [](size_t v) { return (v + 255) / 256 * 256; };
@@ -204,6 +204,25 @@ struct Slab {
 
 	size_t lines_per_owner(int nslabs) const { return ((size_t)G.ny * G.nz + nslabs - 1) / nslabs; }
 
+	// dense host array of the WHOLE grid ((i * ny + j) * nz + k) <-> the local planes [p0, p1) of one field buffer;
+	// host_x0 = global plane held by host plane 0 of `host`.  One 3-D copy per y-block.
+	int copy_planes(FT *dev, const FT *host_c, FT *host_m, int p0, int p1, int host_x0)
+	{
+		for (int b = 0; b < L.nblk; b++) {
+			const int j0 = b << (L.nblk == 1 ? 0 : L.jbs), rows = L.nblk == 1 ? L.ny : std::min(1 << L.jbs, L.ny - j0);
+			cudaMemcpy3DParms P;
+			memset(&P, 0, sizeof P);
+			const size_t hoff = ((size_t)(L.x0 + p0 - host_x0) * L.ny + j0) * L.nz;
+			cudaPitchedPtr hp = make_cudaPitchedPtr((void *)((host_c ? host_c : host_m) + hoff), sizeof(FT) * L.nz, L.nz, L.ny);
+			cudaPitchedPtr dp = make_cudaPitchedPtr((void *)(dev + L.idx(p0, j0, 0)), sizeof(FT) * L.nzp, L.nzp, (size_t)(L.plane / L.nzp));
+			if (host_c) { P.srcPtr = hp; P.dstPtr = dp; P.kind = cudaMemcpyHostToDevice; }
+			else { P.srcPtr = dp; P.dstPtr = hp; P.kind = cudaMemcpyDeviceToHost; }
+			P.extent = make_cudaExtent(sizeof(FT) * L.nz, (size_t)rows, (size_t)(p1 - p0));
+			CU_TRY(cudaMemcpy3DAsync(&P, stream));
+		}
+		return CMC_OK;
+	}
+
 	ConstLayerPtrs<FT> clayer(int logical) const
 	{
 		ConstLayerPtrs<FT> r;
@@ -223,12 +242,11 @@ struct Slab {
 		if (ncode) { cudaFree(ncode); ncode = nullptr; }
 		CU_TRY(cudaMalloc((void **)&ncode, N));
 		CU_TRY(cudaMemcpyAsync(ncode, code, N, cudaMemcpyHostToDevice, stream));
-		const size_t rowb = sizeof(FT) * L.nz, pitch = sizeof(FT) * L.nzp, dense_plane = (size_t)L.ny * L.nz;
 		for (int q = 0; q < 4; q++) {
 			CU_TRY(cudaMemsetAsync(nodev[q], 0, sizeof(FT) * (size_t)L.total, stream));
 			const int p0 = L.x0 > 0 ? -1 : 0, p1 = L.x0 + L.nx < G.nx ? L.nx + 1 : L.nx;   // include the halo planes that exist
-			CU_TRY(cudaMemcpy2DAsync(nodev[q] + L.idx(p0, 0, 0), pitch, src[q] + (size_t)(L.x0 + p0) * dense_plane, rowb, rowb,
-			                         (size_t)(p1 - p0) * L.ny, cudaMemcpyHostToDevice, stream));
+			int rc = copy_planes(nodev[q], src[q], nullptr, p0, p1, 0);
+			if (rc) return rc;
 		}
 		// cur = TimeLayer3D(grid) (TimeLayer3D.h:734-751); half/next/temp are uninitialised in the reference
 		// (TimeLayer3D.h:353) and are defined here as copies of cur.
@@ -274,7 +292,9 @@ struct Engine : cmc_adi3d {
 
 	bool multi() const { return nslabs_total > 1; }
 	int exchange_kind() const override { return !multi() ? 0 : !push_mode() ? 1 : nccl ? 3 : 2; }
-	bool push_mode() const { return multi() && (!nccl || p2p); }
+	// (stores into another slab's buffers assume its layout equals this slab's: equal numbers of planes)
+	bool equal_slabs() const { return G.nx % nslabs_total == 0; }
+	bool push_mode() const { return multi() && equal_slabs() && (!nccl || p2p); }
 
 	// the address, in the slab that holds slab index `r`, of the buffer that is `mine` in slab `s`
 	FT *in_slab(Slab<FT> *s, int r, FT *mine) const
@@ -308,7 +328,21 @@ struct Engine : cmc_adi3d {
 		params = *p;
 		dx = g->dx; dy = g->dy; dz = g->dz;
 		G.nx = g->dimx; G.ny = g->dimy; G.nz = g->dimz; G.gx = g->dimx; G.x0 = 0;
-		G.nzp = round_up(g->dimz, 16) + (getenv("CMC_PAD_Z") ? atoi(getenv("CMC_PAD_Z")) : 0); G.plane = (long long)G.ny * G.nzp; G.total = (long long)(G.nx + 2) * G.plane;
+		{
+			// y-blocking of the storage (Layout).  Default: blocks of about 256 KB per x-plane once a whole plane is
+			// larger than 512 KB (measured on B200, profiles/r01_variants.md: the x-sweep pays per touched page, 512^3 fp64
+			// 7.0 -> 5.2 ms per launch with 64-row blocks).  CMC_JB = rows per block (a power of two >= 8), 0 = one block.
+			int jbs = 30;
+			const int nzp = round_up(g->dimz, 16);
+			int jb = 0;
+			if ((size_t)g->dimy * nzp * sizeof(FT) > (512u << 10)) {
+				jb = 8;
+				while ((size_t)(2 * jb) * nzp * sizeof(FT) <= (256u << 10)) jb *= 2;
+			}
+			if (getenv("CMC_JB")) jb = atoi(getenv("CMC_JB"));
+			if (jb >= 8 && (jb & (jb - 1)) == 0) { jbs = 0; while ((1 << jbs) < jb) jbs++; }
+			G.shape(g->dimx, g->dimy, g->dimz, round_up(g->dimz, 16), jbs);
+		}
 		nslabs_total = ntotal; rank = first_slab; nranks = ntotal;
 		int lo = 0, hi = 0;
 		for (int i = 0; i < nlocal; i++) {
@@ -323,7 +357,7 @@ struct Engine : cmc_adi3d {
 			if (rc) return rc;
 			dev_bytes += s->bytes;
 		}
-		L = G; L.x0 = lo; L.nx = hi - lo; L.total = (long long)(L.nx + 2) * L.plane;
+		L = G; L.x0 = lo; L.shape(hi - lo, G.ny, G.nz, G.nzp, G.jbs);
 		CU_TRY(cudaHostAlloc((void **)&h_err2, 2 * sizeof(double) * nlocal, cudaHostAllocDefault));
 		memset(h_err2, 0, 2 * sizeof(double) * nlocal);
 		CU_TRY(cudaMalloc((void **)&d_timeout, sizeof(int)));
@@ -343,24 +377,33 @@ struct Engine : cmc_adi3d {
 	{
 		if (!multi()) return CMC_OK;
 		span_begin(CMC_TIMING_COMM);
-		const size_t pb = sizeof(FT) * (size_t)G.plane;
+		// an x-plane is one contiguous piece per y-block
+		Slab<FT> *s0 = slabs[0];
+		const int nb = s0->L.nblk;
+		const size_t pb = sizeof(FT) * (size_t)s0->L.plane;
 		if (nccl) {
-			Slab<FT> *s = slabs[0];
-			P2P ops[16]; int n = 0;
+			Slab<FT> *s = s0;
+			std::vector<P2P> ops;
 			for (int q = 0; q < 4; q++) {
 				FT *f = s->field[s->slot[logical]][q];
-				if (rank > 0) ops[n++] = P2P{f + s->L.idx(0, 0, 0), f + s->L.idx(-1, 0, 0), pb, rank - 1};
-				if (rank + 1 < nranks) ops[n++] = P2P{f + s->L.idx(s->L.nx - 1, 0, 0), f + s->L.idx(s->L.nx, 0, 0), pb, rank + 1};
+				for (int b = 0; b < nb; b++) {
+					const long long bo = (long long)b * s->L.bstride;
+					if (rank > 0) ops.push_back(P2P{f + bo + s->L.idx(0, 0, 0), f + bo + s->L.idx(-1, 0, 0), pb, rank - 1});
+					if (rank + 1 < nranks) ops.push_back(P2P{f + bo + s->L.idx(s->L.nx - 1, 0, 0), f + bo + s->L.idx(s->L.nx, 0, 0), pb, rank + 1});
+				}
 			}
-			if (nccl_exchange(nccl, ops, n, stream)) return fail(CMC_ERR_COMM, nccl_error());
+			if (nccl_exchange(nccl, ops.data(), (int)ops.size(), stream)) return fail(CMC_ERR_COMM, nccl_error());
 			launches += 1;
 		} else {
 			for (size_t i = 0; i + 1 < slabs.size(); i++) {
 				Slab<FT> *a = slabs[i], *b = slabs[i + 1];
 				for (int q = 0; q < 4; q++) {
 					FT *fa = a->field[a->slot[logical]][q], *fb = b->field[b->slot[logical]][q];
-					CU_TRY(cudaMemcpyAsync(fb + b->L.idx(-1, 0, 0), fa + a->L.idx(a->L.nx - 1, 0, 0), pb, cudaMemcpyDeviceToDevice, stream));
-					CU_TRY(cudaMemcpyAsync(fa + a->L.idx(a->L.nx, 0, 0), fb + b->L.idx(0, 0, 0), pb, cudaMemcpyDeviceToDevice, stream));
+					for (int k = 0; k < nb; k++) {
+						const long long ao = (long long)k * a->L.bstride, bo = (long long)k * b->L.bstride;
+						CU_TRY(cudaMemcpyAsync(fb + bo + b->L.idx(-1, 0, 0), fa + ao + a->L.idx(a->L.nx - 1, 0, 0), pb, cudaMemcpyDeviceToDevice, stream));
+						CU_TRY(cudaMemcpyAsync(fa + ao + a->L.idx(a->L.nx, 0, 0), fb + bo + b->L.idx(0, 0, 0), pb, cudaMemcpyDeviceToDevice, stream));
+					}
 				}
 			}
 		}
@@ -846,10 +889,8 @@ struct Engine : cmc_adi3d {
 		if (logical < 0 || logical > 3 || var < 0 || var > 3) return fail(CMC_ERR_INVALID, "read_field: bad layer/var");
 		CU_TRY(cudaSetDevice(device));
 		for (auto *s : slabs) {
-			const FT *src = s->field[s->slot[logical]][var] + s->L.idx(0, 0, 0);
-			FT *d = (FT *)dst + (size_t)(s->L.x0 - L.x0) * G.ny * G.nz;
-			CU_TRY(cudaMemcpy2DAsync(d, sizeof(FT) * G.nz, src, sizeof(FT) * G.nzp, sizeof(FT) * G.nz, (size_t)s->L.nx * G.ny,
-			                         cudaMemcpyDeviceToHost, stream));
+			int rc = s->copy_planes(s->field[s->slot[logical]][var], nullptr, (FT *)dst, 0, s->L.nx, L.x0);
+			if (rc) return rc;
 		}
 		CU_TRY(cudaStreamSynchronize(stream));
 		return CMC_OK;
@@ -861,10 +902,8 @@ struct Engine : cmc_adi3d {
 		CU_TRY(cudaSetDevice(device));
 		halos_dirty = true;
 		for (auto *s : slabs) {
-			FT *dst = s->field[s->slot[logical]][var] + s->L.idx(0, 0, 0);
-			const FT *sp = (const FT *)src + (size_t)(s->L.x0 - L.x0) * G.ny * G.nz;
-			CU_TRY(cudaMemcpy2DAsync(dst, sizeof(FT) * G.nzp, sp, sizeof(FT) * G.nz, sizeof(FT) * G.nz, (size_t)s->L.nx * G.ny,
-			                         cudaMemcpyHostToDevice, stream));
+			int rc = s->copy_planes(s->field[s->slot[logical]][var], (const FT *)src, nullptr, 0, s->L.nx, L.x0);
+			if (rc) return rc;
 		}
 		CU_TRY(cudaStreamSynchronize(stream));
 		return CMC_OK;

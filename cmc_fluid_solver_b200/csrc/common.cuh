@@ -8,6 +8,7 @@
 // AdiSolver3D.cpp:251-258).
 //
 //   idx(i, j, k) = (i + 1) * plane + j * nzp + k,   i in [-1, nx],  plane = ny * nzp
+// (optionally blocked along y, see Layout)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -21,11 +22,38 @@ struct Layout {
 	int nzp;              // padded z-line length
 	int x0;               // global index of local plane 0
 	int gx;               // global dimx
-	long long plane;      // ny * nzp
-	long long total;      // (nx + 2) * plane
+	// y-blocking: the grid is stored as blocks of 2^jbs consecutive j-rows, each block holding ALL x-planes of its rows
+	// ([j / jb][i][j % jb][k]).  One block (jbs = 30, the default) is the plain [i][j][k] order.  Blocking shortens the
+	// distance between consecutive rows of an x-line from ny * nzp to jb * nzp elements (2 MB -> 128 KB at 512^3 fp64,
+	// jb = 32), which is what the x-sweep's address translation needs (profiles/r01_variants.md), at the price of
+	// y-lines that jump from block to block every jb rows.
+	int jbs, jbm;         // log2(jb), jb - 1
+	int nblk;             // number of blocks
+	long long plane;      // distance of consecutive x-planes: rows per block * nzp
+	long long bstride;    // distance of consecutive blocks: (nx + 2) * plane
+	long long total;      // nblk * bstride
 	__host__ __device__ __forceinline__ long long idx(int i, int j, int k) const
 	{
-		return (long long)(i + 1) * plane + (long long)j * nzp + k;
+		return (long long)(j >> jbs) * bstride + (long long)(i + 1) * plane + (long long)(j & jbm) * nzp + k;
+	}
+	// element distance to the next / previous j-row (valid memory for every j in [0, ny): rows outside the grid are
+	// only ever touched for values that are not used)
+	__host__ __device__ __forceinline__ long long jup(int j) const
+	{
+		return (((j + 1) & jbm) == 0 && j + 1 < ny) ? bstride - (long long)jbm * nzp : (long long)nzp;
+	}
+	__host__ __device__ __forceinline__ long long jdn(int j) const
+	{
+		return ((j & jbm) == 0 && j > 0) ? bstride - (long long)jbm * nzp : (long long)nzp;
+	}
+	// geometry of a slab of `lnx` planes of a grid ny x nz (block height 2^jbs_, or one block when jbs_ >= 30)
+	__host__ void shape(int lnx, int ny_, int nz_, int nzp_, int jbs_)
+	{
+		nx = lnx; ny = ny_; nz = nz_; nzp = nzp_;
+		if (jbs_ >= 30 || (1 << jbs_) >= ny_) { jbs = 30; jbm = (1 << 30) - 1; nblk = 1; plane = (long long)ny_ * nzp_; }
+		else { jbs = jbs_; jbm = (1 << jbs_) - 1; nblk = (ny_ + jbm) >> jbs_; plane = (long long)(1 << jbs_) * nzp_; }
+		bstride = (long long)(lnx + 2) * plane;
+		total = (long long)nblk * bstride;
 	}
 };
 

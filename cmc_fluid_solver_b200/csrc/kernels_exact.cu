@@ -14,21 +14,32 @@
 
 namespace cmc {
 
+// the grid line of a thread: cell p of it is at line.at(L, p)
+struct ExactLine {
+	int n, i, j, k;
+	template <int DIR>
+	__device__ __forceinline__ long long at(const Layout &L, int p) const
+	{
+		return DIR == 0 ? L.idx(p, j, k) : DIR == 1 ? L.idx(i, p, k) : L.idx(i, j, p);
+	}
+};
+
 template <int DIR>
-__device__ __forceinline__ bool line_of_thread(const Layout &L, long long t, int &n, long long &base, long long &stride)
+__device__ __forceinline__ bool line_of_thread(const Layout &L, long long t, ExactLine &ln)
 {
+	ln.i = ln.j = ln.k = 0;
 	if (DIR == 0) {            // lines along x: one per (j, k), lanes along k (coalesced)
-		const int k = (int)(t % L.nz), j = (int)(t / L.nz);
-		if (j >= L.ny) return false;
-		n = L.nx; base = L.idx(0, j, k); stride = L.plane;
+		ln.k = (int)(t % L.nz); ln.j = (int)(t / L.nz);
+		if (ln.j >= L.ny) return false;
+		ln.n = L.nx;
 	} else if (DIR == 1) {     // lines along y: one per (i, k), lanes along k (coalesced)
-		const int k = (int)(t % L.nz), i = (int)(t / L.nz);
-		if (i >= L.nx) return false;
-		n = L.ny; base = L.idx(i, 0, k); stride = L.nzp;
+		ln.k = (int)(t % L.nz); ln.i = (int)(t / L.nz);
+		if (ln.i >= L.nx) return false;
+		ln.n = L.ny;
 	} else {                   // lines along z: one per (i, j)
-		const int j = (int)(t % L.ny), i = (int)(t / L.ny);
-		if (i >= L.nx) return false;
-		n = L.nz; base = L.idx(i, j, 0); stride = 1;
+		ln.j = (int)(t % L.ny); ln.i = (int)(t / L.ny);
+		if (ln.i >= L.nx) return false;
+		ln.n = L.nz;
 	}
 	return true;
 }
@@ -36,13 +47,16 @@ __device__ __forceinline__ bool line_of_thread(const Layout &L, long long t, int
 template <typename FT, int DIR>
 __global__ void __launch_bounds__(128) k_exact_forward(const SweepArgs<FT> A)
 {
-	int n; long long base, stride;
-	if (!line_of_thread<DIR>(A.L, (long long)blockIdx.x * blockDim.x + threadIdx.x, n, base, stride)) return;
+	ExactLine ln;
+	if (!line_of_thread<DIR>(A.L, (long long)blockIdx.x * blockDim.x + threadIdx.x, ln)) return;
+	const int n = ln.n;
 	RowConst<FT> K; K.init(A, DIR);
-	const long long sx = A.L.plane, sy = A.L.nzp, sz = 1;
+	const long long sx = A.L.plane, sz = 1;
 	FT cpv = 0, cpT = 0, dp[4] = {0, 0, 0, 0};
 	for (int p = 0; p < n; p++) {
-		const long long id = base + p * stride;
+		const long long id = ln.at<DIR>(A.L, p);
+		const int jj = DIR == 1 ? p : ln.j;
+		const long long syp = A.L.jup(jj), sym = A.L.jdn(jj);
 		const unsigned r = A.role[id];
 		if (!(r & R_SEG)) continue;
 		if (r & R_END) {        // ApplyBC1 row closes the running segment: c[n-1] = 0
@@ -63,7 +77,7 @@ __global__ void __launch_bounds__(128) k_exact_forward(const SweepArgs<FT> A)
 			dp[0] = d[0] / b_v; dp[1] = d[1] / b_v; dp[2] = d[2] / b_v; dp[3] = d[3] / b_T;
 		} else if (r & R_INT) {
 			FT a_v, c_v, a_T, c_T, d[4];
-			build_interior_row<FT, DIR>(A, K, id, sx, sy, sz, a_v, c_v, a_T, c_T, d);
+			build_interior_row<FT, DIR>(A, K, id, sx, syp, sym, sz, a_v, c_v, a_T, c_T, d);
 			const FT den_v = K.b_v - a_v * cpv, den_T = K.b_T - a_T * cpT;
 			cpv = c_v / den_v; cpT = c_T / den_T;
 			dp[0] = (d[0] - dp[0] * a_v) / den_v;
@@ -79,11 +93,12 @@ __global__ void __launch_bounds__(128) k_exact_forward(const SweepArgs<FT> A)
 template <typename FT, int DIR>
 __global__ void __launch_bounds__(128) k_exact_backward(const SweepArgs<FT> A)
 {
-	int n; long long base, stride;
-	if (!line_of_thread<DIR>(A.L, (long long)blockIdx.x * blockDim.x + threadIdx.x, n, base, stride)) return;
+	ExactLine ln;
+	if (!line_of_thread<DIR>(A.L, (long long)blockIdx.x * blockDim.x + threadIdx.x, ln)) return;
+	const int n = ln.n;
 	FT x[4] = {0, 0, 0, 0};
 	for (int p = n - 1; p >= 0; p--) {
-		const long long id = base + p * stride;
+		const long long id = ln.at<DIR>(A.L, p);
 		const unsigned r = A.role[id];
 		if (!(r & R_SEG)) continue;
 		if ((r & R_END) && !(r & R_START)) {   // x[n-1] = d[n-1], already in place
@@ -101,7 +116,7 @@ __global__ void __launch_bounds__(128) k_exact_backward(const SweepArgs<FT> A)
 			// Shared cell: the later segment's value stays in `next` (the reference writes segments in list
 			// order, AdiSolver3D.cpp:596-602); the earlier segment still needs ITS last unknown, which is its
 			// ApplyBC1 row eliminated against row p-1 - recompute it with the forward pass's exact operations.
-			const long long im = id - stride;
+			const long long im = ln.at<DIR>(A.L, p - 1);
 			FT a_v, b_v, a_T, b_T, d[4];
 			boundary_row(A, r, id, a_v, b_v, a_T, b_T, d);
 			const FT den_v = b_v - a_v * A.cv[im], den_T = b_T - a_T * A.cT[im];

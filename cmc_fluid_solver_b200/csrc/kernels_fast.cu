@@ -59,13 +59,14 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 
 	// ---- which line ----------------------------------------------------------------------------------------
 	long long base;                 // element index of row 0 of this thread's line
-	long long stride;               // along the line
+	long long stride;               // along the line (y lines: inside one y-block, see rowoff)
+	int jline = 0;                  // x / z lines: the j-row of the line (cross-line neighbours j +- 1)
 	int n;                          // rows of the line
 	bool line_ok;
 	if (DIR == 0) {                 // lines along x: CTA = (j, k-tile)
 		const int ktiles = (L.nz + NL - 1) / NL;
 		const int j = blockIdx.x / ktiles, k = (blockIdx.x % ktiles) * NL + l;
-		line_ok = k < L.nz; n = L.nx; stride = L.plane; base = L.idx(0, j, line_ok ? k : 0);
+		line_ok = k < L.nz; n = L.nx; stride = L.plane; base = L.idx(0, j, line_ok ? k : 0); jline = j;
 	} else if (DIR == 1) {          // lines along y: CTA = (i, k-tile)
 		const int ktiles = (L.nz + NL - 1) / NL;
 		const int i = blockIdx.x / ktiles, k = (blockIdx.x % ktiles) * NL + l;
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 	} else {                        // lines along z: CTA = (i, j-tile)
 		const int jtiles = (L.ny + NL - 1) / NL;
 		const int i = blockIdx.x / jtiles, j = (blockIdx.x % jtiles) * NL + l;
-		line_ok = j < L.ny; n = L.nz; stride = 1; base = L.idx(i, line_ok ? j : 0, 0);
+		line_ok = j < L.ny; n = L.nz; stride = 1; base = L.idx(i, line_ok ? j : 0, 0); jline = line_ok ? j : 0;
 	}
 	const int r0 = g * M;           // first row of this chunk
 	int pi = 0;                     // y / z lines: the x-plane this CTA works in
@@ -92,6 +93,10 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 	}
 	// Row offsets, clamped into the line so that EVERY thread issues valid (if redundant) loads: threads of padding
 	// chunks / lines outside the grid see role 0 everywhere, compute identity rows and store nothing.
+	// offset of row r of a line from its row 0: a y-line jumps to the next y-block every 2^jbs rows
+	auto rowoff = [&](int r) -> int {
+		return DIR == 1 ? (r >> L.jbs) * (int)L.bstride + (r & L.jbm) * (int)L.nzp : r * (int)stride;
+	};
 	int off[M], off_lo, off_hi;      // 32-bit element offsets (launch_fast_sweep checks total < 2^31)
 	if (DIR == 2) {
 		const int rc = min(r0, L.nzp - M);
@@ -100,16 +105,18 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 		off_lo = (int)base + max(r0 - 1, 0);
 		off_hi = (int)base + min(r0 + M, n - 1);
 	} else {
+		// (a chunk never straddles a y-block: one block offset per chunk, rows nzp apart inside it)
+		const int rc = min(r0, n - 1), off0 = (int)base + rowoff(rc), rmax = n - 1 - rc;
 #pragma unroll
-		for (int i = 0; i < M; i++) off[i] = (int)base + min(r0 + i, n - 1) * (int)stride;
+		for (int i = 0; i < M; i++) off[i] = off0 + min(i, rmax) * (int)stride;
 		// rows -1 and n exist for a slab inside a decomposed grid (halo planes): its first / last row can be interior
-		off_lo = (int)base + max(r0 - 1, MODE != 0 ? -1 : 0) * (int)stride;
-		off_hi = (int)base + min(r0 + M, MODE != 0 ? n : n - 1) * (int)stride;
+		off_lo = (int)base + rowoff(max(r0 - 1, MODE != 0 ? -1 : 0));
+		off_hi = (int)base + rowoff(min(r0 + M, MODE != 0 ? n : n - 1));
 	}
 	// ---- L2 prefetch of the inputs of the CTA that will take this CTA's place in the next wave ------------------
 	// (CTAs are scheduled in blockIdx order; the CTA `pf_dist` ahead starts roughly when this one retires.)  The
 	// requests cost no registers or shared memory and keep HBM streaming while this CTA is in its solve phases.
-	if (pf_dist > 0 && blockIdx.x + pf_dist < gridDim.x) {
+	if (pf_dist > 0 && L.nblk == 1 && blockIdx.x + pf_dist < gridDim.x) {
 		const unsigned fb = blockIdx.x + pf_dist;
 		long long fbase;
 		if (DIR == 0) { const int kt = (L.nz + NL - 1) / NL; fbase = L.idx(0, fb / kt, (int)(fb % kt) * NL); }
@@ -126,6 +133,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 			}
 		}
 	}
+	const int step_last = off_hi - off[M - 1];   // from the chunk's last row to the next row of the line (may cross a y-block)
 	unsigned rowmask = 0;           // rows of this chunk that exist
 #pragma unroll
 	for (int i = 0; i < M; i++) rowmask |= (line_ok && r0 + i < n) ? (1u << i) : 0u;
@@ -174,7 +182,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 			// x / y lines: ask L2 for what this CTA reads AFTER the u,v,w solve (the other two temp components, cur.T,
 			// the first cross-line neighbours of temp[DIR]) - the requests cost no registers and HBM keeps streaming while
 			// the SM eliminates and solves.  One request per 64-byte row segment: lane l of a row group takes row l.
-			if (DIR != 2 && pf_self && l < M) {
+			if (DIR != 2 && pf_self && L.nblk == 1 && l < M) {
 				const long long ro = base - l + (long long)min(r0 + l, n - 1) * stride;
 				const long long s1 = DIR == 0 ? L.nzp : L.plane;
 				asm volatile("prefetch.global.L2 [%0];" ::"l"(A.temp[DIR == 0 ? 1 : 0] + ro));
@@ -202,7 +210,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 				if (r & R_INT) {                        // R_PRE: the next cell ends this segment AND starts the next one -
 					if (vfree) b += FT(0.5) * c;        // fold its ApplyBC1 row in:  -x[p-1] + 2 x[p] = 0
 					else {                              //                            x[p] = node value
-						const int idn = off[i] + (int)stride;
+						const int idn = off[i] + (i == M - 1 ? step_last : (int)stride);     // the next cell along the line
 						d0 -= c * A.nodev[0][idn]; d1 -= c * A.nodev[1][idn]; d2 -= c * A.nodev[2][idn];
 					}
 					c = FT(0);
@@ -328,18 +336,20 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 			// to an interior cell always exist, for everything else the (clamped, valid) addresses just deliver values
 			// that are never selected
 			constexpr int QA = DIR == 0 ? 1 : 0, QB = DIR == 2 ? 1 : 2;
-			const long long s1 = DIR == 0 ? L.nzp : L.plane, s2 = DIR == 2 ? L.nzp : 1;
+			// (j +- 1 are different distances at the edges of a y-block)
+			const long long s1p = DIR == 0 ? L.jup(jline) : L.plane, s1m = DIR == 0 ? L.jdn(jline) : L.plane;
+			const long long s2p = DIR == 2 ? L.jup(jline) : 1, s2m = DIR == 2 ? L.jdn(jline) : 1;
 			const FT *tp = A.temp[DIR];
 			FT c1[M], c2[M];
 			{
 				FT p1[M], m1[M];
-				load8<FT, DIR>(tp + s1, off, p1); load8<FT, DIR>(tp - s1, off, m1);
+				load8<FT, DIR>(tp + s1p, off, p1); load8<FT, DIR>(tp - s1m, off, m1);
 #pragma unroll
 				for (int i = 0; i < M; i++) c1[i] = (p1[i] - m1[i]) * K.inv2h1;
 			}
 			{
 				FT p2[M], m2[M];
-				if (DIR == 2) { load8<FT, DIR>(tp + s2, off, p2); load8<FT, DIR>(tp - s2, off, m2); }
+				if (DIR == 2) { load8<FT, DIR>(tp + s2p, off, p2); load8<FT, DIR>(tp - s2m, off, m2); }
 				else {          // +-1 element along k: unaligned, scalar
 #pragma unroll
 					for (int i = 0; i < M; i++) { p2[i] = tp[off[i] + 1]; m2[i] = tp[off[i] - 1]; }
@@ -382,7 +392,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 				const bool tfree = r & R_TFREE;
 				if (r & R_INT) {
 					if (tfree) b += FT(0.5) * c;
-					else d -= c * A.nodev[3][off[i] + (int)stride];
+					else d -= c * A.nodev[3][off[i] + (i == M - 1 ? step_last : (int)stride)];
 					c = FT(0);
 				} else if (r & (R_START | R_END)) {
 					a = ((r & (R_END | R_START)) == R_END && tfree) ? FT(-1) : FT(0);

@@ -51,17 +51,18 @@ struct Tile {
 	int n;               // rows of a line
 	int lines;           // lines of the tile that exist (1..NL)
 	int pi;              // y / z lines: the x-plane of the tile
+	int j0;              // z lines: j-row of the first line (the 8 lines of a tile never straddle a y-block)
 	__device__ __forceinline__ void set(const Layout &L, int tile)
 	{
 		if (DIR == 0) {
 			const int kt = (L.nz + NL - 1) / NL, j = tile / kt, k0 = (tile - j * kt) * NL;
-			tbase = L.idx(0, j, k0); stride = L.plane; n = L.nx; lines = min(NL, L.nz - k0); pi = 0;
+			tbase = L.idx(0, j, k0); stride = L.plane; n = L.nx; lines = min(NL, L.nz - k0); pi = 0; j0 = j;
 		} else if (DIR == 1) {
 			const int kt = (L.nz + NL - 1) / NL, i = tile / kt, k0 = (tile - i * kt) * NL;
-			tbase = L.idx(i, 0, k0); stride = L.nzp; n = L.ny; lines = min(NL, L.nz - k0); pi = i;
+			tbase = L.idx(i, 0, k0); stride = L.nzp; n = L.ny; lines = min(NL, L.nz - k0); pi = i; j0 = 0;
 		} else {
 			const int jt = (L.ny + NL - 1) / NL, i = tile / jt, j0 = (tile - i * jt) * NL;
-			tbase = L.idx(i, j0, 0); stride = 1; n = L.nz; lines = min(NL, L.ny - j0); pi = i;
+			tbase = L.idx(i, j0, 0); stride = 1; n = L.nz; lines = min(NL, L.ny - j0); pi = i; this->j0 = j0;
 		}
 	}
 };
@@ -182,7 +183,9 @@ __global__ void __launch_bounds__(GP * NL, 1) k_ring_sweep(const SweepArgs<FT> A
 			constexpr int PIECES = 2 * GP * S::PC;
 			for (int p = t; p < PIECES; p += STR) {
 				const int side = p / (GP * S::PC), w = p - side * (GP * S::PC);
-				const FT *src = tp + (side ? (long long)T.lines * L.nzp : -(long long)L.nzp) + min(w * S::EPP, L.nzp - S::EPP);
+				// lines j0 - 1 / j0 + lines: the neighbouring rows may live in the neighbouring y-block
+				const long long lo = side ? (long long)(T.lines - 1) * L.nzp + L.jup(T.j0 + T.lines - 1) : -L.jdn(T.j0);
+				const FT *src = tp + lo + min(w * S::EPP, L.nzp - S::EPP);
 				cp_async16(halo + side * (M * GP) + w * S::EPP, src);
 			}
 		} else {
@@ -543,6 +546,7 @@ bool launch_ring_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long lon
 {
 	const Layout &L = A.L;
 	if (!fast_sweep_supported(L, dir)) return false;
+	if (L.nblk > 1 && dir != 2) return false;            // the x / y tiles of this kernel assume the one-block layout
 	const int n = dir == 0 ? L.nx : dir == 1 ? L.ny : L.nz;
 	const int G = (n + M - 1) / M;
 	int GP = 4;

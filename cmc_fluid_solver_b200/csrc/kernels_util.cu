@@ -26,24 +26,25 @@ __global__ void k_build_roles(const Layout G, const uint8_t *__restrict__ ncode,
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	int n;               // cells along the (global) line
 	long long gbase, gstride;   // into ncode (dense global)
-	long long lbase, lstride;   // into role (slab layout); for DIR X local index = p - L.x0
+	int li = 0, lj = 0, lk = 0;   // the line in the slab layout: role cell p of the line = LIDX(p)
 	const int gny = G.ny, gnz = G.nz;
 	if (DIR == 0) {
 		const int k = (int)(t % gnz), j = (int)(t / gnz);
 		if (j >= gny) return;
 		n = G.nx; gbase = (long long)j * gnz + k; gstride = (long long)gny * gnz;
-		lbase = L.idx(-L.x0, j, k); lstride = L.plane;     // so that lbase + p*lstride is local plane p - x0
+		lj = j; lk = k;
 	} else if (DIR == 1) {
 		const int k = (int)(t % gnz), i = (int)(t / gnz);
 		if (i >= L.nx) return;
 		n = gny; gbase = ((long long)(i + L.x0) * gny) * gnz + k; gstride = gnz;
-		lbase = L.idx(i, 0, k); lstride = L.nzp;
+		li = i; lk = k;
 	} else {
 		const int j = (int)(t % gny), i = (int)(t / gny);
 		if (i >= L.nx) return;
 		n = gnz; gbase = ((long long)(i + L.x0) * gny + j) * gnz; gstride = 1;
-		lbase = L.idx(i, j, 0); lstride = 1;
+		li = i; lj = j;
 	}
+#define LIDX(p) (DIR == 0 ? L.idx((p) - L.x0, lj, lk) : DIR == 1 ? L.idx(li, (p), lk) : L.idx(li, lj, (p)))
 	int state = 0, start = 0, prev_end = -1;
 	unsigned long long count = 0, shared_free = 0;
 	for (int p = 0; p + 1 < n; p++) {
@@ -55,7 +56,7 @@ __global__ void k_build_roles(const Layout G, const uint8_t *__restrict__ ncode,
 			for (int q = start; q <= end; q++) {
 				if (DIR == 0 && (q < L.x0 || q >= L.x0 + L.nx)) continue;   // other slabs' cells
 				const unsigned bits = q == start ? R_START : q == end ? R_END : R_INT;
-				role[lbase + (long long)q * lstride] |= (uint8_t)bits;
+				role[LIDX(q)] |= (uint8_t)bits;
 			}
 			// a cell that ends one segment and starts the next one holds TWO unknowns when its boundary row is
 			// BC_FREE; the whole-line fast solver cannot represent that (exact mode can) - count such cells
@@ -66,13 +67,14 @@ __global__ void k_build_roles(const Layout G, const uint8_t *__restrict__ ncode,
 				// into its last interior row (start - 1), which also records the shared cell's boundary kinds
 				const int q = start - 1;
 				if (!(DIR == 0 && (q < L.x0 || q >= L.x0 + L.nx)))
-					role[lbase + (long long)q * lstride] |= (uint8_t)(R_PRE | ((sc & 4u) ? R_VFREE : 0u) | ((sc & 8u) ? R_TFREE : 0u));
+					role[LIDX(q)] |= (uint8_t)(R_PRE | ((sc & 4u) ? R_VFREE : 0u) | ((sc & 8u) ? R_TFREE : 0u));
 			}
 			prev_end = end;
 			count++;
 			state = 0;
 		}
 	}
+#undef LIDX
 	if (count) atomicAdd(seg_count, count);
 	if (shared_free) atomicAdd(seg_count + 4, shared_free);
 }
@@ -123,7 +125,7 @@ __device__ __forceinline__ void for_each_cell(const Layout &L, F f)
 	const int lanes_per_row = 128;                  // one CTA = 128 threads = one row at a time
 	(void)lanes_per_row;
 	for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-		const long long base = L.plane + row * L.nzp;    // idx(i, j, 0) with rows contiguous across i
+		const long long base = L.idx((int)(row / L.ny), (int)(row % L.ny), 0);
 		for (int k = threadIdx.x; k < L.nz; k += blockDim.x) f(base + k);
 	}
 }
@@ -247,12 +249,13 @@ __global__ void __launch_bounds__(256) k_div_error(const Layout L, const uint8_t
                                                     FT dx, FT dy, FT dz, double *partials)
 {
 	double err = 0.0, cnt = 0.0;
-	const long long sx = L.plane, sy = L.nzp;
+	const long long sx = L.plane;
 	const long long rows = (long long)L.nx * L.ny;
 	for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
 		const int i = (int)(row / L.ny), j = (int)(row % L.ny);
 		const int gi = i + L.x0;
 		if (gi == 0 || gi > L.gx - 2 || j == 0 || j > L.ny - 2) continue;
+		const long long sy = L.jdn(j);
 		const long long base = L.idx(i, j, 0);
 		for (int k = 1 + threadIdx.x; k <= L.nz - 2; k += blockDim.x) {
 			const long long id = base + k;

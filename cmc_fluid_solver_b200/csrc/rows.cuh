@@ -33,10 +33,11 @@ struct RowConst {
 
 // Interior row at cell `id` of a sweep in direction DIR.
 //   a = -V/(2h) - vis ; c = V/(2h) - vis ; b = 3/dt + 2 vis ; d = cur*3/dt (+ gradient / dissipation terms)
-// sx, sy, sz: element strides of +1 in x, y, z.
+// sx, sz: element strides of +1 in x, z; syp / sym: distance to the next / previous j-row (they differ at the edges
+// of a y-block, see Layout).
 template <typename FT, int DIR>
 __device__ __forceinline__ void build_interior_row(const SweepArgs<FT> &A, const RowConst<FT> &K, long long id,
-                                                   long long sx, long long sy, long long sz,
+                                                   long long sx, long long syp, long long sym, long long sz,
                                                    FT &a_v, FT &c_v, FT &a_T, FT &c_T, FT d[4])
 {
 	const FT *tu = A.temp[0], *tv = A.temp[1], *tw = A.temp[2], *tT = A.temp[3];
@@ -54,17 +55,17 @@ __device__ __forceinline__ void build_interior_row(const SweepArgs<FT> &A, const
 		const FT u_x = (tu[id + sx] - tu[id - sx]) / K.two_hx;
 		const FT v_x = (tv[id + sx] - tv[id - sx]) / K.two_hx;
 		const FT w_x = (tw[id + sx] - tw[id - sx]) / K.two_hx;
-		const FT u_y = (tu[id + sy] - tu[id - sy]) / K.two_hy;
+		const FT u_y = (tu[id + syp] - tu[id - sym]) / K.two_hy;
 		const FT u_z = (tu[id + sz] - tu[id - sz]) / K.two_hz;
 		d[0] = du - K.v_T * T_x;
 		d[1] = dv;
 		d[2] = dw;
 		d[3] = dT + K.t_phi * (2 * u_x * u_x + v_x * v_x + w_x * w_x + v_x * u_y + w_x * u_z);
 	} else if (DIR == 1) {
-		const FT T_y = (tT[id + sy] - tT[id - sy]) / K.two_hy;
-		const FT u_y = (tu[id + sy] - tu[id - sy]) / K.two_hy;
-		const FT v_y = (tv[id + sy] - tv[id - sy]) / K.two_hy;
-		const FT w_y = (tw[id + sy] - tw[id - sy]) / K.two_hy;
+		const FT T_y = (tT[id + syp] - tT[id - sym]) / K.two_hy;
+		const FT u_y = (tu[id + syp] - tu[id - sym]) / K.two_hy;
+		const FT v_y = (tv[id + syp] - tv[id - sym]) / K.two_hy;
+		const FT w_y = (tw[id + syp] - tw[id - sym]) / K.two_hy;
 		const FT v_x = (tv[id + sx] - tv[id - sx]) / K.two_hx;
 		const FT v_z = (tv[id + sz] - tv[id - sz]) / K.two_hz;
 		d[0] = du;
@@ -77,7 +78,7 @@ __device__ __forceinline__ void build_interior_row(const SweepArgs<FT> &A, const
 		const FT v_z = (tv[id + sz] - tv[id - sz]) / K.two_hz;
 		const FT w_z = (tw[id + sz] - tw[id - sz]) / K.two_hz;
 		const FT w_x = (tw[id + sx] - tw[id - sx]) / K.two_hx;
-		const FT w_y = (tw[id + sy] - tw[id - sy]) / K.two_hy;
+		const FT w_y = (tw[id + syp] - tw[id - sym]) / K.two_hy;
 		d[0] = du;
 		d[1] = dv;
 		d[2] = dw - K.v_T * T_z;
