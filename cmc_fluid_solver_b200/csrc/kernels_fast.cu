@@ -47,9 +47,9 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 	constexpr int GS = DIR == 2 ? 1 : NL;          // shared-memory distance of neighbouring chunks of a line
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	constexpr int NRMAX = MODE == 1 ? 7 : 5;       // matrix (2) + right-hand sides of the widest reduced solve
-	FT *sys = reinterpret_cast<FT *>(smem_raw);    // 3 * NRMAX arrays (CR publications + PCR ping-pong)
-	FT *head = sys + 3 * NRMAX * STR;              // 5 arrays: y0[3], v0, w0 of every chunk
-	FT *sol = head + 5 * STR;                      // NRMAX - 2 arrays: separator solutions
+	FT *sys = reinterpret_cast<FT *>(smem_raw);    // reduced-solve scratch (CR publications + compacted PCR ping-pong)
+	FT *sol = sys;                                 // separator solutions: alias the CR publications (see reduced_solve)
+	FT *head = sys + reduced_scratch_elems<NRMAX - 2, GP, NL>();   // 5 arrays: y0[3], v0, w0 of every chunk
 
 	const Layout &L = A.L;
 	const int t = threadIdx.x;
@@ -470,11 +470,9 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_swee
 #undef ROLE
 }
 
-template <typename FT>
-static size_t fast_smem_bytes(int GP, int NL, int nrhs = 3) { return sizeof(FT) * (size_t)(3 * (2 + nrhs) * GP * NL + 5 * GP * NL + nrhs * GP * NL); }
+template <typename FT, int GP, int NL, int NRHS>
+static size_t fast_smem_bytes() { return sizeof(FT) * (size_t)(reduced_scratch_elems<NRHS, GP, NL>() + 5 * GP * NL); }
 
-// lines per CTA: 8 (64-byte row segments in fp64) up to 256 threads per CTA; the 512-row case keeps 256 threads
-// (4 lines) so that one CTA per SM owns the whole register file: every load of a phase is in flight at once.
 // x / y lines: short lines take more of them per CTA, which widens the row segments a warp touches (8 lines = 64 bytes
 // in fp64, 32 lines = 256 bytes) at the same CTA size; z lines are contiguous anyway.
 constexpr int lines_per_cta(int GP, int DIR = 2) { return DIR == 2 ? 8 : GP <= 16 ? 32 : GP == 32 ? 16 : 8; }
@@ -489,7 +487,7 @@ static unsigned launch_one(const SweepArgs<FT> &A, cudaStream_t s, long long *tr
 	else grid = (unsigned)L.nx * (unsigned)((L.ny + NL - 1) / NL);
 	if (dry) return grid;
 	static bool attr_set = false;
-	const size_t smem = fast_smem_bytes<FT>(GP, NL, MODE == 1 ? 5 : 3);
+	const size_t smem = fast_smem_bytes<FT, GP, NL, (MODE == 1 ? 5 : 3)>();
 	if (!attr_set) {
 		cudaFuncSetAttribute((const void *)k_fast_sweep<FT, DIR, GP, NL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		attr_set = true;
@@ -740,7 +738,7 @@ __global__ void __launch_bounds__(GP * NLB) k_pcr_batch(int nsys, int n, const F
 template <typename FT, int GP>
 static void launch_batch_one(int nsys, int n, const FT *a, const FT *b, const FT *c, const FT *d, FT *x, cudaStream_t s)
 {
-	const size_t smem = fast_smem_bytes<FT>(GP, NLB);
+	const size_t smem = sizeof(FT) * (size_t)(3 * 5 + 5 + 3) * GP * NLB;
 	cudaFuncSetAttribute((const void *)k_pcr_batch<FT, GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	k_pcr_batch<FT, GP><<<(nsys + NLB - 1) / NLB, GP * NLB, smem, s>>>(nsys, n, a, b, c, d, x);
 }
