@@ -634,11 +634,11 @@ struct Engine : cmc_adi3d {
 					done = true;
 				} else if (fast_ok(dir)) {
 					// two data-movement variants of the same arithmetic (kernels_ring.cu / kernels_fast.cu).  Measured on
-					// B200 at 512^3 fp64 (profiles/r01_variants.md): the cp.async ring wins along z (contiguous lines,
-					// 4.99 vs 5.77 ms), the direct-load kernel along y (5.00 vs 5.66 ms) and x (7.05 vs 8.2 ms: rows a
-					// whole plane apart).  CMC_RING=<subset of "xyz"> overrides.
+					// B200 at 512^3 (profiles/r01_variants.md): fp64 - the direct-load kernel wins everywhere (z: 2-line tiles,
+					// four independent CTAs per SM, 4.00 ms against 4.58 ms for the cp.async ring); fp32 - the ring wins
+					// along z (2.42 against 2.71 ms).  CMC_RING=<subset of "xyz"> overrides.
 					static const char *ring_env = getenv("CMC_RING");
-					const bool ring = ring_env ? strchr(ring_env, "xyz"[dir]) != nullptr : dir == CMC_DIR_Z;
+					const bool ring = ring_env ? strchr(ring_env, "xyz"[dir]) != nullptr : (dir == CMC_DIR_Z && sizeof(FT) == 4);
 					if (ring) done = launch_ring_sweep<FT>(dir, A, stream, &launches);
 					if (!done) done = launch_fast_sweep<FT>(dir, A, stream, &launches);
 				}

@@ -38,7 +38,7 @@ namespace cmc {
 // MODE 2: the complete sweep with the neighbours' (now known) adjacent-row solutions folded into the first /
 //         last row of the slab.
 template <typename FT, int DIR, int GP, int NL, int MODE>
-__global__ void __launch_bounds__(GP * NL, (GP * NL <= 256) ? 2 : 1) k_fast_sweep(const SweepArgs<FT> A, const FastConst<FT> K, long long *trace, const int one, const int pf_dist, const int pf_self)
+__global__ void __launch_bounds__(GP * NL, (GP * NL <= 128 && DIR == 2 && GP == 64) ? 4 : (GP * NL <= 256) ? 2 : 1) k_fast_sweep(const SweepArgs<FT> A, const FastConst<FT> K, long long *trace, const int one, const int pf_dist, const int pf_self)
 {
 	static_assert(MODE == 0 || DIR == 0, "slab coupling exists along x only");
 #define CMC_MARK(k) do { if (trace) { __syncthreads(); if (threadIdx.x == 0) trace[(size_t)blockIdx.x * 16 + (k)] = clock64(); } } while (0)
@@ -534,8 +534,11 @@ static unsigned launch_dir(int GP, const SweepArgs<FT> &A, cudaStream_t s, long 
 	case 16: return launch_one<FT, DIR, 16>(A, s, trace, dry);
 	case 32: return launch_one<FT, DIR, 32>(A, s, trace, dry);
 	default: {
-		static const bool nl4 = getenv("CMC_NL64") && atoi(getenv("CMC_NL64")) == 4;
-		return nl4 ? launch_one<FT, DIR, 64, 0, 4>(A, s, trace, dry) : launch_one<FT, DIR, 64>(A, s, trace, dry);
+		// z lines of 512 rows: fewer lines per CTA, more independent CTAs per SM (CMC_NLZ = 2, 4 or 8 lines per CTA)
+		static const int nlz = getenv("CMC_NLZ") ? atoi(getenv("CMC_NLZ")) : 2;     // measured, 512^3 fp64: 4.00 / 4.17 / 4.65 ms for 2 / 4 / 8 lines
+		if (DIR == 2 && nlz == 4) return launch_one<FT, DIR, 64, 0, 4>(A, s, trace, dry);
+		if (DIR == 2 && nlz == 2) return launch_one<FT, DIR, 64, 0, 2>(A, s, trace, dry);
+		return launch_one<FT, DIR, 64>(A, s, trace, dry);
 	}
 	}
 }
