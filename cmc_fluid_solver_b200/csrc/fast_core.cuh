@@ -231,6 +231,30 @@ __device__ __forceinline__ void store8(FT *__restrict__ p, const int (&off)[M], 
 	}
 }
 
+// nonlinear-layer relaxation temp' = (temp + next) / 2 on the fluid cells of a chunk (MergeFieldTo, reference
+// TimeLayer3D.h:415-436), twice when the post-X merge is folded in; all-fluid chunks skip the per-row selects
+template <typename FT, int DIR>
+__device__ __forceinline__ void relax8(FT (&tq)[M], const FT (&x)[M], unsigned inmask, int twice)
+{
+	// (the shortcut pays along z only: in the 512-thread x / y kernels the extra code costs more in register
+	// allocation than the selects it saves - measured)
+	if (DIR == 2 && inmask == 0xffu) {
+#pragma unroll
+		for (int i = 0; i < M; i++) tq[i] = (tq[i] + x[i]) * FT(0.5);
+		if (twice) {
+#pragma unroll
+			for (int i = 0; i < M; i++) tq[i] = (tq[i] + x[i]) * FT(0.5);
+		}
+	} else {
+#pragma unroll
+		for (int i = 0; i < M; i++) tq[i] = (inmask & (1u << i)) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
+		if (twice) {
+#pragma unroll
+			for (int i = 0; i < M; i++) tq[i] = (inmask & (1u << i)) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
+		}
+	}
+}
+
 // Slab-decomposed runs: the boundary x-planes of a sweep's outputs also go straight into the x-neighbours' guard
 // planes (SweepArgs::push_*: the neighbour slab's buffer, in peer memory when it lives on another GPU), so that no
 // separate halo exchange follows the sweep.  y / z lines: the CTAs of planes 0 and nx-1 repeat their stores; x lines

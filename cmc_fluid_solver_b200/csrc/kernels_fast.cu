@@ -38,7 +38,7 @@ namespace cmc {
 // MODE 2: the complete sweep with the neighbours' (now known) adjacent-row solutions folded into the first /
 //         last row of the slab.
 template <typename FT, int DIR, int GP, int NL, int MODE>
-__global__ void __launch_bounds__(GP * NL, (GP * NL <= 128 && DIR == 2 && GP == 64) ? 4 : (GP * NL <= 256) ? 2 : 1) k_fast_sweep(const SweepArgs<FT> A, const FastConst<FT> K, long long *trace, const int one, const int pf_dist, const int pf_self)
+__global__ void __launch_bounds__(GP * NL, (GP * NL <= 64 && DIR == 2 && GP == 64) ? 8 : (GP * NL <= 128 && DIR == 2 && GP == 64) ? 4 : (GP * NL <= 256) ? 2 : 1) k_fast_sweep(const SweepArgs<FT> A, const FastConst<FT> K, long long *trace, const int one, const int pf_dist, const int pf_self)
 {
 	static_assert(MODE == 0 || DIR == 0, "slab coupling exists along x only");
 #define CMC_MARK(k) do { if (trace) { __syncthreads(); if (threadIdx.x == 0) trace[(size_t)blockIdx.x * 16 + (k)] = clock64(); } } while (0)
@@ -161,6 +161,8 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 128 && DIR == 2 && GP == 
 	}
 	const bool any_int = ((rw0 | rw1) & (R_INT * 0x01010101u)) != 0;
 	const unsigned holes = inmask & ~segmask;      // fluid cells outside every segment (dropped runs)
+	// every row a plain interior row (no boundary row, no folded shared cell): the per-row special cases are skipped
+	const bool plain = DIR == 2 && (((rw0 & 0x87878787u) ^ 0x01010101u) | ((rw1 & 0x87878787u) ^ 0x01010101u)) == 0u;
 	// z-lines: the padded tail of the last chunk may be rewritten freely, which keeps the vector path
 	const unsigned full = (DIR == 2 && line_ok && r0 < n) ? 0xffu : rowmask;
 	const unsigned segfull = (segmask | (full & ~rowmask)) == 0xffu ? 0xffu : segmask;
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 128 && DIR == 2 && GP == 
 			const FT Vh = V[i] * K.inv2h;
 			FT a = -Vh - K.vis_v, c = Vh - K.vis_v, b = K.b_v;
 			FT d0 = dp[0][i], d1 = dp[1][i], d2 = dp[2][i];
-			if ((r & (R_SEG | R_PRE)) != R_INT) {       // rare: boundary row, cell outside every segment, or shared-cell fold
+			if (!plain && (r & (R_SEG | R_PRE)) != R_INT) {       // rare: boundary row, cell outside every segment, or shared-cell fold
 				const bool vfree = r & R_VFREE;
 				if (r & R_INT) {                        // R_PRE: the next cell ends this segment AND starts the next one -
 					if (vfree) b += FT(0.5) * c;        // fold its ApplyBC1 row in:  -x[p-1] + 2 x[p] = 0
@@ -310,12 +312,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 128 && DIR == 2 && GP == 
 			for (int i = 0; i < M; i++)
 				if (holes & (1u << i)) x[i] = A.next[q][off[i]];
 		}
-#pragma unroll
-		for (int i = 0; i < M; i++) tq[i] = (inmask & (1u << i)) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
-		if (A.extra_merge) {
-#pragma unroll
-			for (int i = 0; i < M; i++) tq[i] = (inmask & (1u << i)) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
-		}
+		relax8<FT, DIR>(tq, x, inmask, A.extra_merge);
 		store8<FT, DIR>(A.temp_out[q], off, full, tq);
 		store8<FT, DIR>(A.next[q], off, segfull, x);
 		push_planes<FT, DIR, MODE>(A, q, pi, g, GL, off, full, segfull, tq, x);
@@ -388,7 +385,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 128 && DIR == 2 && GP == 
 			const FT Vh = V[i] * K.inv2h;
 			FT a = -Vh - K.vis_T, c = Vh - K.vis_T, b = K.b_T;
 			FT d = cT[i] * K.c3dt + K.t_phi * diss[i];
-			if ((r & (R_SEG | R_PRE)) != R_INT) {
+			if (!plain && (r & (R_SEG | R_PRE)) != R_INT) {
 				const bool tfree = r & R_TFREE;
 				if (r & R_INT) {
 					if (tfree) b += FT(0.5) * c;
@@ -455,12 +452,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 128 && DIR == 2 && GP == 
 			for (int i = 0; i < M; i++)
 				if (holes & (1u << i)) x[i] = A.next[3][off[i]];
 		}
-#pragma unroll
-		for (int i = 0; i < M; i++) tq[i] = (inmask & (1u << i)) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
-		if (A.extra_merge) {
-#pragma unroll
-			for (int i = 0; i < M; i++) tq[i] = (inmask & (1u << i)) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
-		}
+		relax8<FT, DIR>(tq, x, inmask, A.extra_merge);
 		store8<FT, DIR>(A.temp_out[3], off, full, tq);
 		store8<FT, DIR>(A.next[3], off, segfull, x);
 		push_planes<FT, DIR, MODE>(A, 3, pi, g, GL, off, full, segfull, tq, x);
@@ -538,6 +530,7 @@ static unsigned launch_dir(int GP, const SweepArgs<FT> &A, cudaStream_t s, long 
 		static const int nlz = getenv("CMC_NLZ") ? atoi(getenv("CMC_NLZ")) : 2;     // measured, 512^3 fp64: 4.00 / 4.17 / 4.65 ms for 2 / 4 / 8 lines
 		if (DIR == 2 && nlz == 4) return launch_one<FT, DIR, 64, 0, 4>(A, s, trace, dry);
 		if (DIR == 2 && nlz == 2) return launch_one<FT, DIR, 64, 0, 2>(A, s, trace, dry);
+		if (DIR == 2 && nlz == 1) return launch_one<FT, DIR, 64, 0, 1>(A, s, trace, dry);
 		return launch_one<FT, DIR, 64>(A, s, trace, dry);
 	}
 	}

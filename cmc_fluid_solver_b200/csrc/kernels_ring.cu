@@ -143,6 +143,8 @@ __global__ void __launch_bounds__(GP * NL, 1) k_ring_sweep(const SweepArgs<FT> A
 		}
 		const bool any_int = ((rw0 | rw1) & (R_INT * 0x01010101u)) != 0;
 		const unsigned holes = inmask & ~segmask;      // fluid cells outside every segment (dropped runs)
+		// every row a plain interior row (no boundary row, no folded shared cell): the per-row special cases are skipped
+		const bool plain = DIR == 2 && (((rw0 & 0x87878787u) ^ 0x01010101u) | ((rw1 & 0x87878787u) ^ 0x01010101u)) == 0u;
 		const unsigned full = (DIR == 2 && line_ok && r0 < n) ? 0xffu : rowmask;
 		const unsigned segfull = (segmask | (full & ~rowmask)) == 0xffu ? 0xffu : segmask;
 
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(GP * NL, 1) k_ring_sweep(const SweepArgs<FT> A
 				const FT Vh = V[i] * K.inv2h;
 				FT a = -Vh - K.vis_v, c = Vh - K.vis_v, b = K.b_v;
 				FT d0 = dp[0][i], d1 = dp[1][i], d2 = dp[2][i];
-				if ((r & (R_SEG | R_PRE)) != R_INT) {       // rare: boundary row, cell outside every segment, or shared-cell fold
+				if (!plain && (r & (R_SEG | R_PRE)) != R_INT) {       // rare: boundary row, cell outside every segment, or shared-cell fold
 					const bool vfree = r & R_VFREE;
 					if (r & R_INT) {                        // R_PRE: the next cell ends this segment AND starts the next one
 						if (vfree) b += FT(0.5) * c;
@@ -242,12 +244,7 @@ __global__ void __launch_bounds__(GP * NL, 1) k_ring_sweep(const SweepArgs<FT> A
 				for (int i = 0; i < M; i++)
 					if (holes & (1u << i)) x[i] = A.next[q][off[i]];
 			}
-#pragma unroll
-			for (int i = 0; i < M; i++) tq[i] = (inmask & (1u << i)) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
-			if (A.extra_merge) {
-#pragma unroll
-				for (int i = 0; i < M; i++) tq[i] = (inmask & (1u << i)) ? (tq[i] + x[i]) * FT(0.5) : tq[i];
-			}
+			relax8<FT, DIR>(tq, x, inmask, A.extra_merge);
 			store8<FT, DIR>(A.temp_out[q], off, full, tq);
 			store8<FT, DIR>(A.next[q], off, segfull, x);
 			push_planes<FT, DIR, 0>(A, q, T.pi, g, GP, off, full, segfull, tq, x);
@@ -330,7 +327,7 @@ __global__ void __launch_bounds__(GP * NL, 1) k_ring_sweep(const SweepArgs<FT> A
 				const FT Vh = V[i] * K.inv2h;
 				FT a = -Vh - K.vis_T, c = Vh - K.vis_T, b = K.b_T;
 				FT d = cT[i] * K.c3dt + K.t_phi * diss[i];
-				if ((r & (R_SEG | R_PRE)) != R_INT) {
+				if (!plain && (r & (R_SEG | R_PRE)) != R_INT) {
 					const bool tfree = r & R_TFREE;
 					if (r & R_INT) {
 						if (tfree) b += FT(0.5) * c;
@@ -372,12 +369,7 @@ __global__ void __launch_bounds__(GP * NL, 1) k_ring_sweep(const SweepArgs<FT> A
 				for (int i = 0; i < M; i++)
 					if (holes & (1u << i)) x[i] = A.next[3][off[i]];
 			}
-#pragma unroll
-			for (int i = 0; i < M; i++) tT[i] = (inmask & (1u << i)) ? (tT[i] + x[i]) * FT(0.5) : tT[i];
-			if (A.extra_merge) {
-#pragma unroll
-				for (int i = 0; i < M; i++) tT[i] = (inmask & (1u << i)) ? (tT[i] + x[i]) * FT(0.5) : tT[i];
-			}
+			relax8<FT, DIR>(tT, x, inmask, A.extra_merge);
 			store8<FT, DIR>(A.temp_out[3], off, full, tT);
 			store8<FT, DIR>(A.next[3], off, segfull, x);
 			push_planes<FT, DIR, 0>(A, 3, T.pi, g, GP, off, full, segfull, tT, x);
