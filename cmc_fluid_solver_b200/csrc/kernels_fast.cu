@@ -38,7 +38,7 @@ namespace cmc {
 // MODE 2: the complete sweep with the neighbours' (now known) adjacent-row solutions folded into the first /
 //         last row of the slab.
 template <typename FT, int DIR, int GP, int NL, int MODE>
-__global__ void __launch_bounds__(GP * NL, (GP * NL <= 64 && DIR == 2 && GP == 64) ? 8 : (GP * NL <= 128 && DIR == 2 && GP == 64) ? 4 : (GP * NL <= 256) ? 2 : 1) k_fast_sweep(const SweepArgs<FT> A, const FastConst<FT> K, long long *trace, const int one, const int pf_dist, const int pf_self)
+__global__ void __launch_bounds__(GP * NL, (GP * NL <= 64 && DIR == 2 && GP == 64) ? 8 : (GP * NL <= 128 && DIR == 2 && GP == 64) ? 4 : (GP * NL <= 256) ? 2 : 1) k_fast_sweep(const SweepArgs<FT> A, const FastConst<FT> K, long long *trace, const int one)
 {
 	static_assert(MODE == 0 || DIR == 0, "slab coupling exists along x only");
 #define CMC_MARK(k) do { if (trace) { __syncthreads(); if (threadIdx.x == 0) trace[(size_t)blockIdx.x * 16 + (k)] = clock64(); } } while (0)
@@ -113,26 +113,11 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 64 && DIR == 2 && GP == 6
 		off_lo = (int)base + rowoff(max(r0 - 1, MODE != 0 ? -1 : 0));
 		off_hi = (int)base + rowoff(min(r0 + M, MODE != 0 ? n : n - 1));
 	}
-	// ---- L2 prefetch of the inputs of the CTA that will take this CTA's place in the next wave ------------------
-	// (CTAs are scheduled in blockIdx order; the CTA `pf_dist` ahead starts roughly when this one retires.)  The
-	// requests cost no registers or shared memory and keep HBM streaming while this CTA is in its solve phases.
-	if (pf_dist > 0 && L.nblk == 1 && blockIdx.x + pf_dist < gridDim.x) {
-		const unsigned fb = blockIdx.x + pf_dist;
-		long long fbase;
-		if (DIR == 0) { const int kt = (L.nz + NL - 1) / NL; fbase = L.idx(0, fb / kt, (int)(fb % kt) * NL); }
-		else if (DIR == 1) { const int kt = (L.nz + NL - 1) / NL; fbase = L.idx(fb / kt, 0, (int)(fb % kt) * NL); }
-		else { const int jt = (L.ny + NL - 1) / NL; fbase = L.idx(fb / jt, min((int)(fb % jt) * NL + l, L.ny - 1), 0); }
-		// one request per 64-byte row segment: Z - this thread's chunk; X, Y - lane l of a row group takes row l
-#pragma unroll
-		for (int rep = 0; rep < (DIR == 2 ? 1 : M / NL); rep++) {
-			const long long po = fbase + (DIR == 2 ? (long long)min(r0, L.nzp - M) : (long long)min(r0 + l + rep * NL, n - 1) * stride);
-#pragma unroll
-			for (int q = 0; q < 4; q++) {
-				asm volatile("prefetch.global.L2 [%0];" :: "l"(A.cur[q] + po));
-				asm volatile("prefetch.global.L2 [%0];" :: "l"(A.temp[q] + po));
-			}
-		}
-	}
+	// ptxas schedules inside basic blocks only.  These never-taken branches (`one` is always 1) split the kernel where
+	// its latency hiding wants it split - address setup | all loads of a phase | arithmetic; without them the generated
+	// code for the 512-thread kernels is 8 % slower (measured, profiles/r01_variants.md).
+#define CMC_SCHED_FENCE() do { if (one > 1) asm volatile("nanosleep.u32 1;"); } while (0)
+	CMC_SCHED_FENCE();
 	const int step_last = off_hi - off[M - 1];   // from the chunk's last row to the next row of the line (may cross a y-block)
 	unsigned rowmask = 0;           // rows of this chunk that exist
 #pragma unroll
@@ -181,18 +166,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 64 && DIR == 2 && GP == 6
 			load8<FT, DIR>(A.cur[2], off, dp[2]);
 			load8<FT, DIR>(A.temp[3], off, Tl);
 			Tlo = A.temp[3][off_lo]; Thi = A.temp[3][off_hi];
-			// x / y lines: ask L2 for what this CTA reads AFTER the u,v,w solve (the other two temp components, cur.T,
-			// the first cross-line neighbours of temp[DIR]) - the requests cost no registers and HBM keeps streaming while
-			// the SM eliminates and solves.  One request per 64-byte row segment: lane l of a row group takes row l.
-			if (DIR != 2 && pf_self && L.nblk == 1 && l < M) {
-				const long long ro = base - l + (long long)min(r0 + l, n - 1) * stride;
-				const long long s1 = DIR == 0 ? L.nzp : L.plane;
-				asm volatile("prefetch.global.L2 [%0];" ::"l"(A.temp[DIR == 0 ? 1 : 0] + ro));
-				asm volatile("prefetch.global.L2 [%0];" ::"l"(A.temp[DIR == 2 ? 1 : 2] + ro));
-				asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cur[3] + ro));
-				asm volatile("prefetch.global.L2 [%0];" ::"l"(A.temp[DIR] + ro + s1));
-				asm volatile("prefetch.global.L2 [%0];" ::"l"(A.temp[DIR] + ro - s1));
-			}
+			if (DIR != 2) CMC_SCHED_FENCE();      // (z: measured faster without this one)
 		}
 		// right-hand sides of interior rows, in place (rows that are not plain interior are patched below):
 		//   d = cur * 3/dt  ( - v_T * dT/dD for the velocity component along the sweep )
@@ -460,6 +434,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 64 && DIR == 2 && GP == 6
 	CMC_MARK(6);
 #undef CMC_MARK
 #undef ROLE
+#undef CMC_SCHED_FENCE
 }
 
 template <typename FT, int GP, int NL, int NRHS>
@@ -485,35 +460,7 @@ static unsigned launch_one(const SweepArgs<FT> &A, cudaStream_t s, long long *tr
 		attr_set = true;
 	}
 	FastConst<FT> K; K.init(A, DIR);
-	static const int pf_env = getenv("CMC_PF_DIST") ? atoi(getenv("CMC_PF_DIST")) : -1;
-	int pf = pf_env < 0 ? 0 : pf_env;     // off by default: measured slower (the SMs load in step; extra requests only queue up)
-	if (pf_env == -2) {      // CMC_PF_DIST=-2: one full wave of resident CTAs
-		static int per_sm = 0, sms = 0;
-		if (!per_sm) {
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_sweep<FT, DIR, GP, NL, MODE>, GP * NL, smem);
-			int dev = 0; cudaGetDevice(&dev);
-			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-			if (per_sm < 1) per_sm = 1;
-		}
-		pf = per_sm * sms;
-	}
-	// x-lines: rows of a tile are a whole plane apart, so every 64-byte row segment is its own DRAM page visit; CTAs of
-	// a thread-block cluster are co-scheduled and walk neighbouring k-tiles in step, which turns those visits into
-	// 64 * cluster bytes per page (CMC_CLUSTER_X / _Y / _Z = 1, 2, 4, 8; experiments)
-	static const int cl_env[3] = {getenv("CMC_CLUSTER_X") ? atoi(getenv("CMC_CLUSTER_X")) : 1, getenv("CMC_CLUSTER_Y") ? atoi(getenv("CMC_CLUSTER_Y")) : 1,
-	                              getenv("CMC_CLUSTER_Z") ? atoi(getenv("CMC_CLUSTER_Z")) : 1};
-	const int cl = cl_env[DIR];
-	static const int pfs = getenv("CMC_PF_SELF") ? atoi(getenv("CMC_PF_SELF")) : 0;   // measured: neutral on y, -20 % on x (the x-sweep is bound by the number of row requests)
-	if (cl > 1 && grid % cl == 0) {
-		cudaLaunchConfig_t cfg = {};
-		cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GP * NL); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-		cudaLaunchAttribute at[1];
-		at[0].id = cudaLaunchAttributeClusterDimension;
-		at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-		cfg.attrs = at; cfg.numAttrs = 1;
-		cudaLaunchKernelEx(&cfg, k_fast_sweep<FT, DIR, GP, NL, MODE>, A, K, trace, 1, pf, pfs);
-	} else
-		k_fast_sweep<FT, DIR, GP, NL, MODE><<<grid, GP * NL, smem, s>>>(A, K, trace, 1, pf, pfs);
+	k_fast_sweep<FT, DIR, GP, NL, MODE><<<grid, GP * NL, smem, s>>>(A, K, trace, 1);
 	return grid;
 }
 
