@@ -453,11 +453,15 @@ static unsigned launch_one(const SweepArgs<FT> &A, cudaStream_t s, long long *tr
 	else if (DIR == 1) grid = (unsigned)L.nx * (unsigned)((L.nz + NL - 1) / NL);
 	else grid = (unsigned)L.nx * (unsigned)((L.ny + NL - 1) / NL);
 	if (dry) return grid;
-	static bool attr_set = false;
 	const size_t smem = fast_smem_bytes<FT, GP, NL, (MODE == 1 ? 5 : 3)>();
-	if (!attr_set) {
-		cudaFuncSetAttribute((const void *)k_fast_sweep<FT, DIR, GP, NL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		attr_set = true;
+	{   // the attribute is per device: set it once on every device this process launches on
+		static bool attr_set[64] = {};
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+			cudaFuncSetAttribute((const void *)k_fast_sweep<FT, DIR, GP, NL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (dev >= 0 && dev < 64) attr_set[dev] = true;
+		}
 	}
 	FastConst<FT> K; K.init(A, DIR);
 	k_fast_sweep<FT, DIR, GP, NL, MODE><<<grid, GP * NL, smem, s>>>(A, K, trace, 1);

@@ -398,15 +398,18 @@ static bool launch_ring_one(const SweepArgs<FT> &A, cudaStream_t s)
 	else if (DIR == 1) ntiles = L.nx * ((L.nz + NL - 1) / NL);
 	else ntiles = L.nx * ((L.ny + NL - 1) / NL);
 	const size_t smem = ring_smem_bytes<FT, GP, NL>();
-	static int ctas = 0;         // persistent grid: every CTA slot of the device
-	if (!ctas) {
+	static int ctas_of[64] = {};   // persistent grid: every CTA slot of the device (per device of this process)
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64) return false;
+	if (!ctas_of[dev]) {
 		if (cudaFuncSetAttribute((const void *)k_ring_sweep<FT, DIR, GP, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-		int per_sm = 0, sms = 0, dev = 0;
-		cudaGetDevice(&dev);
+		int per_sm = 0, sms = 0;
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ring_sweep<FT, DIR, GP, NL>, GP * NL, smem) != cudaSuccess || per_sm < 1) return false;
-		ctas = per_sm * sms;
+		ctas_of[dev] = per_sm * sms;
 	}
+	const int ctas = ctas_of[dev];
 	FastConst<FT> K; K.init(A, DIR);
 	k_ring_sweep<FT, DIR, GP, NL><<<std::min(ctas, ntiles), GP * NL, smem, s>>>(A, K, ntiles);
 	return true;
