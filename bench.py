@@ -264,14 +264,15 @@ def main():
 
     # ---- e2e: the same step through the public API with HOST buffers (H2D state, D2H layer) inside the timed region ----
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
+        # every rank feeds its own slab from pinned host memory; rank 0 receives the full layer (GetLayer gathers)
         ft = torch.float32 if fpb == 4 else torch.float64
-        host_in = [torch.empty(ncells, dtype=ft).pin_memory() for _ in range(4)]
+        host_in = [torch.empty(local_cells, dtype=ft).pin_memory() for _ in range(4)]
         for q in range(4):
             host_in[q].numpy()[:] = sol.read_field(0, q).ravel()
-        host_vel = torch.empty(ncells * 3, dtype=ft).pin_memory()
-        host_T = torch.empty(ncells, dtype=torch.float64).pin_memory()
-        h2d = 4 * ncells * fpb
+        host_vel = torch.empty(ncells * 3 if rank == 0 else 3, dtype=ft).pin_memory()
+        host_T = torch.empty(ncells if rank == 0 else 1, dtype=torch.float64).pin_memory()
+        h2d = 4 * ncells * fpb                                   # all ranks together
         d2h = ncells * (3 * fpb + 8) + 16
 
         def e2e_step():
@@ -282,20 +283,21 @@ def main():
             sol.GetLayer(0, 0, 0, vel=host_vel.numpy().reshape(-1, 3), T=host_T.numpy())   # device -> host: full layer
 
         e2e_step()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
         t0 = time.perf_counter()
-        a.record(stream)
         for _ in range(args.e2e_steps):
             e2e_step()
-        b.record(stream)
-        torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) * 1e3
-        dev = a.elapsed_time(b)
-        e2e_ms = max(wall, dev)
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
         e2e = {"value": ncells * args.e2e_steps / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": e2e_ms / args.e2e_steps, "steps": args.e2e_steps,
-               "what": "write_field x4 (pinned host -> HBM), UpdateBoundaries, TimeStep(computeError), GetLayer full resolution (HBM -> pinned host)"}
+               "what": "write_field x4 (pinned host -> HBM, every rank its slab), UpdateBoundaries, TimeStep(computeError), GetLayer full "
+                       "resolution (HBM -> pinned host on rank 0); host wall clock between barriers, max over ranks"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
