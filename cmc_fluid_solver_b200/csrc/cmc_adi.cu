@@ -280,6 +280,12 @@ struct Engine : cmc_adi3d {
 	~Engine() override
 	{
 		cudaSetDevice(device);
+		if (p2p && stream) {
+			// the neighbours' last sweeps may still be storing into this rank's arena: every rank publishes once more
+			// when it gets here and waits for the others before anything is unmapped or freed (10 s timeout inside)
+			publish();
+			await(all_mask());
+		}
 		if (stream) cudaStreamSynchronize(stream);
 		spans_collect();
 		if (p2p) peer_unmap(&pm);
