@@ -8,7 +8,7 @@
 # #ifndef guard) and (b) the 2D sources use Windows include paths.
 # The reference's own build system is NOT used (Fermi flags, libnetcdf dependency).
 #
-# Outputs: oracle/_ref/ref_probe3d_f32, ref_probe3d_f64, ref_probe2d_f32 (+ build.log)
+# Outputs: oracle/_ref/ref_probe3d_f32, ref_probe3d_f64, ref_probe2d_f32, dropin3d_f32/f64, dropin2d_f32 (+ build.log)
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${CMC_REFERENCE_ROOT:-/root/reference}"
@@ -80,6 +80,14 @@ build2d() { # fp32 only (BASELINE config 1 is the reference CPU case)
   )
   g++ -fopenmp -o "$OUT/ref_probe2d_f32" "$dir"/*.o -lrt
   echo "built $OUT/ref_probe2d_f32"
+  # 2D drop-in demonstration: reference loader + Grid2D + our Solver2D adapter + libcmcadi.so
+  local pkg="$HERE/../cmc_fluid_solver_b200"
+  if [ -f "$pkg/libcmcadi.so" ]; then
+    $cxx -DWITH_B200 -I"$pkg/host" -I"$HERE/../include" -c "$HERE/ref_probe2d.cpp" -o "$dir/ref_probe2d.o"
+    $cxx -I"$pkg/host" -I"$HERE/../include" -c "$pkg/host/B200AdiSolver2D.cpp" -o "$dir/B200AdiSolver2D.o"
+    g++ -fopenmp -o "$OUT/dropin2d_f32" "$dir"/*.o -lrt -L"$pkg" -lcmcadi -Wl,-rpath,'$ORIGIN/../../cmc_fluid_solver_b200'
+    echo "built $OUT/dropin2d_f32"
+  fi
 }
 
 {

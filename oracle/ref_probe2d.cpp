@@ -9,7 +9,10 @@
 //   solver's current layer and the divergence residual after TimeStep, and every GetLayer output.
 // Nothing here is part of the product; only tests/ and bench.py's cpu_baseline leg may execute the binary.
 //
-// usage: ref_probe2d <data> <config> <out.bin|-> <nsteps|0=all> [dump=every|last|none]
+// usage: ref_probe2d <data> <config> <out.bin|-> <nsteps|0=all> [dump=every|last|none] [solver=cpu|b200]
+//
+// Built with -DWITH_B200 (oracle/_ref/dropin2d_f32) the same driver puts the reference's loader and Grid2D in front of
+// the B200 solver through the Solver2D adapter (cmc_fluid_solver_b200/host/B200AdiSolver2D.*): the 2D drop-in demonstration.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +25,7 @@
 #include <algorithm>
 #include <map>
 #include <list>
+#include <stdexcept>
 #include <omp.h>
 
 #define private public
@@ -30,6 +34,9 @@
 #undef private
 #undef protected
 #include "../Common/Config.h"
+#ifdef WITH_B200
+#include "B200AdiSolver2D.h"
+#endif
 
 using namespace FluidSolver2D;
 using namespace Common;
@@ -59,10 +66,11 @@ static void dump_grid(Grid2D &grid, int step)
 int main(int argc, char **argv)
 {
 	if (argc < 5) { fprintf(stderr, "usage: %s <data> <config> <out.bin|-> <nsteps|0> [dump=every|last|none]\n", argv[0]); return 1; }
-	std::string dump = "every";
+	std::string dump = "every", which = "cpu";
 	int nsteps = atoi(argv[4]);
 	for (int a = 5; a < argc; a++)
 		if (!strncmp(argv[a], "dump=", 5)) dump = argv[a] + 5;
+		else if (!strncmp(argv[a], "solver=", 7)) which = argv[a] + 7;
 
 	Config();
 	Config::LoadFromFile(argv[2]);
@@ -74,15 +82,27 @@ int main(int argc, char **argv)
 	grid.Prepare(0, 0);
 	FluidParams params(Config::viscosity, Config::density, Config::R_specific, Config::k, Config::cv);
 
-	AdiSolver2D *solver = new AdiSolver2D();
-	solver->Init(&grid, params);
-	// half / next / temp / next_local are allocated uninitialised by the reference (TimeLayer2D.h:176-181); define the
-	// cells its copy loops never touch (last row / column) so that dumps are deterministic
-	{
-		TimeLayer2D *ls[4] = {solver->half, solver->next, solver->temp, solver->next_local};
+	Solver2D *solver = NULL;
+	if (which == "cpu") {
+		AdiSolver2D *adi = new AdiSolver2D();
+		adi->Init(&grid, params);
+		// half / next / temp / next_local are allocated uninitialised by the reference (TimeLayer2D.h:176-181); define the
+		// cells its copy loops never touch (last row / column) so that dumps are deterministic
+		TimeLayer2D *ls[4] = {adi->half, adi->next, adi->temp, adi->next_local};
 		for (int l = 0; l < 4; l++)
 			for (int i = 0; i < grid.dimx; i++)
 				for (int j = 0; j < grid.dimy; j++) { ls[l]->U(i, j) = 0; ls[l]->V(i, j) = 0; ls[l]->T(i, j) = 0; }
+		solver = adi;
+	} else {
+#ifdef WITH_B200
+		try {
+			solver = new B200AdiSolver2D(0);       // driven through the Solver2D interface only from here on
+			solver->Init(&grid, params);
+		} catch (const std::exception &e) { fprintf(stderr, "probe2d: exception: %s\n", e.what()); return 3; }
+#else
+		fprintf(stderr, "probe2d: built without the B200 adapter\n");
+		return 1;
+#endif
 	}
 
 	const int frames = grid.GetFramesNum();

@@ -84,3 +84,52 @@ def test_2d_argument_errors():
     with pytest.raises(CmcError):
         s.TimeStep(0.1, 1, 1)           # no grid yet
     s.close()
+
+
+def _write_2d_case(directory):
+    """A 2D case in the reference's own file formats (Grid2D::LoadFromFile, src/FluidSolver2D/Grid2D.cpp:268-372;
+    Config.h:203-245): the masked channel outline at the scale of the reference's data/2D/box_pipe."""
+    from cmc_fluid_solver_b200.cases import BAFFLE_OUTLINE
+    lines = ["1", "0.035", str(len(BAFFLE_OUTLINE))]
+    for kind, pts, vel in BAFFLE_OUTLINE:
+        lines.append(str(len(pts)))
+        lines += [f"{x * 0.08 + 90} {y * 0.08 + 150}" for x, y in pts]
+        lines.append(kind)
+        if kind == "Motion":
+            lines.append(f"{vel[0] * 0.1} {vel[1] * 0.1}")
+    (directory / "data.txt").write_text("\n".join(lines) + "\n")
+    (directory / "config.txt").write_text(
+        "dimension\t2D\nviscosity\t0.05\ndensity\t1000.0\nbc_type\tNoSlip\nbc_strenght\t0.5\ngrid_dx\t0.0008\ngrid_dy\t0.0008\n"
+        "cycles\t1\ntime_steps\t40\nout_time_steps\t10\nout_gridx\t30\nout_gridy\t25\nout_fmt\tNetCDF\nsolver\tADI\nnum_global\t2\nnum_local\t1\n")
+    return directory / "data.txt", directory / "config.txt"
+
+
+@pytest.mark.gpu
+def test_reference_2d_driver_with_b200_solver(oracle_mod, tmp_path):
+    """Drop-in boundary of the 2D solver end to end: the reference's own Grid2D / Config + the Solver2D adapter
+    (cmc_fluid_solver_b200/host/B200AdiSolver2D.*) + libcmcadi.so (oracle/_ref/dropin2d_f32, built by
+    oracle/build_ref.sh) against the reference CPU solver (oracle/_ref/ref_probe2d_f32) on the same case files:
+    bit-identical layers, residuals and GetLayer outputs over all steps."""
+    import subprocess
+    from conftest import ROOT
+    O = oracle_mod
+    ref_bin, drop_bin = ROOT / "oracle" / "_ref" / "ref_probe2d_f32", ROOT / "oracle" / "_ref" / "dropin2d_f32"
+    if not (ref_bin.exists() and drop_bin.exists()):
+        pytest.skip("oracle/_ref/dropin2d_f32 not built (needs /root/reference at build time)")
+    data, cfg = _write_2d_case(tmp_path)
+    for binary, out, solver in ((ref_bin, "cpu.bin", "cpu"), (drop_bin, "gpu.bin", "b200")):
+        r = subprocess.run([str(binary), str(data), str(cfg), str(tmp_path / out), "0", "dump=every", f"solver={solver}"],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    a, b = O.read_probe2d(tmp_path / "cpu.bin"), O.read_probe2d(tmp_path / "gpu.bin")
+    assert (a["dimx"], a["dimy"]) == (b["dimx"], b["dimy"]) and len(a["layers"]) == len(b["layers"]) == 40     # initial + 39 steps
+    for s in a["layers"]:
+        assert a["errs"][s] == b["errs"][s], f"residual differs at step {s}"
+        for q in range(3):
+            assert np.array_equal(a["layers"][s][q], b["layers"][s][q]), f"step {s} field {q}"
+    assert set(a["outputs"]) == set(b["outputs"]) and len(a["outputs"]) >= 3
+    for s in a["outputs"]:
+        assert np.array_equal(a["outputs"][s][0], b["outputs"][s][0]) and np.array_equal(a["outputs"][s][1], b["outputs"][s][1])
+    for s in a["grids"]:        # SetGridBoundaries fed the same velocities back into the reference's grid
+        for k in ("type", "bc", "vx", "vy", "T"):
+            assert np.array_equal(a["grids"][s][k], b["grids"][s][k]), f"grid {k} differs at step {s}"
