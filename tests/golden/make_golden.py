@@ -30,10 +30,26 @@ CASES = [
 ]
 
 
+# the reference's OWN shipped case data/3D/example_tests/non_uniform_pipe (Shape2D outline + depth_var bottom, no `align`:
+# 53 x 53 x 52 in fp32; SURVEY 8(c): NODE_IN = 99959 of 146068, first residual 0.00001366), read by its own loader
+REF_CASES = [
+    ("nupipe_f64", 8, "non_uniform_pipe/non_uniform_pipe_2D", False, 3),
+    ("nupipe_f32", 4, "non_uniform_pipe/non_uniform_pipe_2D", False, 3),
+]
+REF_DATA = Path("/root/reference/data/3D/example_tests")
+
+
 def main():
-    for name, fp, outline, kw, align, steps in CASES:
+    jobs = [(name, fp, outline, kw, align, steps, None) for name, fp, outline, kw, align, steps in CASES]
+    jobs += [(name, fp, None, None, align, steps, stem) for name, fp, stem, align, steps in REF_CASES]
+    for name, fp, outline, kw, align, steps, stem in jobs:
         with tempfile.TemporaryDirectory() as td:
-            data, cfg = write_shape2d_case(td, name, outline=outline, **kw)
+            if stem is None:
+                data, cfg = write_shape2d_case(td, name, outline=outline, **kw)
+            else:       # the reference's files as shipped, CR stripped (bin/Release/run_examples_CPU.sh:12-16)
+                data, cfg = Path(td) / "data.txt", Path(td) / "config.txt"
+                data.write_bytes((REF_DATA / f"{stem}_data.txt").read_bytes().replace(b"\r", b""))
+                cfg.write_bytes((REF_DATA / f"{stem}_config.txt").read_bytes().replace(b"\r", b""))
             out = Path(td) / "dump.bin"
             log = O.run_ref(data, cfg, out, steps, fp_bytes=fp, align=align, dump="every", getlayer=True)
             case = O.read_probe(out)
@@ -54,6 +70,8 @@ def main():
         )
         t = case.type.reshape(case.shape)
         assert not any(((t == 0)[sl]).any() for sl in [np.s_[0], np.s_[-1], np.s_[:, 0], np.s_[:, -1], np.s_[:, :, 0], np.s_[:, :, -1]]), "IN cell on a face"
+        if name == "nupipe_f32":
+            assert case.shape == (53, 53, 52) and case.n_in == 99959 and f"{cur[0]['err']:.8f}" == "0.00001366", "SURVEY 8(c) known answers"
         print(name, case.shape, "NODE_IN", case.n_in, "err", [f"{s['err']:.6e}" for s in cur], log.splitlines()[0])
 
 

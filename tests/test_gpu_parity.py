@@ -33,7 +33,7 @@ def _check_fields(O, ora, sol, case, mode, what=""):
 
 
 @pytest.mark.parametrize("mode", ["exact", "fast"])
-@pytest.mark.parametrize("name", ["box32_f64", "box32_f32", "baffle32_f64", "baffle32_f32"])
+@pytest.mark.parametrize("name", ["box32_f64", "box32_f32", "baffle32_f64", "baffle32_f32", "nupipe_f64", "nupipe_f32"])
 def test_golden_vectors_from_the_reference(name, mode):
     case, exp = load_golden(name)
     s = AdiSolver3D().Init(case, mode=mode)

@@ -11,7 +11,7 @@ from conftest import drive, load_golden
 from cmc_fluid_solver_b200.cases import BAFFLE_OUTLINE, BOX_OUTLINE, write_shape2d_case
 
 
-@pytest.mark.parametrize("name", ["box32_f64", "box32_f32", "baffle32_f64", "baffle32_f32"])
+@pytest.mark.parametrize("name", ["box32_f64", "box32_f32", "baffle32_f64", "baffle32_f32", "nupipe_f64", "nupipe_f32"])
 def test_oracle_matches_golden_bitwise(oracle_mod, name):
     O = oracle_mod
     case, exp = load_golden(name)
