@@ -55,5 +55,32 @@ def main():
     print("steps", steps, "non-IN cells", nonin.size, "err[0], err[-1] =", d["errs"][0], d["errs"][steps - 1])
 
 
+def main_dynamic(name="heart_MR", steps=10):
+    """A moving-boundary case of the reference (data/2D/heart_MR: 25 frames, the node types change almost every step):
+    the full grid arrays of the first `steps` steps, every layer's checksum and the last layer."""
+    ref = Path("/root/reference/data/2D") / name
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        (td / "data.txt").write_bytes((ref / f"{name}_data.txt").read_bytes().replace(b"\r", b""))
+        cfg = (ref / f"{name}_config.txt").read_bytes().replace(b"\r", b"").decode()
+        (td / "config.txt").write_text("\n".join("solver\t\tADI" if ln.startswith("solver") else ln for ln in cfg.splitlines()) + "\n")
+        O.run_ref2d(td / "data.txt", td / "config.txt", td / "out.bin", steps, "every")
+        d = O.read_probe2d(td / "out.bin")
+    g = d["grids"]
+    changed = sum(not np.array_equal(g[s]["type"], g[s - 1]["type"]) for s in range(1, steps))
+    np.savez_compressed(
+        Path(__file__).resolve().parent / f"{name.lower()}2d_f32.npz",
+        dims=np.array([d["dimx"], d["dimy"]]), spacing=np.array([d["dx"], d["dy"]]), dt=d["dt"],
+        params=np.array([d["v_T"], d["v_vis"], d["t_vis"], d["t_phi"]]), startT=d["startT"],
+        iters=np.array([d["num_global"], d["num_local"]]), steps=steps,
+        type=np.stack([g[s]["type"] for s in range(steps)]).astype(np.int8), bc=np.stack([g[s]["bc"] for s in range(steps)]).astype(np.int8),
+        gvx=np.stack([g[s]["vx"] for s in range(steps)]), gvy=np.stack([g[s]["vy"] for s in range(steps)]), gT=np.stack([g[s]["T"] for s in range(steps)]),
+        layer_init=np.stack(d["layers"][-1]), layer_last=np.stack(d["layers"][steps - 1]),
+        err=np.array([d["errs"][s] for s in range(steps)]),
+        sums=np.array([[float(np.sum(d["layers"][s][q].astype(np.float64))) for q in range(3)] for s in range(steps)]))
+    print(name, d["dimx"], d["dimy"], "steps", steps, "node types changed in", changed, "of them")
+
+
 if __name__ == "__main__":
     main()
+    main_dynamic()

@@ -133,3 +133,19 @@ def test_reference_2d_driver_with_b200_solver(oracle_mod, tmp_path):
     for s in a["grids"]:        # SetGridBoundaries fed the same velocities back into the reference's grid
         for k in ("type", "bc", "vx", "vy", "T"):
             assert np.array_equal(a["grids"][s][k], b["grids"][s][k]), f"grid {k} differs at step {s}"
+
+
+@pytest.mark.gpu
+def test_moving_boundaries_2d_matches_reference_bitwise():
+    """Golden vectors of the reference's moving-boundary case data/2D/heart_MR (node types change every step: the
+    segments are rebuilt on the device inside every TimeStep, like AdiSolver2D::CreateSegments)."""
+    from cmc_fluid_solver_b200 import AdiSolver2D
+    from conftest import GOLDEN
+    from test_oracle2d import drive_dynamic
+    z = np.load(GOLDEN / "heart_mr2d_f32.npz")
+    dimx, dimy = (int(v) for v in z["dims"])
+    s = AdiSolver2D().Init(dimx, dimy, *[float(v) for v in z["spacing"]], *[float(v) for v in z["params"]], float(z["startT"]), 4)
+    for q in range(3):
+        s.write_field(0, q, z["layer_init"][q])
+    drive_dynamic(s, z, lambda q: s.read_field(0, q))
+    s.close()

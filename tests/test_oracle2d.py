@@ -108,3 +108,57 @@ def test_segments_2d(oracle_mod):
     ty = z["type"].reshape(dimx, dimy)
     assert f(o.h, 0) == int(np.sum((ty == 0).any(axis=1))) and f(o.h, 1) == int(np.sum((ty == 0).any(axis=0)))
     o.close()
+
+
+def drive_dynamic(solver, z, read):
+    """The moving-boundary golden (reference data/2D/heart_MR): the full grid arrays change every step."""
+    errs = []
+    for s in range(int(z["steps"])):
+        solver.set_grid(z["type"][s].astype(np.int32), z["bc"][s].astype(np.int32), z["gvx"][s], z["gvy"][s], z["gT"][s])
+        solver.update_boundaries()
+        errs.append(solver.time_step(float(z["dt"]), int(z["iters"][0]), int(z["iters"][1])))
+        for q in range(3):
+            assert float(np.sum(read(q).astype(np.float64))) == z["sums"][s, q], f"step {s} field {q}"
+    assert np.array_equal(np.array(errs), z["err"])
+    for q in range(3):
+        assert np.array_equal(read(q), z["layer_last"][q])
+
+
+def test_oracle2d_moving_boundaries_golden(oracle_mod):
+    O = oracle_mod
+    z = np.load(GOLDEN / "heart_mr2d_f32.npz")
+    dimx, dimy = (int(v) for v in z["dims"])
+    assert any(not np.array_equal(z["type"][s], z["type"][s - 1]) for s in range(1, int(z["steps"])))     # the mask really moves
+    o = O.Oracle2D(dimx, dimy, *[float(v) for v in z["spacing"]], *[float(v) for v in z["params"]], float(z["startT"]), 4)
+    for q in range(3):
+        o.field(0, q)[:] = z["layer_init"][q]
+    drive_dynamic(o, z, lambda q: o.field(0, q))
+    o.close()
+
+
+@pytest.mark.parametrize("name", ["heart_MR", "heart_US"])
+def test_oracle2d_moving_boundaries_reference_binary(oracle_mod, tmp_path, name):
+    """120 steps of the reference's moving-boundary cases (25 / 80 frames): every layer and residual bit-for-bit."""
+    O = oracle_mod
+    ref = Path("/root/reference/data/2D") / name
+    if not (O.ref2d_binary().exists() and ref.is_dir()):
+        pytest.skip("oracle/_ref/ref_probe2d_f32 or /root/reference not present")
+    (tmp_path / "data.txt").write_bytes((ref / f"{name}_data.txt").read_bytes().replace(b"\r", b""))
+    cfg = (ref / f"{name}_config.txt").read_bytes().replace(b"\r", b"").decode()
+    (tmp_path / "config.txt").write_text("\n".join("solver\t\tADI" if ln.startswith("solver") else ln for ln in cfg.splitlines()) + "\n")
+    O.run_ref2d(tmp_path / "data.txt", tmp_path / "config.txt", tmp_path / "out.bin", 120, "every")
+    d = O.read_probe2d(tmp_path / "out.bin")
+    o = O.Oracle2D(d["dimx"], d["dimy"], d["dx"], d["dy"], d["v_T"], d["v_vis"], d["t_vis"], d["t_phi"], d["startT"], d["fp_bytes"])
+    for q in range(3):
+        o.field(0, q)[:] = d["layers"][-1][q]
+    changed = 0
+    for s in range(len(d["grids"])):
+        g = d["grids"][s]
+        changed += s > 0 and not np.array_equal(g["type"], d["grids"][s - 1]["type"])
+        o.set_grid(g["type"], g["bc"], g["vx"], g["vy"], g["T"])
+        o.update_boundaries()
+        assert o.time_step(d["dt"], d["num_global"], d["num_local"]) == d["errs"][s]
+        for q in range(3):
+            assert np.array_equal(o.field(0, q), d["layers"][s][q]), f"{name} step {s} field {q}"
+    assert changed > 50
+    o.close()
