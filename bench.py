@@ -317,7 +317,7 @@ def main():
             "dtype": "f64" if fpb == 8 else "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "grid": [DX, DY, DZ], "num_global": NUM_GLOBAL, "num_local": NUM_LOCAL,
                        "sweeps_per_step": NUM_GLOBAL * 3 * NUM_LOCAL, "fluid_fraction": round(fluid, 4), "mode": args.mode,
-                       "parallelism": f"x-slab x{world}", "exchange": sol.exchange_kind(), "residual": "every 10th step (reference driver cadence)",
+                       "parallelism": f"x-slab x{world}", "exchange": sol.exchange_kind(), "storage": f"SoA, y-blocked ({sol.storage_block_rows()} rows per block)" if sol.storage_block_rows() else "SoA [i][j][k]", "residual": "every 10th step (reference driver cadence)",
                        "l2": f"inputs larger than L2: each field {ncells * fpb / 1e9:.2f} GB, 20 resident fields"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clk, "residual": err, "device_bytes": sol.device_bytes(),

@@ -1105,6 +1105,7 @@ int cmc_adi3d_get_option(const cmc_adi3d *h, const char *key, int64_t *value)
 	if (!strcmp(key, "mode")) { *value = h->mode; return CMC_OK; }
 	if (!strcmp(key, "fold_boundaries")) { *value = h->fold_boundaries; return CMC_OK; }
 	if (!strcmp(key, "nzp")) { *value = h->L.nzp; return CMC_OK; }
+	if (!strcmp(key, "jb")) { *value = h->L.nblk == 1 ? 0 : (1 << h->L.jbs); return CMC_OK; }   // rows per y-block, 0 = one block
 	if (!strcmp(key, "exchange")) { *value = h->exchange_kind(); return CMC_OK; }   // 0 none, 1 NCCL send/recv, 2 fused stores (same device), 3 fused stores (peer memory)
 	if (!strcmp(key, "shared_free_cells")) { *value = h->shared_free[0] + h->shared_free[1] + h->shared_free[2]; return CMC_OK; }
 	return fail(CMC_ERR_INVALID, std::string("get_option: unknown key ") + key);

@@ -205,6 +205,11 @@ class AdiSolver3D:
             out[name] = (ms.value, n.value)
         return out
 
+    def storage_block_rows(self) -> int:
+        v = C.c_int64(0)
+        _check(load_library().cmc_adi3d_get_option(self._h, b"jb", C.byref(v)))
+        return v.value
+
     def exchange_kind(self) -> str:
         v = C.c_int64(0)
         _check(load_library().cmc_adi3d_get_option(self._h, b"exchange", C.byref(v)))

@@ -127,7 +127,7 @@ int cmc_adi3d_time_step(cmc_adi3d *h, double dt, int num_global, int num_local,
 int cmc_adi3d_get_layer(cmc_adi3d *h, void *vel_xyz, double *T, int outdimx, int outdimy, int outdimz);
 
 /* ---- options ----  "mode": CMC_MODE_FAST | CMC_MODE_EXACT;  "profile": 0|1|2 (see cmc_adi3d_get_timing);
- * read-only: "nzp" (padded z-line length), "exchange" (how slabs exchange planes and interface systems: 0 single slab,
+ * read-only: "nzp" (padded z-line length), "jb" (rows per y-block of the field storage, 0 = one block), "exchange" (how slabs exchange planes and interface systems: 0 single slab,
  * 1 NCCL send/recv groups, 2 stores fused into the sweep kernels (slabs on one device), 3 the same into peer memory
  * over NVLink - every rank maps the other ranks' exchange arena with CUDA IPC) */
 int cmc_adi3d_set_option(cmc_adi3d *h, const char *key, int64_t value);
