@@ -114,3 +114,31 @@ def test_segment_generation_edge_cases(oracle_mod):
     got = [(int(s[2]), int(s[5]), int(s[6])) for s in segs if s[0] == 1 and s[1] == 1]
     # [0..2] (starts ON an IN cell at index 0), [2..5] shares cell 2, [7..9]; the run 13..15 is unterminated -> dropped
     assert got == [(0, 2, 3), (2, 5, 4), (7, 9, 3)]
+
+
+@pytest.mark.parametrize("fp", [4, 8])
+@pytest.mark.parametrize("iters", [(1, 1), (2, 3), (3, 1)])
+def test_iteration_counts_match_reference_binary(oracle_mod, tmp_path, fp, iters):
+    """num_global / num_local other than the shipped 4 / 2: the outer (global) and inner (local) iteration structure of
+    AdiSolver3D::TimeStep / SolveDirection (AdiSolver3D.cpp:335-358, 589-655) - merges after every local iteration,
+    one more merge per global iteration - bit-for-bit against the reference binary."""
+    O = oracle_mod
+    if not O.have_ref(fp):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    ng, nl = iters
+    case = _ref_case(O, tmp_path, fp, BAFFLE_OUTLINE, 3, True, grid_d=0.045, depth_var=0.2, time_steps=300, num_global=ng, num_local=nl,
+                     out_grid=(8, 9, 7), rim=True)
+    assert (case.num_global, case.num_local) == (ng, nl)
+    o = O.Oracle3D(case)
+    o.create_segments()
+    snaps = {(s["step"], s["kind"]): s for s in case.snapshots}
+    for i in range(3):
+        o.update_boundaries()
+        err = o.time_step(case.dt, ng, nl, (i % 10 == 0) or i == 2)      # the driver's computeError cadence (FluidSolver3D.cpp:242)
+        if i % 10 == 0:          # the probe's driver loop reads a layer here (GetLayer mutates the previous layer)
+            vel, T = o.get_layer(*case.outdims)
+            assert np.array_equal(vel, snaps[(i, 1)]["vel"]) and np.array_equal(T, snaps[(i, 1)]["T"])
+        s = snaps[(i, 0)]
+        assert err == s["err"]
+        for q, n in enumerate("uvwT"):
+            assert np.array_equal(o.field(O.LAYER_CUR, q).ravel(), s[n]), f"({ng},{nl}) step {i} field {n}"
