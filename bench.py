@@ -86,45 +86,93 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------- reference CPU arm
-def run_reference_cpu(steps, warmup, size=128, fp_bytes=8):
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def host_mem_gb():
+    try:
+        for ln in Path("/proc/meminfo").read_text().splitlines():
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+# the masked channel family in the reference's own case format (Shape2D outline + depth_var bottom, `align`), per size
+REF_GRID = {64: dict(grid_d=0.02, depth=1.0), 128: dict(grid_d=0.0095, depth=1.0), 256: dict(grid_d=0.0045, depth=1.14),
+            512: dict(grid_d=0.00215, depth=1.09)}
+
+
+def pick_ref_size(want, budget_s, steps):
+    """Largest grid of the family (<= the workload's) whose `steps` reference steps fit the time budget on this host:
+    the reference CPU solver does about 0.27 Mcell-updates/s per core (measured: 4.4 at 16 cores, 6.4 at 32) and needs
+    about 280 bytes of host memory per cell."""
+    cores, mem = host_cores(), host_mem_gb()
+    for size in (512, 256, 128, 64):
+        if size > want:
+            continue
+        cells = size ** 3
+        if cells * steps / (0.27e6 * cores) <= budget_s and cells * 280 / 1e9 <= 0.8 * mem:
+            return size
+    return 64
+
+
+def run_reference_cpu(steps, warmup, size=128, fp_bytes=8, threads=None):
     """The reference's own CPU solver (oracle/_ref/ref_probe3d_*, built from the unmodified reference sources) on a
-    bounded sample of the workload: the same masked channel family at size^3 read by the reference's own loader."""
+    bounded sample of the workload: the same masked channel family at size^3 read by the reference's own loader, on
+    all host cores (the thread count is passed explicitly: torchrun exports OMP_NUM_THREADS=1)."""
     from cmc_fluid_solver_b200.cases import BAFFLE_OUTLINE, write_shape2d_case
     from oracle import oracle as O
     if not O.have_ref(fp_bytes):
         return None
-    grid_d = {64: 0.02, 128: 0.0095, 256: 0.0045}.get(size, 1.2 / size)
+    threads = threads or host_cores()
+    kw = REF_GRID.get(size, dict(grid_d=1.2 / size, depth=1.0))
     with tempfile.TemporaryDirectory() as td:
-        data, cfg = write_shape2d_case(td, "bench", outline=BAFFLE_OUTLINE, grid_d=grid_d, depth=1.0 if size <= 128 else 1.14,
-                                       depth_var=0.2, time_steps=100, num_global=NUM_GLOBAL, num_local=NUM_LOCAL)
-        out = O.run_ref(data, cfg, "-", steps + warmup, fp_bytes=fp_bytes, align=True, dump="none")
+        data, cfg = write_shape2d_case(td, "bench", outline=BAFFLE_OUTLINE, depth_var=0.2, time_steps=100, num_global=NUM_GLOBAL,
+                                       num_local=NUM_LOCAL, **kw)
+        out = O.run_ref(data, cfg, "-", steps + warmup, fp_bytes=fp_bytes, align=True, dump="none", threads=threads)
     m = re.search(r"grid (\d+) x (\d+) x (\d+), NODE_IN (\d+).*threads (\d+)", out)
     dims = tuple(int(m.group(i)) for i in (1, 2, 3))
-    threads = int(m.group(5))
+    used = int(m.group(5))
     times = [float(x) for x in re.findall(r"probe: step \d+ seconds ([0-9.]+)", out)]
     timed = times[warmup:]
     ncells = dims[0] * dims[1] * dims[2]
     sec = sum(timed) / max(len(timed), 1)
-    return dict(value=ncells / sec / 1e6, sec_per_step=sec, dims=dims, cores=threads, steps=len(timed),
+    return dict(value=ncells / sec / 1e6, sec_per_step=sec, dims=dims, cores=used, steps=len(timed),
                 fluid_fraction=int(m.group(4)) / ncells)
 
 
+def cpu_sample_text(r):
+    return (f"{r['dims'][0]}x{r['dims'][1]}x{r['dims'][2]} masked channel (wall-attached baffle + depth_var 0.2 bottom, the workload's "
+            f"family read by the reference's own loader), fp64, {r['steps']} timed TimeSteps ({r['sec_per_step']:.2f} s/step) of the "
+            f"reference CPU/OpenMP solver built from its unmodified sources (g++ -O2 -fopenmp), {r['cores']} threads")
+
+
 def reference_arm(args):
+    """bench.py --impl reference: rank 0 alone runs the reference CPU solver on all host cores; the other ranks exit."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = run_reference_cpu(args.steps, args.warmup, size=args.ref_size)
+    # each "step" is a bounded sample: at most 2 timed steps (+1 warm-up) of the largest grid of the workload's family
+    # that fits about two minutes on this host - the 512^3 workload itself on a 16-core box
+    timed = max(1, min(args.steps, 2))
+    size = args.ref_size or pick_ref_size(args.size, 150.0, timed + 1)
+    r = run_reference_cpu(timed, 1, size=size)
     if r is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_probe3d_f64 not built (needs /root/reference at build time)"}))
         return
-    sample = (f"{r['dims'][0]}x{r['dims'][1]}x{r['dims'][2]} masked channel (baffle + bottom perturbation), fp64, "
-              f"{r['steps']} timed TimeSteps of the reference CPU/OpenMP solver (unmodified sources, g++ -O2 -fopenmp)")
+    sample = cpu_sample_text(r)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "num_global": NUM_GLOBAL, "num_local": NUM_LOCAL,
-                   "note": "each step is a bounded sample of the workload: " + sample},
+        "config": bench_config(args, world=args.gpus),
+        "sample": sample, "sample_grid": list(r["dims"]), "steps_timed": r["steps"],
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -132,9 +180,29 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
-def workload_name(args):
+def grid_dims(args, world):
+    if args.dims:
+        return tuple(int(v) for v in args.dims.split(","))
+    if args.scaling == "weak":      # BASELINE config 5: 128 x 512 x 512 per GPU => 1024 x 512 x 512 at 8 GPUs
+        return (128 * world, 512, 512)
+    return (args.size, args.size, args.size)
+
+
+def workload_name(args, world=1):
+    if args.scaling == "weak":
+        return (f"3D weak scaling, 128x512x512 masked channel cells per GPU (1024x512x512 at 8 GPUs; wall-attached baffle + depth_var 0.2 "
+                f"bottom), fp{args.fp * 8}, ADI step num_global {NUM_GLOBAL} num_local {NUM_LOCAL}")
     s = args.size
     return f"3D {s}^3 masked channel (wall-attached baffle + depth_var 0.2 bottom), fp{args.fp * 8}, ADI step num_global {NUM_GLOBAL} num_local {NUM_LOCAL}"
+
+
+def bench_config(args, world):
+    """The `config` object of the JSON line: identical for both arms (it names the workload, not the implementation)."""
+    DX, DY, DZ = grid_dims(args, world)
+    return {"workload": workload_name(args, world), "grid": [DX, DY, DZ], "num_global": NUM_GLOBAL, "num_local": NUM_LOCAL,
+            "sweeps_per_step": NUM_GLOBAL * 3 * NUM_LOCAL, "parallelism": f"x-slab x{world}",
+            "residual": "every 10th step (reference driver cadence)",
+            "l2": f"inputs larger than L2: each field {DX * DY * DZ * args.fp / 1e9:.2f} GB, 20 resident fields"}
 
 
 # ------------------------------------------------------------------------------------------------- ours
@@ -148,8 +216,10 @@ def main():
     ap.add_argument("--dims", default=None, help="X,Y,Z grid instead of --size^3 (experiments)")
     ap.add_argument("--fp", type=int, default=8, choices=[4, 8])
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
-    ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--ref-size", type=int, default=128)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--ref-size", type=int, default=0, help="grid of the reference arm's sample (0 = the largest of 512/256/128 that fits ~2 minutes)")
+    ap.add_argument("--cpu-size", type=int, default=128, help="grid of the cpu_baseline leg printed with our own arm")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="weak = BASELINE config 5: 128x512x512 cells per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -181,8 +251,7 @@ def main():
         dist.broadcast(idt, 0)
         nccl_id = bytes(idt.cpu().numpy().tobytes())
 
-    S = args.size
-    DX, DY, DZ = (int(v) for v in args.dims.split(",")) if args.dims else (S, S, S)
+    DX, DY, DZ = grid_dims(args, world)
     case = channel_case(DX, DY, DZ, fp_bytes=args.fp, depth_var=0.2)
     ncells = case.ncells
     fluid = case.n_in / ncells
@@ -230,34 +299,54 @@ def main():
         ms = float(t.item())
     value = ncells * args.steps / (ms * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel (directional sweep): algorithmic bytes per launch / avg launch duration ----
+    # ---- per-field checksums of the final layer (all-reduced): the same numbers at every N ----------------------------
+    sums = sol.field_sums(0)
+    checksums = {n: {"sum": v[0], "l2": v[1] ** 0.5} for n, v in sums.items()}
+
+    # ---- roofline of the dominant kernel: algorithmic bytes per launch / average launch duration ---------------------
+    # a directional sweep reads cur x4 + temp x4, writes next x4 + temp' x4 and reads 1 descriptor byte per
+    # cell.  N > 1: the slab-coupled x-sweep is TWO passes over the slab - the spike pass reads 8 values + 1 byte and
+    # writes nothing, the coupled pass moves the 16 + 1 - plus the interface solve; it is counted ONCE, with those bytes,
+    # over the sum of its three spans.
     fpb = args.fp
     local_cells = sol.nx * case.dimy * case.dimz
-    sweep_bytes = local_cells * (16 * fpb + 1)             # read cur x4 + temp x4, write next x4 + temp' x4, 1 descriptor byte
+    sweep_bytes = local_cells * (16 * fpb + 1)
+    spike_bytes = local_cells * (8 * fpb + 1)
     peak, peak_src = peaks()
     per_dir = {}
     for k in ("sweep_x", "sweep_y", "sweep_z"):
         tot, n = timings[k]
-        if n:
-            per_dir[k] = {"ms_per_launch": tot / n, "launches": n, "gbs": sweep_bytes / (tot / n * 1e-3) / 1e9}
+        if not n:
+            continue
+        nbytes = sweep_bytes
+        if k == "sweep_x" and timings["x_spike"][1]:
+            tot += timings["x_spike"][0] + timings["x_interface"][0]
+            nbytes += spike_bytes
+        per_dir[k] = {"ms_per_launch": tot / n, "launches": n, "bytes_per_launch": nbytes, "gbs": nbytes / (tot / n * 1e-3) / 1e9,
+                      "frac": nbytes / (tot / n * 1e-3) / 1e9 / peak}
     dom = max(per_dir, key=lambda k: per_dir[k]["ms_per_launch"] * per_dir[k]["launches"]) if per_dir else None
-    sweep_ms = sum(timings[k][0] for k in ("sweep_x", "sweep_y", "sweep_z"))
-    sweep_n = sum(timings[k][1] for k in ("sweep_x", "sweep_y", "sweep_z"))
-    achieved = sweep_bytes * sweep_n / (sweep_ms * 1e-3) / 1e9 if sweep_ms else None
+    sweep_ms = sum(v["ms_per_launch"] * v["launches"] for v in per_dir.values())
+    sweep_n = sum(v["launches"] for v in per_dir.values())
     step_bytes = local_cells * (NUM_GLOBAL * 3 * NUM_LOCAL * (16 * fpb + 1) + NUM_GLOBAL * 12 * fpb + 8 * fpb)   # BASELINE.md B_step
     # measured DRAM traffic per launch of the dominant kernel: one ncu --set full capture, committed under profiles/
-    traffic = None
-    tp = ROOT / "profiles" / "r01_ncu_traffic.json"
+    traffic, traffic_src = None, None
     key = f"{DX}x{DY}x{DZ}_f{fpb * 8}"
-    if tp.exists() and world == 1 and dom:
-        traffic = json.loads(tp.read_text()).get(key, {}).get(dom, {}).get("dram_bytes")
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        tp = ROOT / "profiles" / name
+        if tp.exists() and world == 1 and dom:
+            traffic = json.loads(tp.read_text()).get(key, {}).get(dom, {}).get("dram_bytes")
+            if traffic:
+                traffic_src = f"profiles/{name} (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch of the dominant kernel)"
+                break
+    kname = {"sweep_x": "x", "sweep_y": "y", "sweep_z": "z"}
     roofline = {
-        "bound": "hbm", "kernel": "k_fast_sweep<%s,X|Y|Z> (all three directions, %d launches)" % ("double" if fpb == 8 else "float", sweep_n),
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic,
-        "traffic_source": "profiles/r01_ncu_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch of the dominant kernel)" if traffic else None,
-        "peak_source": peak_src, "algorithmic_bytes_per_launch": sweep_bytes,
+        "bound": "hbm", "kernel": f"directional sweep along {kname[dom]} ({sol.sweep_kernel_name(dom)})" if dom else None,
+        "achieved": per_dir[dom]["gbs"] if dom else None, "peak": peak, "unit": "GB/s",
+        "frac": per_dir[dom]["frac"] if dom else None, "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": per_dir[dom]["bytes_per_launch"] if dom else None,
         "per_direction": per_dir, "dominant": dom,
-        "sweep_share_of_step": sweep_ms / (ms if world == 1 else max(ms, 1e-9)),
+        "all_sweeps_gbs": sum(v["bytes_per_launch"] * v["launches"] for v in per_dir.values()) / (sweep_ms * 1e-3) / 1e9 if sweep_ms else None,
+        "sweep_share_of_step": sweep_ms / max(ms, 1e-9),
         "step_achieved_gbs": step_bytes * args.steps / (ms * 1e-3) / 1e9, "step_frac": step_bytes * args.steps / (ms * 1e-3) / 1e9 / peak,
         "kernel_ms": {k: v[0] / args.steps for k, v in timings.items() if v[1]},
     }
@@ -300,27 +389,24 @@ def main():
                        "resolution (HBM -> pinned host on rank 0); host wall clock between barriers, max over ranks"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         try:
-            r = run_reference_cpu(3, 1, size=args.ref_size)
+            r = run_reference_cpu(3, 1, size=args.cpu_size)
             if r:
-                cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
-                       "sample": f"{r['dims'][0]}x{r['dims'][1]}x{r['dims'][2]} masked channel of the same family, fp64, {r['steps']} timed steps "
-                                 f"({r['sec_per_step']:.2f} s/step) of the reference CPU/OpenMP solver built from its unmodified sources"}
+                cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": cpu_sample_text(r)}
         except Exception as ex:      # noqa: BLE001
-            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+            cpu = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "reference", "sample": f"failed: {ex}"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64" if fpb == 8 else "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "grid": [DX, DY, DZ], "num_global": NUM_GLOBAL, "num_local": NUM_LOCAL,
-                       "sweeps_per_step": NUM_GLOBAL * 3 * NUM_LOCAL, "fluid_fraction": round(fluid, 4), "mode": args.mode,
-                       "parallelism": f"x-slab x{world}", "exchange": sol.exchange_kind(), "storage": f"SoA, y-blocked ({sol.storage_block_rows()} rows per block)" if sol.storage_block_rows() else "SoA [i][j][k]", "residual": "every 10th step (reference driver cadence)",
-                       "l2": f"inputs larger than L2: each field {ncells * fpb / 1e9:.2f} GB, 20 resident fields"},
+            "config": bench_config(args, world),
+            "implementation": {"mode": args.mode, "exchange": sol.exchange_kind(), "fluid_fraction": round(fluid, 4),
+                               "storage": f"SoA, y-blocked ({sol.storage_block_rows()} rows per block)" if sol.storage_block_rows() else "SoA [i][j][k]"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clk, "residual": err, "device_bytes": sol.device_bytes(),
+            "clocks": clk, "residual": err, "checksums": checksums, "device_bytes": sol.device_bytes(),
         }
         print(json.dumps(line))
     sol.close()

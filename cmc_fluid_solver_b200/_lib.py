@@ -15,7 +15,7 @@ SYMBOLS = [
     "cmc_adi3d_update_boundaries", "cmc_adi3d_time_step", "cmc_adi3d_get_layer",
     "cmc_adi3d_set_option", "cmc_adi3d_get_option",
     "cmc_adi3d_read_field", "cmc_adi3d_write_field", "cmc_adi3d_step_prologue", "cmc_adi3d_solve_direction",
-    "cmc_adi3d_eval_div_error", "cmc_adi3d_time_step_async", "cmc_adi3d_sync", "cmc_adi3d_stream",
+    "cmc_adi3d_eval_div_error", "cmc_adi3d_field_sums", "cmc_adi3d_time_step_async", "cmc_adi3d_sync", "cmc_adi3d_stream",
     "cmc_adi3d_launch_count", "cmc_adi3d_get_timing", "cmc_adi3d_device_bytes", "cmc_solve_tridiagonal_batch",
     "cmc_adi2d_create", "cmc_adi2d_destroy", "cmc_adi2d_set_grid", "cmc_adi2d_init_layer", "cmc_adi2d_update_boundaries",
     "cmc_adi2d_time_step", "cmc_adi2d_get_layer", "cmc_adi2d_read_field", "cmc_adi2d_write_field", "cmc_adi2d_launch_count",
@@ -71,6 +71,7 @@ def load_library() -> C.CDLL:
         "cmc_adi3d_step_prologue": [vp],
         "cmc_adi3d_solve_direction": [vp, i32, dbl, i32, i32, i32],
         "cmc_adi3d_eval_div_error": [vp, i32, P(dbl)],
+        "cmc_adi3d_field_sums": [vp, i32, P(dbl)],
         "cmc_adi3d_time_step_async": [vp, dbl, i32, i32, i32],
         "cmc_adi3d_sync": [vp, P(dbl)],
         "cmc_adi3d_stream": [vp, P(vp)],

@@ -59,7 +59,9 @@ struct cmc_adi3d {
 	virtual int step_prologue() = 0;
 	virtual int solve_direction(int dir, double dt, int nl, int cur_layer, int next_layer) = 0;
 	virtual int eval_div_error(int layer, double *err) = 0;
+	virtual int field_sums(int layer, double *sums8) = 0;
 	virtual int exchange_kind() const = 0;
+	virtual int kernel_kind(int dir) const = 0;
 
 	int device = 0, fp = 8;
 	int rank = 0, nranks = 1;       // position of this handle's (first) slab among all slabs of the grid
@@ -70,7 +72,6 @@ struct cmc_adi3d {
 	long long num_segs[3] = {0, 0, 0};
 	long long shared_free[3] = {0, 0, 0};   // cells shared by two segments with a BC_FREE row (informational)
 	int mode = CMC_MODE_FAST;
-	int fold_boundaries = 0;
 	bool have_nodes = false, have_lines = false;
 
 	// optional per-kernel-kind device timing (cmc_adi3d_set_option "profile"): CUDA event pairs on `stream`
@@ -131,7 +132,7 @@ struct Slab {
 	uint8_t *role[3] = {};
 	uint8_t *ncode = nullptr;      // whole-grid node codes (only until the line descriptors are built)
 	FT *cv = nullptr, *cT = nullptr;
-	double *d_partials = nullptr, *d_err2 = nullptr;
+	double *d_partials = nullptr, *d_err2 = nullptr, *d_sums8 = nullptr;
 	unsigned long long *d_segcount = nullptr;
 	FT *d_outvel = nullptr;
 	double *d_outT = nullptr;
@@ -153,7 +154,7 @@ struct Slab {
 		if (arena) cudaFree(arena);
 		for (auto &p : nodev) if (p) cudaFree(p);
 		for (auto &p : role) if (p) cudaFree(p);
-		void *misc[] = {cv, cT, d_partials, d_err2, d_segcount, d_outvel, d_outT, ncode, xcoef_send, xbnd_send};
+		void *misc[] = {cv, cT, d_partials, d_err2, d_sums8, d_segcount, d_outvel, d_outT, ncode, xcoef_send, xbnd_send};
 		for (void *p : misc) if (p) cudaFree(p);
 	}
 
@@ -193,6 +194,7 @@ struct Slab {
 		if ((rc = dalloc(cT, (size_t)L.total))) return rc;
 		if ((rc = dalloc(d_partials, (size_t)2 * kMaxErrBlocks))) return rc;
 		if ((rc = dalloc(d_err2, 2))) return rc;
+		if ((rc = dalloc(d_sums8, 8))) return rc;
 		if ((rc = dalloc(d_segcount, 8))) return rc;
 		if (nslabs > 1) {
 			const size_t lpo = lines_per_owner(nslabs);
@@ -267,8 +269,13 @@ struct Engine : cmc_adi3d {
 	cmc_fluid_params params{};
 	double dx = 0, dy = 0, dz = 0;
 	double diffError = 0.0;
-	bool err_pending = false;
-	double *h_err2 = nullptr;          // pinned: [2 * nlocal] (sum, count) per local slab
+	// residuals of enqueued (asynchronous) steps: pinned ring of kErrRing entries of [2 * nlocal] (sum, count) per local
+	// slab.  sync() looks at EVERY pending entry, so a step that diverged in the middle of an asynchronous run is not
+	// hidden by the steps that followed it (the reference checks after every step, AdiSolver3D.cpp:371-374)
+	static constexpr int kErrRing = 64;
+	int err_head = 0, err_pending = 0; // next entry to write / entries written since the last fetch
+	double worst_err = 0.0;            // largest residual among the entries of the last fetch
+	double *h_err2 = nullptr;
 	// exchanges as stores into the other slabs' buffers (see SweepArgs::push_*): always when all slabs share this
 	// device (emulation), and between processes once every rank has mapped every other rank's arena (peer memory)
 	PeerMap pm;
@@ -364,8 +371,8 @@ struct Engine : cmc_adi3d {
 			dev_bytes += s->bytes;
 		}
 		L = G; L.x0 = lo; L.shape(hi - lo, G.ny, G.nz, G.nzp, G.jbs);
-		CU_TRY(cudaHostAlloc((void **)&h_err2, 2 * sizeof(double) * nlocal, cudaHostAllocDefault));
-		memset(h_err2, 0, 2 * sizeof(double) * nlocal);
+		CU_TRY(cudaHostAlloc((void **)&h_err2, 2 * sizeof(double) * nlocal * kErrRing, cudaHostAllocDefault));
+		memset(h_err2, 0, 2 * sizeof(double) * nlocal * kErrRing);
 		CU_TRY(cudaMalloc((void **)&d_timeout, sizeof(int)));
 		CU_TRY(cudaMemsetAsync(d_timeout, 0, sizeof(int), stream));
 		CU_TRY(cudaStreamSynchronize(stream));
@@ -456,6 +463,9 @@ struct Engine : cmc_adi3d {
 			for (size_t id = 0; id < N; id++) {
 				const int32_t *hd = (const int32_t *)(base + id * aos_stride);
 				const FT *fv = (const FT *)(base + id * aos_stride + (sizeof(FT) == 8 ? 16 : 12));
+				if (hd[0] < 0 || hd[0] > 3) return fail(CMC_ERR_INVALID, "set_nodes_aos: node type out of range");
+				if ((hd[1] != CMC_BC_NOSLIP && hd[1] != CMC_BC_FREE) || (hd[2] != CMC_BC_NOSLIP && hd[2] != CMC_BC_FREE))
+					return fail(CMC_ERR_INVALID, "set_nodes_aos: boundary-condition type out of range");
 				code[id] = (uint8_t)((hd[0] & 3) | (hd[1] == CMC_BC_FREE ? 4 : 0) | (hd[2] == CMC_BC_FREE ? 8 : 0));
 				tmp[0][id] = fv[0]; tmp[1][id] = fv[1]; tmp[2][id] = fv[2]; tmp[3][id] = fv[3];
 			}
@@ -463,6 +473,8 @@ struct Engine : cmc_adi3d {
 		} else {
 			for (size_t id = 0; id < N; id++) {
 				if (type[id] < 0 || type[id] > 3) return fail(CMC_ERR_INVALID, "set_nodes: node type out of range");
+				if ((bc_vel[id] != CMC_BC_NOSLIP && bc_vel[id] != CMC_BC_FREE) || (bc_temp[id] != CMC_BC_NOSLIP && bc_temp[id] != CMC_BC_FREE))
+					return fail(CMC_ERR_INVALID, "set_nodes: boundary-condition type out of range");
 				code[id] = (uint8_t)((type[id] & 3) | (bc_vel[id] == CMC_BC_FREE ? 4 : 0) | (bc_temp[id] == CMC_BC_FREE ? 8 : 0));
 			}
 		}
@@ -473,7 +485,7 @@ struct Engine : cmc_adi3d {
 		CU_TRY(cudaStreamSynchronize(stream));
 		halos_dirty = true;
 		have_nodes = true; have_lines = false;
-		diffError = 0.0; err_pending = false;
+		diffError = 0.0; err_pending = 0; worst_err = 0.0;
 		return CMC_OK;
 	}
 
@@ -579,6 +591,25 @@ struct Engine : cmc_adi3d {
 
 	bool fast_ok(int dir) const { return mode == CMC_MODE_FAST && fast_sweep_supported(slabs[0]->L, dir); }
 
+	// which kernel a sweep along `dir` runs (get_option "kernel_x|y|z"): 0 exact Thomas kernels + merge, 1 direct-load
+	// partition kernel (kernels_fast.cu), 2 cp.async ring kernel (kernels_ring.cu), 4 slab-coupled x-sweep (spike pass +
+	// interface solve + coupled pass)
+	int kernel_kind(int dir) const override
+	{
+		if (multi() && dir == CMC_DIR_X) return 4;
+		if (!fast_ok(dir)) return 0;
+		return want_ring(dir) && ring_sweep_supported(slabs[0]->L, dir) ? 2 : 1;
+	}
+	// two data-movement variants of the same arithmetic (kernels_ring.cu / kernels_fast.cu).  Measured on B200 at 512^3
+	// (profiles/r01_variants.md): fp64 - the direct-load kernel wins everywhere (z: 2-line tiles, four independent CTAs per
+	// SM, 4.00 ms against 4.58 ms for the cp.async ring); fp32 - the ring wins along z (2.42 against 2.71 ms).
+	// CMC_RING=<subset of "xyz"> overrides.
+	static bool want_ring(int dir)
+	{
+		static const char *ring_env = getenv("CMC_RING");
+		return ring_env ? strchr(ring_env, "xyz"[dir]) != nullptr : (dir == CMC_DIR_Z && sizeof(FT) == 4);
+	}
+
 	// AdiSolver3D::SolveDirection (AdiSolver3D.cpp:564-666): num_local x { solve every line for u,v,w,T ; merge }
 	// temp_is_cur: the linearisation layer still equals `cur` (first sweep of a step; the temp<-cur copy is folded
 	// away).  fold_post_merge: the last local iteration also applies the post-X MergeLayerTo (AdiSolver3D.cpp:354).
@@ -593,15 +624,13 @@ struct Engine : cmc_adi3d {
 			if (!(push_mode() && halos_ready))
 				if ((rc = halo_exchange(t_is_c ? CMC_LAYER_CUR : CMC_LAYER_TEMP))) return rc;   // x-stencils of the sweep read the neighbours' planes
 			const bool coupled = multi() && dir == CMC_DIR_X;
-			if (multi() && mode != CMC_MODE_FAST)
-				return fail(CMC_ERR_UNSUPPORTED, "slab-decomposed runs support CMC_MODE_FAST only");
 			// the neighbours have finished their previous sweep: their stores into this slab's guard planes are complete,
 			// and they no longer read the guard planes this sweep is about to overwrite on their side
 			await(neighbour_mask());
 			if (coupled) {
 				// partitioned solve along the decomposed axis: spike pass -> coefficients to the line owners -> interface
 				// solve -> neighbour values back -> coupled sweep.  (replaces LaunchSolveSegments_X, AdiSolver3D.cu:524-640)
-				span_begin(CMC_TIMING_SWEEP_X);
+				span_begin(CMC_TIMING_X_SPIKE);
 				for (auto *s : slabs) {
 					SweepArgs<FT> A = sweep_args(s, dir, dt, cur_layer, next_layer);
 					if (t_is_c)
@@ -612,7 +641,7 @@ struct Engine : cmc_adi3d {
 				const size_t lpo = slabs[0]->lines_per_owner(nslabs_total);
 				if (push_mode()) { span_begin(CMC_TIMING_COMM); publish(); await(all_mask()); span_end(); }
 				else if ((rc = all_to_all(&Slab<FT>::xcoef_send, &Slab<FT>::xcoef_recv, lpo * 16))) return rc;
-				span_begin(CMC_TIMING_SWEEP_X);
+				span_begin(CMC_TIMING_X_INTERFACE);
 				const long long nlines = (long long)G.ny * G.nz;
 				for (auto *s : slabs) {
 					const long long first = (long long)s->index * (long long)lpo;
@@ -639,13 +668,7 @@ struct Engine : cmc_adi3d {
 					if (!launch_x_coupled<FT>(A, stream, &launches)) return fail(CMC_ERR_UNSUPPORTED, "coupled x-sweep: unsupported slab shape");
 					done = true;
 				} else if (fast_ok(dir)) {
-					// two data-movement variants of the same arithmetic (kernels_ring.cu / kernels_fast.cu).  Measured on
-					// B200 at 512^3 (profiles/r01_variants.md): fp64 - the direct-load kernel wins everywhere (z: 2-line tiles,
-					// four independent CTAs per SM, 4.00 ms against 4.58 ms for the cp.async ring); fp32 - the ring wins
-					// along z (2.42 against 2.71 ms).  CMC_RING=<subset of "xyz"> overrides.
-					static const char *ring_env = getenv("CMC_RING");
-					const bool ring = ring_env ? strchr(ring_env, "xyz"[dir]) != nullptr : (dir == CMC_DIR_Z && sizeof(FT) == 4);
-					if (ring) done = launch_ring_sweep<FT>(dir, A, stream, &launches);
+					if (want_ring(dir)) done = launch_ring_sweep<FT>(dir, A, stream, &launches);
 					if (!done) done = launch_fast_sweep<FT>(dir, A, stream, &launches);
 				}
 				if (done) swapped[si] = 1;                               // merged temp went to the other buffer
@@ -681,6 +704,11 @@ struct Engine : cmc_adi3d {
 
 	int enqueue_div_error(int logical_layer, bool halos_ready = false)
 	{
+		if (err_pending == kErrRing) {         // ring full: drain it (one stream synchronisation every kErrRing residuals)
+			int rc = fetch_error();
+			if (rc) return rc;
+		}
+		double *slot_h = h_err2 + (size_t)err_head * 2 * slabs.size();
 		// the residual reads the i-1 plane (TimeLayer3D.h:614-621)
 		if (push_mode() && halos_ready) await(neighbour_mask());
 		else {
@@ -693,25 +721,48 @@ struct Engine : cmc_adi3d {
 			launch_div_error<FT>(s->L, s->role[2], s->field[l][0], s->field[l][1], s->field[l][2], (FT)dx, (FT)dy, (FT)dz,
 			                     s->d_partials, Slab<FT>::kMaxErrBlocks, s->d_err2, stream, &launches);
 			if (nccl && nccl_allreduce_sum_f64(nccl, s->d_err2, 2, stream)) return fail(CMC_ERR_COMM, nccl_error());
-			CU_TRY(cudaMemcpyAsync(h_err2 + 2 * i, s->d_err2, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+			CU_TRY(cudaMemcpyAsync(slot_h + 2 * i, s->d_err2, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
 		}
-		err_pending = true;
+		err_head = (err_head + 1) % kErrRing;
+		err_pending++;
 		return CMC_OK;
 	}
 
-	double err_from_host() const
+	double err_from_host(int entry) const
 	{
+		const double *slot_h = h_err2 + (size_t)entry * 2 * slabs.size();
 		double e = 0.0, c = 0.0;
-		for (size_t i = 0; i < slabs.size(); i++) { e += h_err2[2 * i]; c += h_err2[2 * i + 1]; }
+		for (size_t i = 0; i < slabs.size(); i++) { e += slot_h[2 * i]; c += slot_h[2 * i + 1]; }
 		return e / c;           // err / count (TimeLayer3D.h:639); 0/0 = NaN like the reference
 	}
 
+	// waits for the enqueued residuals: diffError = the latest one, worst_err = the largest of them
 	int fetch_error()
 	{
+		worst_err = diffError;
 		if (err_pending) {
 			CU_TRY(cudaStreamSynchronize(stream));
-			diffError = err_from_host();
-			err_pending = false;
+			worst_err = 0.0;
+			for (int k = err_pending; k >= 1; k--) {
+				const double e = err_from_host((err_head - k + 2 * kErrRing) % kErrRing);
+				diffError = e;
+				if (e > worst_err || e != e) worst_err = e;
+			}
+			err_pending = 0;
+		}
+		return CMC_OK;
+	}
+
+	// a peer that never published its epoch (dead or stalled rank): k_peer_wait gave up after 10 s and the kernels after it
+	// ran on stale guard planes / interface tables.  Called after every host-visible synchronisation.
+	int check_peers()
+	{
+		if (!p2p) return CMC_OK;
+		int t = 0;
+		CU_TRY(cudaMemcpy(&t, d_timeout, sizeof t, cudaMemcpyDeviceToHost));
+		if (t) {
+			CU_TRY(cudaMemset(d_timeout, 0, sizeof(int)));
+			return fail(CMC_ERR_COMM, "a peer rank did not publish its epoch within 10 s (peer_wait timed out): the fields of this step are invalid");
 		}
 		return CMC_OK;
 	}
@@ -721,6 +772,8 @@ struct Engine : cmc_adi3d {
 	{
 		int rc;
 		if (ng < 0 || nl < 0) return fail(CMC_ERR_INVALID, "time_step: negative iteration count");
+		if (multi() && mode != CMC_MODE_FAST)     // before anything is enqueued or any layer is touched
+			return fail(CMC_ERR_UNSUPPORTED, "slab-decomposed runs support CMC_MODE_FAST only");
 		const FT dt = (FT)dt_in;                                   // FluidSolver3D.cpp:242 casts to FTYPE
 		// fast mode folds two full-field passes into the sweeps (identical arithmetic, fewer HBM round trips):
 		//  * temp <- cur (:320): the first Z sweep reads `cur` as its linearisation layer;
@@ -756,7 +809,9 @@ struct Engine : cmc_adi3d {
 		}
 		if (!async) {
 			if ((rc = fetch_error())) return rc;
+			CU_TRY(cudaStreamSynchronize(stream));
 			CU_TRY(cudaGetLastError());
+			if ((rc = check_peers())) return rc;
 			if (err) *err = diffError;
 			if (diffError > CMC_ERR_THRESHOLD) {                   // :371-374 (layers are not swapped)
 				char buf[96];
@@ -775,15 +830,14 @@ struct Engine : cmc_adi3d {
 		if (rc) return rc;
 		CU_TRY(cudaStreamSynchronize(stream));
 		CU_TRY(cudaGetLastError());
-		if (p2p) {
-			int t = 0;
-			CU_TRY(cudaMemcpy(&t, d_timeout, sizeof t, cudaMemcpyDeviceToHost));
-			if (t) return fail(CMC_ERR_COMM, "a peer rank did not publish its epoch within 10 s (peer_wait timed out)");
-		}
+		if ((rc = check_peers())) return rc;
 		if (err) *err = diffError;
-		if (diffError > CMC_ERR_THRESHOLD) {
+		// every residual enqueued since the last synchronisation is checked, not only the latest one.  (The layers of an
+		// asynchronous run have been swapped by then - unlike cmc_adi3d_time_step, which leaves them unswapped.)
+		if (worst_err > CMC_ERR_THRESHOLD) {
 			char buf[96];
-			snprintf(buf, sizeof buf, "Error is too big! %f", diffError);
+			snprintf(buf, sizeof buf, "Error is too big! %f", worst_err);
+			worst_err = 0.0;
 			return fail(CMC_ERR_DIVERGED, buf);
 		}
 		return CMC_OK;
@@ -794,6 +848,7 @@ struct Engine : cmc_adi3d {
 		if (!have_lines) return fail(CMC_ERR_INVALID, "solve_direction: call cmc_adi3d_build_lines first");
 		if (dir < 0 || dir > 2 || cur_layer < 0 || cur_layer > 3 || next_layer < 0 || next_layer > 3 || cur_layer == next_layer)
 			return fail(CMC_ERR_INVALID, "solve_direction: bad direction or layers");
+		if (multi() && mode != CMC_MODE_FAST) return fail(CMC_ERR_UNSUPPORTED, "slab-decomposed runs support CMC_MODE_FAST only");
 		CU_TRY(cudaSetDevice(device));
 		halos_dirty = true;
 		int rc = solve_direction_impl(dir, (FT)dt, nl, cur_layer, next_layer);
@@ -807,12 +862,34 @@ struct Engine : cmc_adi3d {
 	{
 		if (!have_lines) return fail(CMC_ERR_INVALID, "eval_div_error: call cmc_adi3d_build_lines first");
 		CU_TRY(cudaSetDevice(device));
-		int rc = enqueue_div_error(logical);
+		int rc = fetch_error();                  // residuals of earlier asynchronous steps stay accounted for
 		if (rc) return rc;
-		CU_TRY(cudaStreamSynchronize(stream));
-		err_pending = false;
-		if (err) *err = err_from_host();
-		return CMC_OK;
+		const double keep = diffError, keep_worst = worst_err;
+		if ((rc = enqueue_div_error(logical))) return rc;
+		if ((rc = fetch_error())) return rc;
+		if (err) *err = diffError;
+		diffError = keep; worst_err = keep_worst;
+		CU_TRY(cudaGetLastError());
+		return check_peers();
+	}
+
+	int field_sums(int logical, double *sums8) override
+	{
+		if (!have_lines) return fail(CMC_ERR_INVALID, "field_sums: call cmc_adi3d_build_lines first");
+		CU_TRY(cudaSetDevice(device));
+		double tot[8] = {};
+		for (auto *s : slabs) {
+			// (d_partials holds 2 doubles per block for the residual: use a quarter of the blocks here)
+			launch_field_sums<FT>(s->L, s->role[2], s->clayer(logical), s->d_partials, Slab<FT>::kMaxErrBlocks / 4, s->d_sums8, stream, &launches);
+			if (nccl && nccl_allreduce_sum_f64(nccl, s->d_sums8, 8, stream)) return fail(CMC_ERR_COMM, nccl_error());
+			double h8[8];
+			CU_TRY(cudaMemcpyAsync(h8, s->d_sums8, sizeof h8, cudaMemcpyDeviceToHost, stream));
+			CU_TRY(cudaStreamSynchronize(stream));
+			for (int q = 0; q < 8; q++) tot[q] += h8[q];
+		}
+		for (int q = 0; q < 8; q++) sums8[q] = tot[q];
+		CU_TRY(cudaGetLastError());
+		return check_peers();
 	}
 
 	// Solver3D::GetLayer (Solver3D.cpp:21-25)
@@ -886,7 +963,7 @@ struct Engine : cmc_adi3d {
 		}
 		CU_TRY(cudaStreamSynchronize(stream));
 		CU_TRY(cudaGetLastError());
-		return CMC_OK;
+		return check_peers();
 	}
 
 	// dense host copy of the locally held planes (all local slabs, in x order)
@@ -1088,7 +1165,6 @@ int cmc_adi3d_set_option(cmc_adi3d *h, const char *key, int64_t value)
 		h->mode = (int)value;
 		return CMC_OK;
 	}
-	if (!strcmp(key, "fold_boundaries")) { h->fold_boundaries = value != 0; return CMC_OK; }
 	if (!strcmp(key, "profile")) {
 		h->spans_collect();
 		h->profile = value != 0;
@@ -1103,9 +1179,9 @@ int cmc_adi3d_get_option(const cmc_adi3d *h, const char *key, int64_t *value)
 	H_CHECK(h);
 	if (!key || !value) return fail(CMC_ERR_INVALID, "get_option: null argument");
 	if (!strcmp(key, "mode")) { *value = h->mode; return CMC_OK; }
-	if (!strcmp(key, "fold_boundaries")) { *value = h->fold_boundaries; return CMC_OK; }
 	if (!strcmp(key, "nzp")) { *value = h->L.nzp; return CMC_OK; }
 	if (!strcmp(key, "jb")) { *value = h->L.nblk == 1 ? 0 : (1 << h->L.jbs); return CMC_OK; }   // rows per y-block, 0 = one block
+	if (!strncmp(key, "kernel_", 7) && key[7] >= 'x' && key[7] <= 'z' && !key[8]) { *value = h->kernel_kind(key[7] - 'x'); return CMC_OK; }
 	if (!strcmp(key, "exchange")) { *value = h->exchange_kind(); return CMC_OK; }   // 0 none, 1 NCCL send/recv, 2 fused stores (same device), 3 fused stores (peer memory)
 	if (!strcmp(key, "shared_free_cells")) { *value = h->shared_free[0] + h->shared_free[1] + h->shared_free[2]; return CMC_OK; }
 	return fail(CMC_ERR_INVALID, std::string("get_option: unknown key ") + key);
@@ -1138,6 +1214,13 @@ int cmc_adi3d_eval_div_error(cmc_adi3d *h, int layer, double *err)
 	H_CHECK(h);
 	if (layer < 0 || layer > 3) return fail(CMC_ERR_INVALID, "eval_div_error: bad layer");
 	return h->eval_div_error(layer, err);
+}
+
+int cmc_adi3d_field_sums(cmc_adi3d *h, int layer, double *sums8)
+{
+	H_CHECK(h);
+	if (layer < 0 || layer > 3 || !sums8) return fail(CMC_ERR_INVALID, "field_sums: bad argument");
+	return h->field_sums(layer, sums8);
 }
 
 int cmc_adi3d_stream(const cmc_adi3d *h, void **s)

@@ -19,6 +19,7 @@ bool launch_fast_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long lon
 // kernels_ring.cu: the same sweep as persistent CTAs fed by a cp.async shared-memory ring (MODE 0 lines only)
 template <typename FT>
 bool launch_ring_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
+bool ring_sweep_supported(const Layout &L, int dir);
 // partitioned x-sweep (slab-decomposed grid): spike pass, interface solve, coupled sweep
 template <typename FT>
 bool launch_x_spike(const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
@@ -64,6 +65,10 @@ template <typename FT>
 void launch_div_error(const Layout &L, const uint8_t *role, const FT *U, const FT *V, const FT *W,
                       FT dx, FT dy, FT dz, double *block_partials, int max_blocks, double *result2,
                       cudaStream_t s, long long *launches);
+// per-field sums and sums of squares over the non-OUT cells of the slab (checksums; block_partials: 8 per block)
+template <typename FT>
+void launch_field_sums(const Layout &L, const uint8_t *role, ConstLayerPtrs<FT> f, double *block_partials, int max_blocks, double *result8,
+                       cudaStream_t s, long long *launches);
 // Solver3D::GetLayer: OUT cells of `layer` <- 99999 (Clear, reference TimeLayer3D.h:974-998) ...
 template <typename FT>
 void launch_clear_out(const Layout &L, const uint8_t *role, LayerPtrs<FT> layer, FT value, cudaStream_t s, long long *launches);

@@ -427,12 +427,17 @@ static bool launch_ring_dir(int GP, const SweepArgs<FT> &A, cudaStream_t s)
 	}
 }
 
+bool ring_sweep_supported(const Layout &L, int dir)
+{
+	if (!fast_sweep_supported(L, dir)) return false;
+	return !(L.nblk > 1 && dir != 2);                    // the x / y tiles of this kernel assume the one-block layout
+}
+
 template <typename FT>
 bool launch_ring_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches)
 {
 	const Layout &L = A.L;
-	if (!fast_sweep_supported(L, dir)) return false;
-	if (L.nblk > 1 && dir != 2) return false;            // the x / y tiles of this kernel assume the one-block layout
+	if (!ring_sweep_supported(L, dir)) return false;
 	const int n = dir == 0 ? L.nx : dir == 1 ? L.ny : L.nz;
 	const int G = (n + M - 1) / M;
 	int GP = 4;

@@ -94,17 +94,24 @@ void launch_build_roles(int dir, const Layout &G, const uint8_t *ncode, const La
 __global__ void k_role_type_bits(const Layout G, const uint8_t *__restrict__ ncode, const Layout L,
                                  uint8_t *rx, uint8_t *ry, uint8_t *rz)
 {
-	const long long rows = (long long)L.nx * L.ny;
+	// the guard planes that hold a neighbouring slab's boundary plane get their type bits too (in the z array only):
+	// k_update_boundaries refreshes them together with the slab's own cells
+	const int ilo = L.x0 > 0 ? -1 : 0, ihi = L.x0 + L.nx < G.nx ? L.nx + 1 : L.nx;
+	const long long rows = (long long)(ihi - ilo) * L.ny;
 	for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-		const int i = (int)(row / L.ny), j = (int)(row % L.ny);
+		const int i = (int)(row / L.ny) + ilo, j = (int)(row % L.ny);
+		const bool guard = i < 0 || i >= L.nx;
 		const uint8_t *src = ncode + ((long long)(i + L.x0) * G.ny + j) * G.nz;
 		const long long dst = L.idx(i, j, 0);
 		for (int k = threadIdx.x; k < L.nz; k += blockDim.x) {
 			const unsigned c = src[k];
 			const unsigned ty = code_type(c);
+			// the boundary kinds of a NODE_IN cell are never read by the reference (its rows are interior rows); on such
+			// a cell R_VFREE / R_TFREE are reserved for the folded shared cell that follows it (R_PRE, k_build_roles)
 			unsigned bits = (ty == 0u ? R_IN : 0u) | ((ty == 2u || ty == 3u) ? R_BV : 0u)
-			              | ((c & 4u) ? R_VFREE : 0u) | ((c & 8u) ? R_TFREE : 0u);
-			rx[dst + k] = (uint8_t)bits; ry[dst + k] = (uint8_t)bits; rz[dst + k] = (uint8_t)bits;
+			              | ((ty != 0u && (c & 4u)) ? R_VFREE : 0u) | ((ty != 0u && (c & 8u)) ? R_TFREE : 0u);
+			if (!guard) { rx[dst + k] = (uint8_t)bits; ry[dst + k] = (uint8_t)bits; }
+			rz[dst + k] = (uint8_t)bits;
 		}
 	}
 }
@@ -112,7 +119,7 @@ __global__ void k_role_type_bits(const Layout G, const uint8_t *__restrict__ nco
 void launch_role_type_bits(const Layout &G, const uint8_t *ncode, const Layout &L, uint8_t *rx, uint8_t *ry, uint8_t *rz,
                            cudaStream_t s, long long *launches)
 {
-	k_role_type_bits<<<grid_for((long long)L.nx * L.ny, 1), 128, 0, s>>>(G, ncode, L, rx, ry, rz);
+	k_role_type_bits<<<grid_for((long long)(L.nx + 2) * L.ny, 1), 128, 0, s>>>(G, ncode, L, rx, ry, rz);
 	if (launches) (*launches)++;
 }
 
@@ -167,15 +174,22 @@ __global__ void k_merge_to(const Layout L, const uint8_t *__restrict__ role, Con
 	});
 }
 
+// (planes -1 and nx included: the guard planes mirror the neighbouring slabs' boundary planes, whose BOUND / VALVE cells
+// the neighbours refresh at the same moment; guard planes at the ends of the grid carry no type bits)
 template <typename FT>
 __global__ void k_update_boundaries(const Layout L, const uint8_t *__restrict__ role, ConstLayerPtrs<FT> nodev, LayerPtrs<FT> cur)
 {
-	for_each_cell<FT>(L, [&](long long id) {
-		if (role[id] & R_BV) {
-			cur.f[0][id] = nodev.f[0][id]; cur.f[1][id] = nodev.f[1][id];
-			cur.f[2][id] = nodev.f[2][id]; cur.f[3][id] = nodev.f[3][id];
+	const long long rows = (long long)(L.nx + 2) * L.ny;
+	for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+		const long long base = L.idx((int)(row / L.ny) - 1, (int)(row % L.ny), 0);
+		for (int k = threadIdx.x; k < L.nz; k += blockDim.x) {
+			const long long id = base + k;
+			if (role[id] & R_BV) {
+				cur.f[0][id] = nodev.f[0][id]; cur.f[1][id] = nodev.f[1][id];
+				cur.f[2][id] = nodev.f[2][id]; cur.f[3][id] = nodev.f[3][id];
+			}
 		}
-	});
+	}
 }
 
 template <typename FT>
@@ -221,7 +235,7 @@ void launch_merge_to(const Layout &L, const uint8_t *role, ConstLayerPtrs<FT> tm
 template <typename FT>
 void launch_update_boundaries(const Layout &L, const uint8_t *role, ConstLayerPtrs<FT> nodev, LayerPtrs<FT> cur, cudaStream_t s, long long *launches)
 {
-	k_update_boundaries<FT><<<grid_for((long long)L.nx * L.ny, 1), 128, 0, s>>>(L, role, nodev, cur);
+	k_update_boundaries<FT><<<grid_for((long long)(L.nx + 2) * L.ny, 1), 128, 0, s>>>(L, role, nodev, cur);
 	if (launches) (*launches)++;
 }
 template <typename FT>
@@ -309,6 +323,54 @@ void launch_div_error(const Layout &L, const uint8_t *role, const FT *U, const F
 	if (launches) *launches += 2;
 }
 
+// ---- per-field checksums of one layer: sum and sum of squares over the cells of the slab that are not NODE_OUT ------
+// (the role of the reference's sum_layer debug hook, AdiSolver3D.cpp:30-58).  partials: [8] per block, result8:
+// (sum u, v, w, T, sum of squares u, v, w, T).  Fixed reduction tree: the result does not depend on scheduling.
+template <typename FT>
+__global__ void __launch_bounds__(256) k_field_sums(const Layout L, const uint8_t *__restrict__ role, ConstLayerPtrs<FT> f, double *partials)
+{
+	double acc[8] = {};
+	for_each_cell<FT>(L, [&](long long id) {
+		if (role[id] & (R_IN | R_BV)) {
+#pragma unroll
+			for (int q = 0; q < 4; q++) { const double v = (double)f.f[q][id]; acc[q] += v; acc[4 + q] += v * v; }
+		}
+	});
+	__shared__ double sh[8][8];
+	const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+	for (int q = 0; q < 8; q++) {
+		double v = acc[q];
+		for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+		if (l == 0) sh[q][w] = v;
+	}
+	__syncthreads();
+	if (threadIdx.x < 8) {
+		double v = 0.0;
+		for (int k = 0; k < 8; k++) v += sh[threadIdx.x][k];
+		partials[8 * blockIdx.x + threadIdx.x] = v;
+	}
+}
+
+__global__ void k_field_sums_final(const double *partials, int nblocks, double *result8)
+{
+	const int q = threadIdx.x;
+	if (q >= 8) return;
+	double v = 0.0;
+	for (int b = 0; b < nblocks; b++) v += partials[8 * b + q];
+	result8[q] = v;
+}
+
+template <typename FT>
+void launch_field_sums(const Layout &L, const uint8_t *role, ConstLayerPtrs<FT> f, double *block_partials, int max_blocks, double *result8,
+                       cudaStream_t s, long long *launches)
+{
+	unsigned g = grid_for((long long)L.nx * L.ny, 1, max_blocks);
+	k_field_sums<FT><<<g, 256, 0, s>>>(L, role, f, block_partials);
+	k_field_sums_final<<<1, 32, 0, s>>>(block_partials, (int)g, result8);
+	if (launches) *launches += 2;
+}
+
 // ---- TimeLayer3D::FilterToArrays (reference TimeLayer3D.h:842-854): nearest-lower downsample ---------
 template <typename FT>
 __global__ void k_filter(const Layout L, ConstLayerPtrs<FT> layer, int ox, int oy, int oz, int oi0, int oi1, FT *vel, double *T)
@@ -346,7 +408,8 @@ void launch_filter(const Layout &L, ConstLayerPtrs<FT> layer, int ox, int oy, in
 	template void launch_clear_out<FT>(const Layout &, const uint8_t *, LayerPtrs<FT>, FT, cudaStream_t, long long *); \
 	template void launch_fill<FT>(FT *, long long, FT, cudaStream_t, long long *); \
 	template void launch_div_error<FT>(const Layout &, const uint8_t *, const FT *, const FT *, const FT *, FT, FT, FT, double *, int, double *, cudaStream_t, long long *); \
-	template void launch_filter<FT>(const Layout &, ConstLayerPtrs<FT>, int, int, int, int, int, FT *, double *, cudaStream_t, long long *);
+	template void launch_filter<FT>(const Layout &, ConstLayerPtrs<FT>, int, int, int, int, int, FT *, double *, cudaStream_t, long long *); \
+	template void launch_field_sums<FT>(const Layout &, const uint8_t *, ConstLayerPtrs<FT>, double *, int, double *, cudaStream_t, long long *);
 CMC_INST(float)
 CMC_INST(double)
 

@@ -181,6 +181,12 @@ class AdiSolver3D:
         _check(load_library().cmc_adi3d_eval_div_error(self._h, layer, C.byref(e)))
         return e.value
 
+    def field_sums(self, layer=LAYER_CUR):
+        """(sum, sum of squares) of u, v, w, T over the non-OUT cells of the whole grid (all ranks call, all receive)."""
+        a = (C.c_double * 8)()
+        _check(load_library().cmc_adi3d_field_sums(self._h, layer, a))
+        return {n: (a[q], a[4 + q]) for q, n in enumerate("uvwT")}
+
     def stream(self) -> int:
         s = C.c_void_p()
         _check(load_library().cmc_adi3d_stream(self._h, C.byref(s)))
@@ -191,7 +197,7 @@ class AdiSolver3D:
         _check(load_library().cmc_adi3d_launch_count(self._h, C.byref(n), int(reset)))
         return n.value
 
-    TIMING_KINDS = ("sweep_x", "sweep_y", "sweep_z", "merge", "copy", "boundary", "residual", "readback", "comm")
+    TIMING_KINDS = ("sweep_x", "sweep_y", "sweep_z", "merge", "copy", "boundary", "residual", "readback", "comm", "x_spike", "x_interface")
 
     def set_profile(self, on=True, reset=False):
         _check(load_library().cmc_adi3d_set_option(self._h, b"profile", 2 if (on and reset) else int(bool(on))))
@@ -204,6 +210,15 @@ class AdiSolver3D:
             _check(load_library().cmc_adi3d_get_timing(self._h, k, C.byref(ms), C.byref(n)))
             out[name] = (ms.value, n.value)
         return out
+
+    def sweep_kernel_name(self, kind: str) -> str:
+        """Name of the kernel behind a timing kind ("sweep_x" / "sweep_y" / "sweep_z")."""
+        d = "xyz".index(kind[-1])
+        v = C.c_int64(0)
+        _check(load_library().cmc_adi3d_get_option(self._h, f"kernel_{kind[-1]}".encode(), C.byref(v)))
+        ft = "double" if self.fp == 8 else "float"
+        return {0: f"k_exact_forward/backward<{ft}> + k_merge", 1: f"k_fast_sweep<{ft},{d}>", 2: f"k_ring_sweep<{ft},{d}>",
+                3: f"k_tma_sweep<{ft},{d}>", 4: f"k_fast_sweep<{ft},0,MODE 1> + k_x_interface + k_fast_sweep<{ft},0,MODE 2>"}[v.value]
 
     def storage_block_rows(self) -> int:
         v = C.c_int64(0)

@@ -127,7 +127,9 @@ int cmc_adi3d_time_step(cmc_adi3d *h, double dt, int num_global, int num_local,
 int cmc_adi3d_get_layer(cmc_adi3d *h, void *vel_xyz, double *T, int outdimx, int outdimy, int outdimz);
 
 /* ---- options ----  "mode": CMC_MODE_FAST | CMC_MODE_EXACT;  "profile": 0|1|2 (see cmc_adi3d_get_timing);
- * read-only: "nzp" (padded z-line length), "jb" (rows per y-block of the field storage, 0 = one block), "exchange" (how slabs exchange planes and interface systems: 0 single slab,
+ * read-only: "kernel_x" / "kernel_y" / "kernel_z" (which kernel a sweep along that axis runs: 0 exact Thomas kernels,
+ * 1 direct-load partition kernel, 2 cp.async ring kernel, 3 TMA-staged tile kernel, 4 slab-coupled x-sweep),
+ * "nzp" (padded z-line length), "jb" (rows per y-block of the field storage, 0 = one block), "exchange" (how slabs exchange planes and interface systems: 0 single slab,
  * 1 NCCL send/recv groups, 2 stores fused into the sweep kernels (slabs on one device), 3 the same into peer memory
  * over NVLink - every rank maps the other ranks' exchange arena with CUDA IPC) */
 int cmc_adi3d_set_option(cmc_adi3d *h, const char *key, int64_t value);
@@ -144,6 +146,11 @@ int cmc_adi3d_solve_direction(cmc_adi3d *h, int dir, double dt, int num_local, i
 /* TimeLayer3D::EvalDivError of one layer (TimeLayer3D.h:595-641) */
 int cmc_adi3d_eval_div_error(cmc_adi3d *h, int layer, double *err_out);
 
+/* per-field checksums of one layer over all non-OUT cells of the WHOLE grid (all ranks of a distributed handle must
+ * call; every rank receives the result): sums8 = { sum u, v, w, T, sum of squares u, v, w, T }.  The role of the
+ * reference's sum_layer debug hook (AdiSolver3D.cpp:30-58). */
+int cmc_adi3d_field_sums(cmc_adi3d *h, int layer, double *sums8);
+
 /* ---- device-resident control for benchmarking (inputs already in HBM) ---- */
 /* enqueue a step without any host synchronisation (compute_error results are fetched by cmc_adi3d_sync) */
 int cmc_adi3d_time_step_async(cmc_adi3d *h, double dt, int num_global, int num_local, int compute_error);
@@ -159,7 +166,10 @@ int cmc_adi3d_launch_count(const cmc_adi3d *h, int64_t *n, int reset);
 enum {
 	CMC_TIMING_SWEEP_X = 0, CMC_TIMING_SWEEP_Y = 1, CMC_TIMING_SWEEP_Z = 2, CMC_TIMING_MERGE = 3,
 	CMC_TIMING_COPY = 4, CMC_TIMING_BOUNDARY = 5, CMC_TIMING_RESIDUAL = 6, CMC_TIMING_READBACK = 7,
-	CMC_TIMING_COMM = 8, CMC_TIMING_KINDS = 9
+	CMC_TIMING_COMM = 8,
+	/* slab-decomposed x-sweep: the spike pass and the interface solve are timed apart from the coupled pass
+	 * (CMC_TIMING_SWEEP_X), so that each launch can be set against the bytes it moves */
+	CMC_TIMING_X_SPIKE = 9, CMC_TIMING_X_INTERFACE = 10, CMC_TIMING_KINDS = 11
 };
 int cmc_adi3d_get_timing(cmc_adi3d *h, int kind, double *total_ms, int64_t *calls);
 /* bytes of device memory held by this handle */

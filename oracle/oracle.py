@@ -83,7 +83,17 @@ def read_probe(path) -> Case:
         off += 8
         (err,) = struct.unpack_from("<d", data, off)
         off += 8
-        if kind == 1:  # GetLayer output: Vec3D[outN] + double[outN]
+        if kind == 5:  # compact record: stride, sample dims, per field (sum, sum of squares, sum |.|, strided subsample)
+            stride, sx, sy, sz = struct.unpack_from("<4i", data, off)
+            off += 16
+            rec = dict(step=step, kind=kind, err=err, stride=stride, sums=[], sumsq=[], sumabs=[], sample=[])
+            for _ in range(4):
+                s1, s2, sa = struct.unpack_from("<3d", data, off)
+                off += 24
+                rec["sums"].append(s1); rec["sumsq"].append(s2); rec["sumabs"].append(sa)
+                rec["sample"].append(take(ft, sx * sy * sz).reshape(sx, sy, sz))
+            case.snapshots.append(rec)
+        elif kind == 1:  # GetLayer output: Vec3D[outN] + double[outN]
             vel = take(ft, 3 * outN).reshape(outN, 3)
             T = take(np.float64, outN)
             case.snapshots.append(dict(step=step, kind=kind, err=err, vel=vel, T=T))
@@ -103,12 +113,14 @@ def have_ref(fp_bytes: int = 8) -> bool:
 
 
 def run_ref(data_file, config_file, out_file, nsteps, fp_bytes=8, align=True, dump="last",
-            getlayer=False, dt=None, sweep=None, threads=None, timeout=3600):
+            getlayer=False, dt=None, sweep=None, threads=None, timeout=3600, stats=0):
     """Run the real reference CPU solver through the probe driver; returns its stdout."""
     cmd = [str(ref_binary(fp_bytes)), str(data_file), str(config_file), str(out_file), str(int(nsteps))]
     if align:
         cmd.append("align")
     cmd.append(f"dump={dump}")
+    if stats:
+        cmd.append(f"stats={int(stats)}")
     if getlayer:
         cmd.append("getlayer")
     if dt is not None:

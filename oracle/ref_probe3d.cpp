@@ -9,8 +9,12 @@
 // restatement (oracle/adi3d_oracle.c) and with the CUDA path.  Only tests/, smoke() and
 // bench.py's cpu_baseline / --impl reference legs may execute the resulting binary.
 //
-// usage: ref_probe3d <data> <config> <out.bin|-> <nsteps> [align] [dump=every|last|none]
-//                    [getlayer] [dt=<v>] [sweep=<Z|Y|X>] [threads=<n>] [solver=cpu|b200|b200exact]
+// usage: ref_probe3d <data> <config> <out.bin|-> <nsteps> [align] [dump=every|last|none|list:<s0,s1,..>]
+//                    [stats=<stride>] [getlayer] [dt=<v>] [sweep=<Z|Y|X>] [threads=<n>] [solver=cpu|b200|b200exact]
+//                    [gpus=<n>]
+// stats=<stride>: the steps selected by dump= are written as compact records (kind 5: per-field sum, sum of squares,
+// sum of |.|, and the strided subsample [::stride, ::stride, ::stride]) instead of whole layers - what the golden
+// vectors of the BASELINE-sized configs (256^3, 512^3) hold.
 //
 // Built with -DWITH_B200 (oracle/_ref/dropin3d_*) the same driver can put the reference's loader and Node[] in
 // front of the B200 solver through the Solver3D adapter (cmc_fluid_solver_b200/host/B200AdiSolver3D.*): that binary
@@ -62,6 +66,34 @@ static void put_field(ScalarField3D *f, size_t n)
 	put(&f->elem(0, 0, 0), n * sizeof(FTYPE));
 }
 
+// kind 5 record of one layer given as four dense arrays (u, v, w, T)
+static void put_stats(int step, double err, const FTYPE *const f[4], int dimx, int dimy, int dimz, int stride)
+{
+	put_i32(step); put_i32(5); put_f64(err);
+	const int sx = (dimx + stride - 1) / stride, sy = (dimy + stride - 1) / stride, sz = (dimz + stride - 1) / stride;
+	put_i32(stride); put_i32(sx); put_i32(sy); put_i32(sz);
+	std::vector<FTYPE> smp((size_t)sx * sy * sz);
+	for (int q = 0; q < 4; q++) {
+		double s1 = 0.0, s2 = 0.0, sa = 0.0;
+		const size_t n = (size_t)dimx * dimy * dimz;
+		for (size_t id = 0; id < n; id++) { const double v = (double)f[q][id]; s1 += v; s2 += v * v; sa += fabs(v); }
+		put_f64(s1); put_f64(s2); put_f64(sa);
+		size_t o = 0;
+		for (int i = 0; i < dimx; i += stride)
+			for (int j = 0; j < dimy; j += stride)
+				for (int k = 0; k < dimz; k += stride) smp[o++] = f[q][((size_t)i * dimy + j) * dimz + k];
+		put(smp.data(), smp.size() * sizeof(FTYPE));
+	}
+}
+
+static bool step_selected(const std::string &dump, const std::vector<int> &list, int i, int nsteps)
+{
+	if (dump == "every") return true;
+	if (dump == "last") return i == nsteps - 1;
+	if (dump == "list") return std::find(list.begin(), list.end(), i) != list.end();
+	return false;
+}
+
 static void put_layer(int step, int kind, double err, TimeLayer3D *L, size_t n)
 {
 	put_i32(step); put_i32(kind); put_f64(err);
@@ -78,10 +110,20 @@ int main(int argc, char **argv)
 	std::string dump = "last", sweep = "", which = "cpu";
 	double dt_override = -1;
 	int nsteps = atoi(argv[4]);
+	int stats_stride = 0, ngpus = 1;
+	std::vector<int> dump_list;
 	for (int a = 5; a < argc; a++) {
 		if (!strcmp(argv[a], "align")) align = true;
 		else if (!strcmp(argv[a], "getlayer")) getlayer = true;
+		else if (!strncmp(argv[a], "dump=list:", 10)) {
+			dump = "list";
+			std::stringstream ss(argv[a] + 10);
+			std::string tok;
+			while (std::getline(ss, tok, ',')) dump_list.push_back(atoi(tok.c_str()));
+		}
 		else if (!strncmp(argv[a], "dump=", 5)) dump = argv[a] + 5;
+		else if (!strncmp(argv[a], "stats=", 6)) stats_stride = atoi(argv[a] + 6);
+		else if (!strncmp(argv[a], "gpus=", 5)) ngpus = atoi(argv[a] + 5);
 		else if (!strncmp(argv[a], "dt=", 3)) dt_override = atof(argv[a] + 3);
 		else if (!strncmp(argv[a], "sweep=", 6)) sweep = argv[a] + 6;
 		else if (!strncmp(argv[a], "threads=", 8)) omp_set_num_threads(atoi(argv[a] + 8));
@@ -189,9 +231,16 @@ int main(int argc, char **argv)
 					put(resVel, outN * sizeof(Vec3D));
 					put(resT, outN * sizeof(double));
 				}
-				if (dump == "every" || (dump == "last" && i == nsteps - 1)) {
-					put_i32(i); put_i32(0); put_f64(b200->GetError());
-					for (int q = 0; q < 4; q++) { b200->ReadField(CMC_LAYER_CUR, q, buf.data()); put(buf.data(), N * sizeof(FTYPE)); }
+				if (step_selected(dump, dump_list, i, nsteps)) {
+					if (stats_stride > 0) {
+						std::vector<FTYPE> all(4 * N);
+						const FTYPE *f[4];
+						for (int q = 0; q < 4; q++) { b200->ReadField(CMC_LAYER_CUR, q, all.data() + q * N); f[q] = all.data() + q * N; }
+						put_stats(i, b200->GetError(), f, dimx, dimy, dimz, stats_stride);
+					} else {
+						put_i32(i); put_i32(0); put_f64(b200->GetError());
+						for (int q = 0; q < 4; q++) { b200->ReadField(CMC_LAYER_CUR, q, buf.data()); put(buf.data(), N * sizeof(FTYPE)); }
+					}
 				}
 			}
 			printf("\nprobe: b200 steps %d, seconds %.6f, err %.10g\n", nsteps, t_steps, b200->GetError());
@@ -247,8 +296,13 @@ int main(int argc, char **argv)
 				put(resVel, outN * sizeof(Vec3D));
 				put(resT, outN * sizeof(double));
 			}
-			if (dump == "every" || (dump == "last" && i == nsteps - 1))
-				put_layer(i, 0, solver->diffError, solver->cur, N);
+			if (step_selected(dump, dump_list, i, nsteps)) {
+				if (stats_stride > 0) {
+					const FTYPE *f[4] = {&solver->cur->U->elem(0, 0, 0), &solver->cur->V->elem(0, 0, 0), &solver->cur->W->elem(0, 0, 0), &solver->cur->T->elem(0, 0, 0)};
+					put_stats(i, solver->diffError, f, dimx, dimy, dimz, stats_stride);
+				} else
+					put_layer(i, 0, solver->diffError, solver->cur, N);
+			}
 		}
 		printf("\nprobe: steps %d, seconds %.6f, sec_per_step %.6f, mcells_per_s %.6f, err %.10g\n",
 			nsteps, t_steps, nsteps ? t_steps / nsteps : 0.0,

@@ -77,6 +77,38 @@ def layer_errors(ref4, got4):
     return linf_v, l2_v, linf_T, l2_T
 
 
+COMPONENT_FLOOR = 1e-3
+
+
+def component_errors(ref4, got4):
+    """north_star's wording - "fields (u, v, w, T) must agree within a relative L2 / L-inf tolerance" - taken field by
+    field: for each of u, v, w, T the L-inf and L2 error relative to THAT field's own max / norm.  A component whose
+    magnitude is below COMPONENT_FLOOR (1e-3) of the velocity magnitude (v and w in a straight channel are rounding noise
+    around 0) is measured against that floor instead of against itself.  Returns [(linf, l2)] * 4."""
+    r = [np.asarray(a, dtype=np.float64).ravel() for a in ref4]
+    g = [np.asarray(a, dtype=np.float64).ravel() for a in got4]
+    vmax = max(max(float(np.abs(a).max()) for a in r[:3]), 1e-300)
+    vnorm = max(np.sqrt(sum(float(np.sum(a ** 2)) for a in r[:3])), 1e-300)
+    out = []
+    for q in range(4):
+        fmax, fnorm = float(np.abs(r[q]).max()), float(np.linalg.norm(r[q]))
+        if q < 3:
+            fmax, fnorm = max(fmax, COMPONENT_FLOOR * vmax), max(fnorm, COMPONENT_FLOOR * vnorm)
+        out.append((float(np.abs(r[q] - g[q]).max()) / max(fmax, 1e-300), float(np.linalg.norm(r[q] - g[q])) / max(fnorm, 1e-300)))
+    return out
+
+
+def assert_fields_close(ref4, got4, fp, what=""):
+    """The tolerance of every fast-mode parity test: fp64 1e-10, fp32 1e-5, per field (u, v, w, T separately) AND for the
+    velocity taken as one vector field."""
+    tol = {8: 1e-10, 4: 1e-5}[fp]
+    errs = layer_errors(ref4, got4)
+    assert max(errs) <= tol, f"{what}: (linf_vel, l2_vel, linf_T, l2_T) = {tuple(f'{e:.3e}' for e in errs)} > {tol}"
+    comp = component_errors(ref4, got4)
+    worst = max(max(c) for c in comp)
+    assert worst <= tol, f"{what}: per-field (linf, l2) of u, v, w, T = {[tuple(f'{e:.2e}' for e in c) for c in comp]} > {tol}"
+
+
 @pytest.fixture(scope="session")
 def oracle_mod():
     from oracle import oracle as O

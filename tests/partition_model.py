@@ -1,7 +1,7 @@
 """Host-side bookkeeping of the x-slab decomposition and a NumPy restatement of the partitioned (SPIKE-style)
 line solve that the CUDA kernels implement along the decomposed axis (csrc/kernels_fast.cu MODE 1 / k_x_interface /
-MODE 2).  Used by the host logic (slab table, line ownership) and by the CPU tests of the N > 1 path, which run the
-same algebra over `torch.distributed` (gloo) - no GPU involved.
+MODE 2).  TEST MODEL ONLY: used by tests/test_dist_gloo.py, which runs the same algebra over `torch.distributed`
+(gloo, world size 2) - no GPU involved; the product (cmc_fluid_solver_b200/) never imports it.
 
 Reference counterparts: GPUplan::splitEven1D (src/Common/GPUplan.cpp:122-141) for the split; the pipelined
 distributed Thomas it replaces is LaunchSolveSegments_X (src/FluidSolver3D/AdiSolver3D.cu:524-640).

@@ -1,5 +1,5 @@
 """The N > 1 path on CPU: world_size-2 (and 3) `gloo` process groups run the host-side restatement of the
-slab-decomposed x-solve (cmc_fluid_solver_b200/partition.py - the algebra of the CUDA kernels MODE 1, k_x_interface,
+slab-decomposed x-solve (tests/partition_model.py - the algebra of the CUDA kernels MODE 1, k_x_interface,
 MODE 2) with the same exchange pattern as the NCCL transport: all-to-all of the spike coefficients by line
 ownership, interface solve on the owner, all-to-all of the neighbours' row values back."""
 import os
@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from cmc_fluid_solver_b200 import partition as P
+import partition_model as P
 
 
 def test_split_even_matches_reference_rule():

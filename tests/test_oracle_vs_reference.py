@@ -142,3 +142,36 @@ def test_iteration_counts_match_reference_binary(oracle_mod, tmp_path, fp, iters
         assert err == s["err"]
         for q, n in enumerate("uvwT"):
             assert np.array_equal(o.field(O.LAYER_CUR, q).ravel(), s[n]), f"({ng},{nl}) step {i} field {n}"
+
+
+def test_oracle_matches_config2_golden_statistics(oracle_mod, tmp_path):
+    """BASELINE config 2 at its stated size (data/3D box_pipe at 128^3, 20 steps, fp64): the oracle restatement against the
+    statistics the reference CPU solver wrote (tests/golden/c2_box128_f64.npz, make_golden_configs.py).  The grid comes
+    from the reference's own loader (a 0-step run of the probe dumps its Node[] array)."""
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, str(GOLDEN))
+    import make_golden_configs as MG
+    O = oracle_mod
+    if not O.have_ref(8):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    z = np.load(GOLDEN / "c2_box128_f64.npz")
+    data, cfg = MG.write_case("c2_box128_f64", tmp_path)
+    O.run_ref(data, cfg, tmp_path / "nodes.bin", 0, fp_bytes=8, align=True, dump="none")
+    case = O.read_probe(tmp_path / "nodes.bin")
+    assert case.shape == (128, 128, 128) and case.n_in == int(z["n_in"])
+    o = O.Oracle3D(case)
+    o.create_segments()
+    stride = int(z["stride"])
+    want = {int(s): k for k, s in enumerate(z["steps"])}
+    for i in range(int(z["steps"][-1]) + 1):
+        o.update_boundaries()
+        err = o.time_step(case.dt, case.num_global, case.num_local, (i % 10 == 0) or i == 19)
+        if i in want:
+            k = want[i]
+            assert err == z["err"][k]
+            for q in range(4):
+                f = o.field(O.LAYER_CUR, q)
+                assert np.array_equal(f[::stride, ::stride, ::stride], z["sample"][k][q]), f"step {i} field {q}"
+                # the probe accumulates serially in index order; numpy sums pairwise: a different rounding of a 2-million-term sum
+                assert abs(float(f.sum(dtype=np.float64)) - z["sums"][k][q]) <= 1e-10 * max(z["sumabs"][k][q], 1e-300)

@@ -40,6 +40,8 @@ def main():
         one = AdiSolver3D().Init(case, device=lr, mode="fast"); one.CreateSegments()
         many = AdiSolver3D().Init(case, device=lr, mode="fast", rank=rank, nranks=world, nccl_id=nid); many.CreateSegments()
         assert [many.numSegs(d) for d in range(3)] == [one.numSegs(d) for d in range(3)], "segment counts differ"
+        if rank == 0:
+            print(f"exchange {many.exchange_kind()}", flush=True)
         for i in range(4):
             one.UpdateBoundaries(); many.UpdateBoundaries()
             e1 = one.TimeStep(case.dt, 4, 2, True)
@@ -49,6 +51,9 @@ def main():
         v, T = many.GetLayer(*case.outdims)
         if rank == 0:
             assert np.allclose(v, v1, rtol=0, atol=tol * 1e5) and np.allclose(T, T1, rtol=0, atol=tol * 1e5), "GetLayer differs"
+        s1, sN = one.field_sums(0), many.field_sums(0)
+        for n in "uvwT":
+            assert abs(s1[n][0] - sN[n][0]) <= tol * max(abs(s1[n][1]) ** 0.5, 1.0) * 1e3, ("checksum", n, s1[n], sN[n])
         sl = slice(many.x0, many.x0 + many.nx)
         errs = layer_errors([one.read_field(0, q)[sl] for q in range(4)], [many.read_field(0, q) for q in range(4)])
         good = max(errs) <= tol
