@@ -323,7 +323,7 @@ def main():
             tot += timings["x_spike"][0] + timings["x_interface"][0]
             nbytes += spike_bytes
         per_dir[k] = {"ms_per_launch": tot / n, "launches": n, "bytes_per_launch": nbytes, "gbs": nbytes / (tot / n * 1e-3) / 1e9,
-                      "frac": nbytes / (tot / n * 1e-3) / 1e9 / peak}
+                      "frac": nbytes / (tot / n * 1e-3) / 1e9 / peak, "kernel": sol.sweep_kernel_name(k)}
     dom = max(per_dir, key=lambda k: per_dir[k]["ms_per_launch"] * per_dir[k]["launches"]) if per_dir else None
     sweep_ms = sum(v["ms_per_launch"] * v["launches"] for v in per_dir.values())
     sweep_n = sum(v["launches"] for v in per_dir.values())

@@ -72,6 +72,13 @@ struct cmc_adi3d {
 	long long num_segs[3] = {0, 0, 0};
 	long long shared_free[3] = {0, 0, 0};   // cells shared by two segments with a BC_FREE row (informational)
 	int mode = CMC_MODE_FAST;
+	int tma_mask = default_tma_mask();
+	static int default_tma_mask()
+	{
+		const char *env = getenv("CMC_TMA");
+		if (!env) return 0;
+		return (strchr(env, 'x') ? 1 : 0) | (strchr(env, 'y') ? 2 : 0);
+	}
 	bool have_nodes = false, have_lines = false;
 
 	// optional per-kernel-kind device timing (cmc_adi3d_set_option "profile"): CUDA event pairs on `stream`
@@ -598,8 +605,12 @@ struct Engine : cmc_adi3d {
 	{
 		if (multi() && dir == CMC_DIR_X) return 4;
 		if (!fast_ok(dir)) return 0;
+		if (want_tma(dir) && tma_sweep_supported(slabs[0]->L, dir)) return 3;
 		return want_ring(dir) && ring_sweep_supported(slabs[0]->L, dir) ? 2 : 1;
 	}
+	// TMA-staged persistent tiles for the strided axes (kernels_tma.cu): option "tma" (bit 0 = x, bit 1 = y), default from
+	// CMC_TMA=<subset of "xy"> ("" = off)
+	bool want_tma(int dir) const { return dir != CMC_DIR_Z && ((tma_mask >> dir) & 1); }
 	// two data-movement variants of the same arithmetic (kernels_ring.cu / kernels_fast.cu).  Measured on B200 at 512^3
 	// (profiles/r01_variants.md): fp64 - the direct-load kernel wins everywhere (z: 2-line tiles, four independent CTAs per
 	// SM, 4.00 ms against 4.58 ms for the cp.async ring); fp32 - the ring wins along z (2.42 against 2.71 ms).
@@ -668,7 +679,8 @@ struct Engine : cmc_adi3d {
 					if (!launch_x_coupled<FT>(A, stream, &launches)) return fail(CMC_ERR_UNSUPPORTED, "coupled x-sweep: unsupported slab shape");
 					done = true;
 				} else if (fast_ok(dir)) {
-					if (want_ring(dir)) done = launch_ring_sweep<FT>(dir, A, stream, &launches);
+					if (want_tma(dir)) done = launch_tma_sweep<FT>(dir, A, stream, &launches);
+					if (!done && want_ring(dir)) done = launch_ring_sweep<FT>(dir, A, stream, &launches);
 					if (!done) done = launch_fast_sweep<FT>(dir, A, stream, &launches);
 				}
 				if (done) swapped[si] = 1;                               // merged temp went to the other buffer
@@ -1165,6 +1177,7 @@ int cmc_adi3d_set_option(cmc_adi3d *h, const char *key, int64_t value)
 		h->mode = (int)value;
 		return CMC_OK;
 	}
+	if (!strcmp(key, "tma")) { h->tma_mask = (int)value & 3; return CMC_OK; }
 	if (!strcmp(key, "profile")) {
 		h->spans_collect();
 		h->profile = value != 0;
@@ -1179,6 +1192,7 @@ int cmc_adi3d_get_option(const cmc_adi3d *h, const char *key, int64_t *value)
 	H_CHECK(h);
 	if (!key || !value) return fail(CMC_ERR_INVALID, "get_option: null argument");
 	if (!strcmp(key, "mode")) { *value = h->mode; return CMC_OK; }
+	if (!strcmp(key, "tma")) { *value = h->tma_mask; return CMC_OK; }
 	if (!strcmp(key, "nzp")) { *value = h->L.nzp; return CMC_OK; }
 	if (!strcmp(key, "jb")) { *value = h->L.nblk == 1 ? 0 : (1 << h->L.jbs); return CMC_OK; }   // rows per y-block, 0 = one block
 	if (!strncmp(key, "kernel_", 7) && key[7] >= 'x' && key[7] <= 'z' && !key[8]) { *value = h->kernel_kind(key[7] - 'x'); return CMC_OK; }

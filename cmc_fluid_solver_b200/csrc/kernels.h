@@ -20,6 +20,10 @@ bool launch_fast_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long lon
 template <typename FT>
 bool launch_ring_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
 bool ring_sweep_supported(const Layout &L, int dir);
+// kernels_tma.cu: x / y sweeps as persistent CTAs fed by bulk-tensor copies (TMA); false = not applicable, use the above
+template <typename FT>
+bool launch_tma_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
+bool tma_sweep_supported(const Layout &L, int dir);
 // partitioned x-sweep (slab-decomposed grid): spike pass, interface solve, coupled sweep
 template <typename FT>
 bool launch_x_spike(const SweepArgs<FT> &A, cudaStream_t s, long long *launches);

@@ -1,0 +1,592 @@
+// kernels_tma.cu - CMC_MODE_FAST sweeps along the strided axes (x, y) as persistent CTAs fed by the Tensor Memory
+// Accelerator (cp.async.bulk.tensor / UTMALDG): BASELINE.json north_star's "TMA-staged tiles" for the strided-axis sweeps.
+//
+// Same arithmetic as k_fast_sweep (kernels_fast.cu: partition method with 8-row chunks in registers, CR + PCR reduced
+// solve in shared memory, coefficient build / boundary rows / mask / relaxation fused), different data movement.  The
+// direct-load kernel is latency bound (ncu, profiles/r01_ncu_sweeps_final.md): one 512-thread CTA per SM owns the
+// register file, ~150 LDG and ~64 STG per thread per tile go through the LSU (lg_throttle 2.0-2.3 stall cycles per
+// issue), its load phases are separated by barriers and HBM idles while the SM solves (DRAM 42 % busy).  Here
+//   * one persistent CTA per SM walks over its tiles (tile = 8 neighbouring lines x all rows of the line);
+//   * every input field of a tile arrives by ONE bulk-tensor copy per field (a 5-D box that gathers the 64-byte row
+//     segments of the tile - rows 256 KB (x) / 4 KB (y) apart - straight into a shared-memory slot laid out
+//     [row-in-chunk][chunk][line], which the compute threads read without bank conflicts); thread 0 issues them, an
+//     mbarrier per slot counts the bytes in;
+//   * six slots (6 x 32 KB in fp64), eleven copies per tile, each issued one solve phase (or more) before its use:
+//         slot 0: temp[DIR]            (resident from the u,v,w phase to the dissipation function)
+//         slot 1: temp.T   -> the first other temp component
+//         slot 2: cur.u    -> the second other temp component
+//         slot 3: cur.v    -> temp[DIR] of the cross-line neighbour below (j-1 for x lines, i-1 for y lines)
+//         slot 4: cur.w    -> temp[DIR] of the cross-line neighbour above
+//         slot 5: cur.T    -> temp.T (for the relaxation of T at the end)
+//     so HBM streams while the SM eliminates / solves the reduced systems, and the LSU only sees shared-memory loads and
+//     the result stores;
+//   * no global load in the common path except the k +- 1 neighbours of the two edge lines of a tile.
+// Requirements (launch_tma_sweep returns false otherwise and the caller uses k_fast_sweep): x or y sweep of a slab whose
+// lines stay inside the slab (MODE 0), line length a multiple of 8 and at most 512.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <algorithm>
+#include <cuda.h>
+#include "kernels.h"
+#include "fast_core.cuh"
+#include "ring_slots.cuh"
+
+namespace cmc {
+
+// ---- tensor maps ------------------------------------------------------------------------------------------------------
+struct TmaMaps {
+	CUtensorMap temp[4];     // linearisation layer (read)
+	CUtensorMap cur[4];      // the sweep's "cur" layer
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+	static EncodeTiledFn fn = nullptr;
+	static bool tried = false;
+	if (!tried) {
+		tried = true;
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+			fn = reinterpret_cast<EncodeTiledFn>(p);
+		else
+			cudaGetLastError();
+	}
+	return fn;
+}
+
+// One map per (field buffer, direction, layout): the layers rotate through a handful of physical buffers, so the maps
+// are built once and cached.
+struct MapKey {
+	const void *ptr; int dir, fp, gp, nx, ny, nz, jbs;
+	bool operator<(const MapKey &o) const { return memcmp(this, &o, sizeof(MapKey)) < 0; }
+};
+
+template <typename FT>
+static bool tensor_map_for(const FT *field, const Layout &L, int dir, int GP, CUtensorMap *out)
+{
+	static std::map<MapKey, CUtensorMap> cache;
+	static std::mutex mu;
+	MapKey key;
+	memset(&key, 0, sizeof key);
+	key.ptr = field; key.dir = dir; key.fp = (int)sizeof(FT); key.gp = GP; key.nx = L.nx; key.ny = L.ny; key.nz = L.nz; key.jbs = L.jbs;
+	std::lock_guard<std::mutex> lock(mu);
+	auto it = cache.find(key);
+	if (it != cache.end()) { *out = it->second; return true; }
+	EncodeTiledFn enc = encode_fn();
+	if (!enc) return false;
+	const cuuint64_t es = sizeof(FT);
+	const int rows_per_block = L.nblk > 1 ? (1 << L.jbs) : L.ny;
+	cuuint64_t dims[5], strides[4];
+	cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+	void *base;
+	if (dir == 0) {
+		// (k, chunk along x, row in chunk, j inside its y-block, y-block); plane 0 is the first real plane
+		dims[0] = (cuuint64_t)L.nzp; dims[1] = (cuuint64_t)(L.nx / M); dims[2] = M; dims[3] = (cuuint64_t)rows_per_block; dims[4] = (cuuint64_t)L.nblk;
+		strides[0] = (cuuint64_t)(M * L.plane) * es; strides[1] = (cuuint64_t)L.plane * es; strides[2] = (cuuint64_t)L.nzp * es; strides[3] = (cuuint64_t)L.bstride * es;
+		box[0] = 8; box[1] = (cuuint32_t)GP; box[2] = M; box[3] = 1; box[4] = 1;
+		base = (void *)(field + L.plane);
+	} else {
+		// (k, chunk inside a y-block, y-block, row in chunk, x-plane incl. the guard planes)
+		const int gb = rows_per_block / M;
+		dims[0] = (cuuint64_t)L.nzp; dims[1] = (cuuint64_t)gb; dims[2] = (cuuint64_t)L.nblk; dims[3] = M; dims[4] = (cuuint64_t)(L.nx + 2);
+		strides[0] = (cuuint64_t)(M * L.nzp) * es; strides[1] = (cuuint64_t)L.bstride * es; strides[2] = (cuuint64_t)L.nzp * es; strides[3] = (cuuint64_t)L.plane * es;
+		const int bg = L.nblk > 1 ? gb : GP;            // chunks of one y-block in the box; GP / bg blocks
+		box[0] = 8; box[1] = (cuuint32_t)bg; box[2] = (cuuint32_t)(GP / bg); box[3] = M; box[4] = 1;
+		base = (void *)field;
+	}
+	const CUtensorMapDataType dt = sizeof(FT) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+	CUtensorMap m;
+	const CUresult r = enc(&m, dt, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+	                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) {
+		static bool warned = false;
+		if (!warned) { warned = true; fprintf(stderr, "[cmc] cuTensorMapEncodeTiled failed (%d) for dir %d: using the direct-load sweep kernel\n", (int)r, dir); }
+		return false;
+	}
+	cache[key] = m;
+	*out = m;
+	return true;
+}
+
+// ---- device helpers -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+	// try_wait suspends the thread for up to the given time (ns) per attempt; a copy that never completes (a tensor map
+	// that does not describe the buffer) must not hang the device: trap after about two seconds
+	long long t0 = 0;
+	for (int tries = 0;; tries++) {
+		unsigned ok;
+		asm volatile(
+			"{\n\t"
+			".reg .pred P1;\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x100000;\n\t"
+			"selp.u32 %0, 1, 0, P1;\n\t"
+			"}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+		if (ok) return;
+		if ((tries & 63) == 63) {
+			const long long now = clock64();
+			if (!t0) t0 = now;
+			else if (now - t0 > 4000000000ll) __trap();       // ~2 s at 1.9 GHz
+		}
+	}
+}
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, int c2, int c3, int c4)
+{
+	asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+	             ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)),
+	             "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------------------------------
+template <typename FT, int DIR, int GP>
+__global__ void __launch_bounds__(GP * 8, GP >= 64 ? 1 : 2)
+k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant__ TmaMaps TM, const int ntiles)
+{
+	static_assert(DIR == 0 || DIR == 1, "strided axes only (z lines are contiguous: kernels_fast.cu)");
+	constexpr int NL = 8;
+	constexpr int STR = GP * NL;
+	constexpr int GS = NL;                          // shared-memory distance of neighbouring chunks of a line
+	constexpr int SLOT = STR * M;                   // elements per slot: one field of one tile
+	constexpr int NW = STR / 32;                    // warps
+	constexpr unsigned SLOT_BYTES = SLOT * (unsigned)sizeof(FT);
+	// the two temp components other than the one along the sweep, and their slots
+	constexpr int QO1 = DIR == 0 ? 1 : 0, QO2 = 2;
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	FT *slots = reinterpret_cast<FT *>(smem_raw);                                   // 6 slots
+	FT *sys = slots + 6 * SLOT;                                                     // reduced-solve scratch
+	FT *sol = sys;                                                                  // aliases the CR publications (see reduced_solve)
+	FT *headx = sys + reduced_scratch_elems<3, GP, NL>();                           // heads that cross a warp: 5 x (NW * 8)
+	uint8_t *roles = reinterpret_cast<uint8_t *>(headx + 5 * NW * 8);               // descriptor bytes of the tile: 8 * STR
+	unsigned long long *full = reinterpret_cast<unsigned long long *>(roles + 8 * STR);   // 6 mbarriers
+#define SLOTP(k) (slots + (k) * SLOT)
+
+	const Layout &L = A.L;
+	const int t = threadIdx.x;
+	const int l = t % NL, g = t / NL;               // line in tile, chunk
+	const int e = t;                                // == g * NL + l
+	const int lane = t & 31, warp = t >> 5;
+	const int r0 = g * M;
+	const int n = DIR == 0 ? L.nx : L.ny;
+	const int GL = n / M;                           // chunks that hold real rows (n % 8 == 0)
+	const int ktiles = (L.nz + NL - 1) / NL;
+	const int stride = DIR == 0 ? (int)L.plane : (int)L.nzp;        // between the rows of a chunk
+
+	if (t == 0) {
+#pragma unroll
+		for (int s = 0; s < 6; s++) mbar_init(full + s, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	__syncthreads();
+	unsigned ph = 0;                                // phase parity of every slot's mbarrier
+#define WAIT_SLOT(s) do { mbar_wait(full + (s), (ph >> (s)) & 1u); ph ^= 1u << (s); } while (0)
+
+	// box coordinates of (field tile, cross-line shift dj) of a tile
+	auto issue = [&](int s, const CUtensorMap *map, int tile, int shift) {
+		const int a = tile / ktiles, k0 = (tile - a * ktiles) * NL;       // a = j (x lines) or i (y lines)
+		mbar_expect_tx(full + s, SLOT_BYTES);
+		if (DIR == 0) {
+			const int j = min(max(a + shift, 0), L.ny - 1);
+			tma_load_5d(SLOTP(s), map, full + s, k0, 0, 0, j & L.jbm, j >> L.jbs);
+		} else
+			tma_load_5d(SLOTP(s), map, full + s, k0, 0, 0, 0, a + 1 + shift);
+	};
+	auto issue_A = [&](int tile) {                 // u,v,w phase inputs
+		issue(0, &TM.temp[DIR], tile, 0);
+		issue(1, &TM.temp[3], tile, 0);
+		issue(2, &TM.cur[0], tile, 0);
+		issue(3, &TM.cur[1], tile, 0);
+		issue(4, &TM.cur[2], tile, 0);
+	};
+	// descriptor bytes: 8 per tile row, thread <-> tile row
+	auto issue_roles = [&](int tile) {
+		const int a = tile / ktiles, k0 = (tile - a * ktiles) * NL;
+		const int r = min(t, n - 1);
+		const long long o = DIR == 0 ? L.idx(r, a, k0) : L.idx(a, r, k0);
+		cp_async8(roles + (size_t)t * 8, A.role + o);
+		cp_async_commit();
+	};
+
+	int tile = blockIdx.x;
+	if (tile < ntiles) {
+		if (t == 0) { issue_A(tile); issue(5, &TM.cur[3], tile, 0); }
+		issue_roles(tile);
+	}
+
+	for (; tile < ntiles; tile += gridDim.x) {
+		const int next_tile = tile + (int)gridDim.x;
+		const int a = tile / ktiles, k0 = (tile - a * ktiles) * NL;
+		const int k = k0 + l;
+		const bool line_ok = k < L.nz;
+		// global offsets of the chunk's rows (stores, boundary-row node values, edge-line k +- 1 loads)
+		const int rc = min(r0, n - 1);              // (padding chunks: clamped, never stored)
+		const int off0 = (int)(DIR == 0 ? L.idx(rc, a, line_ok ? k : 0) : L.idx(a, rc, line_ok ? k : 0));
+		int off[M];
+#pragma unroll
+		for (int i = 0; i < M; i++) off[i] = off0 + (r0 < n ? i : 0) * stride;
+		// distance from the chunk's last row to the next row of the line (y lines: may cross into the next y-block)
+		const int rn = min(r0 + M, n - 1);
+		const int step_last = (int)(DIR == 0 ? L.idx(rn, a, line_ok ? k : 0) : L.idx(a, rn, line_ok ? k : 0)) - off[M - 1];
+		unsigned rowmask = (line_ok && r0 < n) ? 0xffu : 0u;
+		// rows r0 - 1 and r0 + 8 of the line inside a slot (clamped into the line like the direct-load kernel)
+		const int e_lo = g > 0 ? (M - 1) * STR + e - GS : e;               // row r0 - 1 = last row of chunk g - 1
+		const int e_hi = g + 1 < GL ? e + GS : (M - 1) * STR + e;          // row r0 + 8 = first row of chunk g + 1
+
+		cp_async_wait_all();
+		WAIT_SLOT(0); WAIT_SLOT(1); WAIT_SLOT(2); WAIT_SLOT(3); WAIT_SLOT(4);
+		__syncthreads();            // roles (cp.async of every thread) have landed
+
+		unsigned rw0 = 0, rw1 = 0;
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			rw0 |= (unsigned)roles[(min(r0, n - M) + i) * 8 + l] << (8 * i);
+			rw1 |= (unsigned)roles[(min(r0, n - M) + 4 + i) * 8 + l] << (8 * i);
+		}
+		if (!rowmask) { rw0 = 0; rw1 = 0; }
+#define ROLE(i) (((i) < 4 ? rw0 >> (8 * (i)) : rw1 >> (8 * ((i) - 4))) & 0xffu)
+		unsigned segmask = 0, inmask = 0;
+#pragma unroll
+		for (int i = 0; i < M; i++) {
+			segmask |= (ROLE(i) & R_SEG) ? (1u << i) : 0u;
+			inmask |= (ROLE(i) & R_IN) ? (1u << i) : 0u;
+		}
+		const bool any_int = ((rw0 | rw1) & (R_INT * 0x01010101u)) != 0;
+		const unsigned holes = inmask & ~segmask;      // fluid cells outside every segment (dropped runs)
+		const unsigned full_m = rowmask;
+		const unsigned segfull = segmask;
+
+		// ======================================= phase V: u, v, w ==========================================
+		FT cp[M], lp[M], dp[3][M];
+		FT b7 = FT(1), rr;
+		{
+			FT V[M], Tl[M];
+#pragma unroll
+			for (int i = 0; i < M; i++) {
+				V[i] = SLOTP(0)[i * STR + e];
+				Tl[i] = SLOTP(1)[i * STR + e];
+				dp[0][i] = SLOTP(2)[i * STR + e];
+				dp[1][i] = SLOTP(3)[i * STR + e];
+				dp[2][i] = SLOTP(4)[i * STR + e];
+			}
+			const FT Tlo = SLOTP(1)[e_lo], Thi = SLOTP(1)[e_hi];
+			__syncthreads();        // every thread has its inputs in registers: slots 1-4 are free (slot 0 stays)
+			if (t == 0) {
+				issue(1, &TM.temp[QO1], tile, 0);
+				issue(2, &TM.temp[QO2], tile, 0);
+				issue(3, &TM.temp[DIR], tile, -1);
+				issue(4, &TM.temp[DIR], tile, +1);
+			}
+#pragma unroll
+			for (int i = 0; i < M; i++) {
+				dp[0][i] *= K.c3dt; dp[1][i] *= K.c3dt; dp[2][i] *= K.c3dt;
+				dp[DIR][i] -= K.v_T * cdiff<FT>(Tl, Tlo, Thi, i, K.inv2h);
+			}
+#pragma unroll
+			for (int i = 0; i < M; i++) {
+				const unsigned r = ROLE(i);
+				const FT Vh = V[i] * K.inv2h;
+				FT a_ = -Vh - K.vis_v, c = Vh - K.vis_v, b = K.b_v;
+				FT d0 = dp[0][i], d1 = dp[1][i], d2 = dp[2][i];
+				if ((r & (R_SEG | R_PRE)) != R_INT) {       // rare: boundary row, cell outside every segment, or shared-cell fold
+					const bool vfree = r & R_VFREE;
+					if (r & R_INT) {                        // R_PRE: the next cell ends this segment AND starts the next one
+						if (vfree) b += FT(0.5) * c;
+						else {
+							const int idn = off[i] + (i == M - 1 ? step_last : stride);
+							d0 -= c * A.nodev[0][idn]; d1 -= c * A.nodev[1][idn]; d2 -= c * A.nodev[2][idn];
+						}
+						c = FT(0);
+					} else if (r & (R_START | R_END)) {     // ApplyBC0 / ApplyBC1 (a shared cell keeps its start row only)
+						a_ = ((r & (R_END | R_START)) == R_END && vfree) ? FT(-1) : FT(0);
+						c = ((r & R_START) && vfree) ? FT(-1) : FT(0);
+						b = vfree ? FT(2) : FT(1);
+						d0 = d1 = d2 = FT(0);
+						if (!vfree) { d0 = A.nodev[0][off[i]]; d1 = A.nodev[1][off[i]]; d2 = A.nodev[2][off[i]]; }
+					} else { a_ = FT(0); c = FT(0); b = FT(1); d0 = d1 = d2 = FT(0); }
+				}
+				CMC_ELIM_ROW(i, a_, b, c)
+				if (i == M - 1) { dp[0][i] = d0; dp[1][i] = d1; dp[2][i] = d2; }
+				else if (i == 0) { dp[0][0] = d0 * rr; dp[1][0] = d1 * rr; dp[2][0] = d2 * rr; }
+				else {
+					dp[0][i] = (d0 - a_ * dp[0][i - 1]) * rr;
+					dp[1][i] = (d1 - a_ * dp[1][i - 1]) * rr;
+					dp[2][i] = (d2 - a_ * dp[2][i - 1]) * rr;
+				}
+			}
+		}
+		// head of the NEXT chunk of the line (thread t + 8): lanes 0-23 by shuffle, lanes 24-31 from the next warp's
+		// lanes 0-7 through headx
+#define NEXT_HEAD(dst, val, slot_)                                                     \
+		do {                                                                           \
+			const FT sh__ = __shfl_down_sync(0xffffffffu, (val), 8);                   \
+			(dst) = lane < 24 ? sh__ : (warp + 1 < NW ? headx[(slot_) * (NW * 8) + (warp + 1) * 8 + (lane - 24)] : FT(0)); \
+		} while (0)
+		FT E[3];
+		{
+			// coupling of the first interior row to the two separators: x_0 = y0 - v0*E(g-1) - w0*E(g)
+			FT y0[3] = {dp[0][M - 2], dp[1][M - 2], dp[2][M - 2]}, v0 = lp[M - 2], w0 = cp[M - 2];
+#pragma unroll
+			for (int i = M - 3; i >= 0; i--) {
+				y0[0] = dp[0][i] - cp[i] * y0[0]; y0[1] = dp[1][i] - cp[i] * y0[1]; y0[2] = dp[2][i] - cp[i] * y0[2];
+				v0 = lp[i] - cp[i] * v0; w0 = -cp[i] * w0;
+			}
+			if (lane < 8) {
+				headx[0 * (NW * 8) + warp * 8 + lane] = y0[0]; headx[1 * (NW * 8) + warp * 8 + lane] = y0[1];
+				headx[2 * (NW * 8) + warp * 8 + lane] = y0[2]; headx[3 * (NW * 8) + warp * 8 + lane] = v0;
+				headx[4 * (NW * 8) + warp * 8 + lane] = w0;
+			}
+			__syncthreads();
+			FT ny0, ny1, ny2, nv, nw;
+			NEXT_HEAD(ny0, y0[0], 0); NEXT_HEAD(ny1, y0[1], 1); NEXT_HEAD(ny2, y0[2], 2); NEXT_HEAD(nv, v0, 3); NEXT_HEAD(nw, w0, 4);
+			const FT a7 = lp[M - 1], c7 = cp[M - 1];
+			rr = rcp<FT>(b7 - a7 * cp[M - 2] - c7 * nv);
+			FT Rd[3];
+			Rd[0] = (dp[0][M - 1] - a7 * dp[0][M - 2] - c7 * ny0) * rr;
+			Rd[1] = (dp[1][M - 1] - a7 * dp[1][M - 2] - c7 * ny1) * rr;
+			Rd[2] = (dp[2][M - 1] - a7 * dp[2][M - 2] - c7 * ny2) * rr;
+			reduced_solve<FT, 3, GP, GS, NL>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, E);    // every row's solution -> sol[]
+		}
+		// back substitution in place (dp[q] <- x: retires cp / lp), then store u, v, w and the relaxed linearisation layer
+#pragma unroll
+		for (int q = 0; q < 3; q++) {
+			const FT El = g > 0 ? sol[q * STR + e - GS] : FT(0);
+			dp[q][M - 1] = E[q];
+#pragma unroll
+			for (int i = M - 2; i >= 0; i--) dp[q][i] = dp[q][i] - lp[i] * El - cp[i] * dp[q][i + 1];
+		}
+		WAIT_SLOT(1); WAIT_SLOT(2);
+#pragma unroll
+		for (int q = 0; q < 3; q++) {
+			FT (&x)[M] = dp[q];
+			const FT *sq = q == DIR ? SLOTP(0) : q == QO1 ? SLOTP(1) : SLOTP(2);
+			FT tq[M];
+#pragma unroll
+			for (int i = 0; i < M; i++) tq[i] = sq[i * STR + e];
+			if (holes) {                      // merge those with the OLD value of `next` (MergeFieldTo reads whatever is there)
+#pragma unroll
+				for (int i = 0; i < M; i++)
+					if (holes & (1u << i)) x[i] = A.next[q][off[i]];
+			}
+			relax8<FT, DIR>(tq, x, inmask, A.extra_merge);
+			store8<FT, DIR>(A.temp_out[q], off, full_m, tq);
+			store8<FT, DIR>(A.next[q], off, segfull, x);
+			push_planes<FT, DIR, 0>(A, q, a, g, GP, off, full_m, segfull, tq, x);
+		}
+
+		// ======================================= phase T ======================================================
+		FT (&dT)[M] = dp[0];
+		{
+			FT diss[M], V[M];
+			{
+				// dissipation function of the sweep direction (TimeLayer3D.h:554-588), accumulated component by component:
+				//   X: 2 u_x^2 + v_x^2 + w_x^2 + v_x u_y + w_x u_z ; Y: u_y^2 + 2 v_y^2 + w_y^2 + u_y v_x + w_y v_z
+				// c1, c2: the two cross-line derivatives of temp[DIR]; c1 pairs with component QA, c2 with QB
+				constexpr int QA = DIR == 0 ? 1 : 0, QB = 2;
+				FT c1[M], c2[M];
+				{
+					// second cross direction (k +- 1): the neighbouring lines of the tile, the two edge lines from L2 / HBM
+					FT p2[M], m2[M];
+					if (l == NL - 1) {
+#pragma unroll
+						for (int i = 0; i < M; i++) p2[i] = A.temp[DIR][off[i] + 1];
+					} else {
+#pragma unroll
+						for (int i = 0; i < M; i++) p2[i] = SLOTP(0)[i * STR + e + 1];
+					}
+					if (l == 0) {
+#pragma unroll
+						for (int i = 0; i < M; i++) m2[i] = A.temp[DIR][off[i] - 1];
+					} else {
+#pragma unroll
+						for (int i = 0; i < M; i++) m2[i] = SLOTP(0)[i * STR + e - 1];
+					}
+#pragma unroll
+					for (int i = 0; i < M; i++) c2[i] = (p2[i] - m2[i]) * K.inv2h2;
+				}
+				WAIT_SLOT(3); WAIT_SLOT(4);
+#pragma unroll
+				for (int i = 0; i < M; i++) c1[i] = (SLOTP(4)[i * STR + e] - SLOTP(3)[i * STR + e]) * K.inv2h1;
+#pragma unroll
+				for (int i = 0; i < M; i++) diss[i] = FT(0);
+#pragma unroll
+				for (int q = 0; q < 3; q++) {
+					const FT *sq = q == DIR ? SLOTP(0) : q == QO1 ? SLOTP(1) : SLOTP(2);
+					FT f[M];
+#pragma unroll
+					for (int i = 0; i < M; i++) f[i] = sq[i * STR + e];
+					const FT lo = sq[e_lo], hi = sq[e_hi];
+#pragma unroll
+					for (int i = 0; i < M; i++) {
+						const FT d = cdiff<FT>(f, lo, hi, i, K.inv2h);
+						FT w = q == DIR ? d + d : d;
+						if (q == QA) w += c1[i];
+						if (q == QB) w += c2[i];
+						diss[i] += d * w;
+					}
+					if (q == DIR) {
+#pragma unroll
+						for (int i = 0; i < M; i++) V[i] = f[i];
+					}
+				}
+				if (!any_int) {      // no interior row: the (clamped) neighbour values above were never meant to be used
+#pragma unroll
+					for (int i = 0; i < M; i++) diss[i] = FT(0);
+				}
+			}
+			FT cT[M];
+			WAIT_SLOT(5);
+#pragma unroll
+			for (int i = 0; i < M; i++) cT[i] = SLOTP(5)[i * STR + e];
+			__syncthreads();        // every slot has been consumed
+			if (t == 0) {
+				issue(5, &TM.temp[3], tile, 0);
+				if (next_tile < ntiles) issue_A(next_tile);
+			}
+			if (next_tile < ntiles) issue_roles(next_tile);
+#pragma unroll
+			for (int i = 0; i < M; i++) {
+				const unsigned r = ROLE(i);
+				const FT Vh = V[i] * K.inv2h;
+				FT a_ = -Vh - K.vis_T, c = Vh - K.vis_T, b = K.b_T;
+				FT d = cT[i] * K.c3dt + K.t_phi * diss[i];
+				if ((r & (R_SEG | R_PRE)) != R_INT) {
+					const bool tfree = r & R_TFREE;
+					if (r & R_INT) {
+						if (tfree) b += FT(0.5) * c;
+						else d -= c * A.nodev[3][off[i] + (i == M - 1 ? step_last : stride)];
+						c = FT(0);
+					} else if (r & (R_START | R_END)) {
+						a_ = ((r & (R_END | R_START)) == R_END && tfree) ? FT(-1) : FT(0);
+						c = ((r & R_START) && tfree) ? FT(-1) : FT(0);
+						b = tfree ? FT(2) : FT(1);
+						d = tfree ? FT(0) : A.nodev[3][off[i]];
+					} else { a_ = FT(0); c = FT(0); b = FT(1); d = FT(0); }
+				}
+				CMC_ELIM_ROW(i, a_, b, c)
+				if (i == M - 1) dT[i] = d;
+				else if (i == 0) dT[0] = d * rr;
+				else dT[i] = (d - a_ * dT[i - 1]) * rr;
+			}
+		}
+		{
+			FT y0 = dT[M - 2], v0 = lp[M - 2], w0 = cp[M - 2];
+#pragma unroll
+			for (int i = M - 3; i >= 0; i--) { y0 = dT[i] - cp[i] * y0; v0 = lp[i] - cp[i] * v0; w0 = -cp[i] * w0; }
+			if (lane < 8) {
+				headx[0 * (NW * 8) + warp * 8 + lane] = y0; headx[3 * (NW * 8) + warp * 8 + lane] = v0; headx[4 * (NW * 8) + warp * 8 + lane] = w0;
+			}
+			__syncthreads();
+			FT ny0, nv, nw;
+			NEXT_HEAD(ny0, y0, 0); NEXT_HEAD(nv, v0, 3); NEXT_HEAD(nw, w0, 4);
+			const FT a7 = lp[M - 1], c7 = cp[M - 1];
+			rr = rcp<FT>(b7 - a7 * cp[M - 2] - c7 * nv);
+			FT Rd[1] = {(dT[M - 1] - a7 * dT[M - 2] - c7 * ny0) * rr}, ET[1];
+			reduced_solve<FT, 1, GP, GS, NL>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, ET);
+			const FT El = g > 0 ? sol[e - GS] : FT(0);
+			FT x[M], tq[M];
+			x[M - 1] = ET[0];
+#pragma unroll
+			for (int i = M - 2; i >= 0; i--) x[i] = dT[i] - lp[i] * El - cp[i] * x[i + 1];
+			WAIT_SLOT(5);
+#pragma unroll
+			for (int i = 0; i < M; i++) tq[i] = SLOTP(5)[i * STR + e];
+			__syncthreads();        // slot 5 consumed (and sol / headx are free for the next tile)
+			if (t == 0 && next_tile < ntiles) issue(5, &TM.cur[3], next_tile, 0);
+			if (holes) {
+#pragma unroll
+				for (int i = 0; i < M; i++)
+					if (holes & (1u << i)) x[i] = A.next[3][off[i]];
+			}
+			relax8<FT, DIR>(tq, x, inmask, A.extra_merge);
+			store8<FT, DIR>(A.temp_out[3], off, full_m, tq);
+			store8<FT, DIR>(A.next[3], off, segfull, x);
+			push_planes<FT, DIR, 0>(A, 3, a, g, GP, off, full_m, segfull, tq, x);
+		}
+	}
+	cp_async_wait_all();
+#undef ROLE
+#undef SLOTP
+#undef WAIT_SLOT
+#undef NEXT_HEAD
+}
+
+template <typename FT, int GP>
+static size_t tma_smem_bytes()
+{
+	const size_t STR = (size_t)GP * 8;
+	return sizeof(FT) * (6 * STR * M + reduced_scratch_elems<3, GP, 8>() + 5 * (STR / 32) * 8) + 8 * STR + 6 * sizeof(unsigned long long);
+}
+
+bool tma_sweep_supported(const Layout &L, int dir)
+{
+	if (dir != 0 && dir != 1) return false;
+	if (!fast_sweep_supported(L, dir)) return false;
+	const int n = dir == 0 ? L.nx : L.ny;
+	if (n % M != 0 || n / M > 64 || n / M <= 16) return false;           // 136 .. 512 rows: 256- and 512-thread CTAs
+	if (L.nblk > 1 && ((1 << L.jbs) % M != 0)) return false;
+	return encode_fn() != nullptr;
+}
+
+template <typename FT, int DIR, int GP>
+static bool launch_tma_one(const SweepArgs<FT> &A, cudaStream_t s)
+{
+	const Layout &L = A.L;
+	if (DIR == 1 && L.nblk > 1 && (GP % ((1 << L.jbs) / M) != 0)) return false;
+	TmaMaps TM;
+	for (int q = 0; q < 4; q++) {
+		if (!tensor_map_for<FT>(A.temp[q], L, DIR, GP, &TM.temp[q])) return false;
+		if (!tensor_map_for<FT>(A.cur[q], L, DIR, GP, &TM.cur[q])) return false;
+	}
+	const int ntiles = (DIR == 0 ? L.ny : L.nx) * ((L.nz + 7) / 8);
+	const size_t smem = tma_smem_bytes<FT, GP>();
+	static int ctas_of[64] = {};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64) return false;
+	if (!ctas_of[dev]) {
+		if (cudaFuncSetAttribute((const void *)k_tma_sweep<FT, DIR, GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
+		int per_sm = 0, sms = 0;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tma_sweep<FT, DIR, GP>, GP * 8, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return false; }
+		ctas_of[dev] = per_sm * sms;
+	}
+	FastConst<FT> K; K.init(A, DIR);
+	k_tma_sweep<FT, DIR, GP><<<std::min(ctas_of[dev], ntiles), GP * 8, smem, s>>>(A, K, TM, ntiles);
+	return true;
+}
+
+template <typename FT>
+bool launch_tma_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches)
+{
+	const Layout &L = A.L;
+	if (!tma_sweep_supported(L, dir)) return false;
+	const int n = dir == 0 ? L.nx : L.ny;
+	const int GP = n / M > 32 ? 64 : 32;
+	bool ok;
+	if (dir == 0) ok = GP == 64 ? launch_tma_one<FT, 0, 64>(A, s) : launch_tma_one<FT, 0, 32>(A, s);
+	else ok = GP == 64 ? launch_tma_one<FT, 1, 64>(A, s) : launch_tma_one<FT, 1, 32>(A, s);
+	if (ok && launches) (*launches)++;
+	return ok;
+}
+template bool launch_tma_sweep<float>(int, const SweepArgs<float> &, cudaStream_t, long long *);
+template bool launch_tma_sweep<double>(int, const SweepArgs<double> &, cudaStream_t, long long *);
+
+} // namespace cmc

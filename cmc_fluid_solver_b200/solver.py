@@ -101,6 +101,14 @@ class AdiSolver3D:
         _check(load_library().cmc_adi3d_set_option(self._h, b"mode", m))
         self.mode = m
 
+    def set_option(self, key: str, value: int):
+        _check(load_library().cmc_adi3d_set_option(self._h, key.encode(), int(value)))
+
+    def get_option(self, key: str) -> int:
+        v = C.c_int64(0)
+        _check(load_library().cmc_adi3d_get_option(self._h, key.encode(), C.byref(v)))
+        return v.value
+
     def close(self):
         if self._h:
             load_library().cmc_adi3d_destroy(self._h)

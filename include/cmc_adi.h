@@ -126,7 +126,8 @@ int cmc_adi3d_time_step(cmc_adi3d *h, double dt, int num_global, int num_local,
  * Output dims of 0 mean "grid dims".  On a distributed handle every rank must call; rank 0 receives the result. */
 int cmc_adi3d_get_layer(cmc_adi3d *h, void *vel_xyz, double *T, int outdimx, int outdimy, int outdimz);
 
-/* ---- options ----  "mode": CMC_MODE_FAST | CMC_MODE_EXACT;  "profile": 0|1|2 (see cmc_adi3d_get_timing);
+/* ---- options ----  "mode": CMC_MODE_FAST | CMC_MODE_EXACT;  "tma": bit 0 / bit 1 = run the x / y sweeps as TMA-staged
+ * persistent tiles where the grid allows (kernels_tma.cu; default from the environment variable CMC_TMA);  "profile": 0|1|2 (see cmc_adi3d_get_timing);
  * read-only: "kernel_x" / "kernel_y" / "kernel_z" (which kernel a sweep along that axis runs: 0 exact Thomas kernels,
  * 1 direct-load partition kernel, 2 cp.async ring kernel, 3 TMA-staged tile kernel, 4 slab-coupled x-sweep),
  * "nzp" (padded z-line length), "jb" (rows per y-block of the field storage, 0 = one block), "exchange" (how slabs exchange planes and interface systems: 0 single slab,

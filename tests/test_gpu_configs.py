@@ -98,7 +98,8 @@ def _compare_with_golden(name, got, exact):
             # identical fields => identical host-side sums (same accumulation code) and identical samples
             assert np.array_equal(ref_s, got_s), f"{name} step {step}: exact mode differs from the reference"
             assert np.array_equal(z["sums"][si], got["sums"][si]) and np.array_equal(z["sumsq"][si], got["sumsq"][si])
-            assert abs(got["err"][si] - z["err"][si]) <= 1e-12 * abs(z["err"][si])
+            # the residual is a sum over all cells (serial on the CPU, a block reduction on the device)
+            assert abs(got["err"][si] - z["err"][si]) <= 1e-10 * abs(z["err"][si])
         else:
             assert_fields_close(list(ref_s), list(got_s), fp, f"{name} step {step} (strided subsample)")
             tol = TOL[fp]
