@@ -143,6 +143,29 @@ def channel_case(dimx, dimy, dimz, fp_bytes=8, baffle=True, depth_var=0.2, h=Non
                 vx=vx.ravel(), vy=zero, vz=zero.copy(), T=T.ravel(), baseT=baseT)
 
 
+def moving_baffle_case(dimx, dimy, dimz, fp_bytes=8, shift=0, **kw) -> Case:
+    """The masked channel with its wall-attached baffle displaced by `shift` cells along x: successive shifts are the
+    node arrays a moving-boundary case hands to the solver step after step (Grid3D::Prepare(t), reference
+    src/FluidSolver3D/Grid3D.cpp:900-945).  Cells the baffle leaves become fluid (NODE_IN), cells it enters become
+    NODE_OUT / NODE_BOUND."""
+    base = channel_case(dimx, dimy, dimz, fp_bytes=fp_bytes, baffle=False, **kw)
+    shp = base.shape
+    t = base.type.reshape(shp); bv = base.bc_vel.reshape(shp); bt = base.bc_temp.reshape(shp)
+    vx = base.vx.reshape(shp); T = base.T.reshape(shp)
+    i0, i1 = int(0.3 * dimx) + shift, int(0.45 * dimx) + shift
+    j1 = max(4, int(0.35 * dimy))
+    assert i1 < dimx - 3
+    fluid_col = (t[i0:i1 + 1, 2:j1 + 1, :] == NODE_IN)                      # fluid cells the baffle covers
+    blk = np.zeros(shp, bool); blk[i0:i1 + 1, 2:j1 + 1, :] = True
+    inner = np.zeros(shp, bool); inner[i0 + 1:i1, 2:j1, :] = True
+    sel = blk & (t == NODE_IN)
+    t[sel & inner] = NODE_OUT
+    shell = sel & ~inner
+    t[shell] = NODE_BOUND; bt[shell] = BC_FREE; T[shell] = base.baseT; vx[shell] = 0
+    del fluid_col
+    return base
+
+
 # ---- case files in the reference's formats ---------------------------------------------------------------
 BOX_OUTLINE = [  # unit box channel: two passive walls, inflow valve (1 m/s), free outflow valve
     ("Passive", [(0, 0), (1000, 0)], None),

@@ -19,6 +19,8 @@
 #include <string>
 #include <vector>
 #include <new>
+#include <thread>
+#include <atomic>
 
 #include "../../include/cmc_adi.h"
 #include "kernels.h"
@@ -48,7 +50,7 @@ static int fail(int code, const std::string &msg)
 struct cmc_adi3d {
 	virtual ~cmc_adi3d() {}
 	virtual int set_nodes(const int32_t *type, const int32_t *bc_vel, const int32_t *bc_temp,
-	                      const void *vx, const void *vy, const void *vz, const void *T, size_t aos_stride) = 0;
+	                      const void *vx, const void *vy, const void *vz, const void *T, size_t aos_stride, bool keep_layers) = 0;
 	virtual int build_lines() = 0;
 	virtual int update_boundaries() = 0;
 	virtual int time_step(double dt, int ng, int nl, int ce, double *err, bool async) = 0;
@@ -117,6 +119,23 @@ namespace {
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// host loops over all cells of the grid (node packing): chunks of the index range on all hardware threads
+template <typename F>
+static void parallel_for(size_t n, F body)
+{
+	unsigned nt = std::thread::hardware_concurrency();
+	if (nt > 32) nt = 32;
+	if (nt < 2 || n < (1u << 20)) { body(0, n); return; }
+	std::vector<std::thread> pool;
+	const size_t chunk = (n + nt - 1) / nt;
+	for (unsigned t = 0; t < nt; t++) {
+		const size_t a = t * chunk, b = std::min(n, a + chunk);
+		if (a >= b) break;
+		pool.emplace_back([=] { body(a, b); });
+	}
+	for (auto &th : pool) th.join();
+}
+
 // GPUplan::splitEven1D (reference GPUplan.cpp:122-141): dimx / n planes each, remainder spread over the first slabs
 static void split_even(int dimx, int n, int r, int &x0, int &nx)
 {
@@ -141,6 +160,7 @@ struct Slab {
 	FT *cv = nullptr, *cT = nullptr;
 	double *d_partials = nullptr, *d_err2 = nullptr, *d_sums8 = nullptr;
 	unsigned long long *d_segcount = nullptr;
+	int *d_tilectr = nullptr;      // tile counter of the persistent sweep kernels
 	FT *d_outvel = nullptr;
 	double *d_outT = nullptr;
 	size_t out_cap = 0;
@@ -161,7 +181,7 @@ struct Slab {
 		if (arena) cudaFree(arena);
 		for (auto &p : nodev) if (p) cudaFree(p);
 		for (auto &p : role) if (p) cudaFree(p);
-		void *misc[] = {cv, cT, d_partials, d_err2, d_sums8, d_segcount, d_outvel, d_outT, ncode, xcoef_send, xbnd_send};
+		void *misc[] = {cv, cT, d_partials, d_err2, d_sums8, d_segcount, d_tilectr, d_outvel, d_outT, ncode, xcoef_send, xbnd_send};
 		for (void *p : misc) if (p) cudaFree(p);
 	}
 
@@ -203,6 +223,7 @@ struct Slab {
 		if ((rc = dalloc(d_err2, 2))) return rc;
 		if ((rc = dalloc(d_sums8, 8))) return rc;
 		if ((rc = dalloc(d_segcount, 8))) return rc;
+		if ((rc = dalloc(d_tilectr, 32))) return rc;
 		if (nslabs > 1) {
 			const size_t lpo = lines_per_owner(nslabs);
 			if ((rc = dalloc(xcoef_send, lpo * 16 * nslabs))) return rc;
@@ -246,7 +267,7 @@ struct Slab {
 	}
 
 	// dense host (whole grid) -> padded device slab, plus the neighbour planes into the guard (halo) planes
-	int upload_nodes(const uint8_t *code, size_t N, const FT *const src[4])
+	int upload_nodes(const uint8_t *code, size_t N, const FT *const src[4], bool keep_layers)
 	{
 		if (ncode) { cudaFree(ncode); ncode = nullptr; }
 		CU_TRY(cudaMalloc((void **)&ncode, N));
@@ -257,6 +278,7 @@ struct Slab {
 			int rc = copy_planes(nodev[q], src[q], nullptr, p0, p1, 0);
 			if (rc) return rc;
 		}
+		if (keep_layers) return CMC_OK;        // Grid3D::Prepare(t): new nodes, same time layers
 		// cur = TimeLayer3D(grid) (TimeLayer3D.h:734-751); half/next/temp are uninitialised in the reference
 		// (TimeLayer3D.h:353) and are defined here as copies of cur.
 		for (int l = 0; l < 5; l++)
@@ -456,8 +478,9 @@ struct Engine : cmc_adi3d {
 
 	// ------------------------------------------------------------------------------------------- set up
 	int set_nodes(const int32_t *type, const int32_t *bc_vel, const int32_t *bc_temp,
-	              const void *vx, const void *vy, const void *vz, const void *T, size_t aos_stride) override
+	              const void *vx, const void *vy, const void *vz, const void *T, size_t aos_stride, bool keep_layers) override
 	{
+		if (keep_layers && !have_nodes) return fail(CMC_ERR_INVALID, "update_nodes: call cmc_adi3d_set_nodes first");
 		CU_TRY(cudaSetDevice(device));
 		const size_t N = (size_t)G.nx * G.ny * G.nz;
 		std::vector<uint8_t> code(N);
@@ -467,32 +490,43 @@ struct Engine : cmc_adi3d {
 			// reference Node (Grid3D.h:73-88): {int type; int bc_vel; int bc_temp; FTYPE v[3]; FTYPE T}
 			const char *base = (const char *)type;
 			for (int q = 0; q < 4; q++) tmp[q].resize(N);
-			for (size_t id = 0; id < N; id++) {
-				const int32_t *hd = (const int32_t *)(base + id * aos_stride);
-				const FT *fv = (const FT *)(base + id * aos_stride + (sizeof(FT) == 8 ? 16 : 12));
-				if (hd[0] < 0 || hd[0] > 3) return fail(CMC_ERR_INVALID, "set_nodes_aos: node type out of range");
-				if ((hd[1] != CMC_BC_NOSLIP && hd[1] != CMC_BC_FREE) || (hd[2] != CMC_BC_NOSLIP && hd[2] != CMC_BC_FREE))
-					return fail(CMC_ERR_INVALID, "set_nodes_aos: boundary-condition type out of range");
-				code[id] = (uint8_t)((hd[0] & 3) | (hd[1] == CMC_BC_FREE ? 4 : 0) | (hd[2] == CMC_BC_FREE ? 8 : 0));
-				tmp[0][id] = fv[0]; tmp[1][id] = fv[1]; tmp[2][id] = fv[2]; tmp[3][id] = fv[3];
-			}
+			FT *t0 = tmp[0].data(), *t1 = tmp[1].data(), *t2 = tmp[2].data(), *t3 = tmp[3].data();
+			uint8_t *cd = code.data();
+			std::atomic<int> bad(0);
+			parallel_for(N, [&](size_t a, size_t b) {
+				for (size_t id = a; id < b; id++) {
+					const int32_t *hd = (const int32_t *)(base + id * aos_stride);
+					const FT *fv = (const FT *)(base + id * aos_stride + (sizeof(FT) == 8 ? 16 : 12));
+					if (hd[0] < 0 || hd[0] > 3) bad = 1;
+					if ((hd[1] != CMC_BC_NOSLIP && hd[1] != CMC_BC_FREE) || (hd[2] != CMC_BC_NOSLIP && hd[2] != CMC_BC_FREE)) bad = 2;
+					cd[id] = (uint8_t)((hd[0] & 3) | (hd[1] == CMC_BC_FREE ? 4 : 0) | (hd[2] == CMC_BC_FREE ? 8 : 0));
+					t0[id] = fv[0]; t1[id] = fv[1]; t2[id] = fv[2]; t3[id] = fv[3];
+				}
+			});
+			if (bad == 1) return fail(CMC_ERR_INVALID, "set_nodes_aos: node type out of range");
+			if (bad == 2) return fail(CMC_ERR_INVALID, "set_nodes_aos: boundary-condition type out of range");
 			for (int q = 0; q < 4; q++) src[q] = tmp[q].data();
 		} else {
-			for (size_t id = 0; id < N; id++) {
-				if (type[id] < 0 || type[id] > 3) return fail(CMC_ERR_INVALID, "set_nodes: node type out of range");
-				if ((bc_vel[id] != CMC_BC_NOSLIP && bc_vel[id] != CMC_BC_FREE) || (bc_temp[id] != CMC_BC_NOSLIP && bc_temp[id] != CMC_BC_FREE))
-					return fail(CMC_ERR_INVALID, "set_nodes: boundary-condition type out of range");
-				code[id] = (uint8_t)((type[id] & 3) | (bc_vel[id] == CMC_BC_FREE ? 4 : 0) | (bc_temp[id] == CMC_BC_FREE ? 8 : 0));
-			}
+			uint8_t *cd = code.data();
+			std::atomic<int> bad(0);
+			parallel_for(N, [&](size_t a, size_t b) {
+				for (size_t id = a; id < b; id++) {
+					if (type[id] < 0 || type[id] > 3) bad = 1;
+					if ((bc_vel[id] != CMC_BC_NOSLIP && bc_vel[id] != CMC_BC_FREE) || (bc_temp[id] != CMC_BC_NOSLIP && bc_temp[id] != CMC_BC_FREE)) bad = 2;
+					cd[id] = (uint8_t)((type[id] & 3) | (bc_vel[id] == CMC_BC_FREE ? 4 : 0) | (bc_temp[id] == CMC_BC_FREE ? 8 : 0));
+				}
+			});
+			if (bad == 1) return fail(CMC_ERR_INVALID, "set_nodes: node type out of range");
+			if (bad == 2) return fail(CMC_ERR_INVALID, "set_nodes: boundary-condition type out of range");
 		}
 		for (auto *s : slabs) {
-			int rc = s->upload_nodes(code.data(), N, src);
+			int rc = s->upload_nodes(code.data(), N, src, keep_layers);
 			if (rc) return rc;
 		}
 		CU_TRY(cudaStreamSynchronize(stream));
 		halos_dirty = true;
 		have_nodes = true; have_lines = false;
-		diffError = 0.0; err_pending = 0; worst_err = 0.0;
+		if (!keep_layers) { diffError = 0.0; err_pending = 0; worst_err = 0.0; }
 		return CMC_OK;
 	}
 
@@ -570,6 +604,7 @@ struct Engine : cmc_adi3d {
 		A.cv = s->cv; A.cT = s->cT;
 		A.xcoef = s->xcoef_send; A.xbnd = s->xbnd_recv; A.lpo = (int)s->lines_per_owner(nslabs_total);
 		A.extra_merge = 0;
+		A.tile_counter = s->d_tilectr;
 		for (int q = 0; q < 4; q++) A.push_lo[q] = A.push_hi[q] = A.pushn_lo[q] = A.pushn_hi[q] = nullptr;
 		for (int r = 0; r < MAX_SLABS; r++) A.xcoef_to[r] = nullptr;
 		if (multi()) {
@@ -687,6 +722,17 @@ struct Engine : cmc_adi3d {
 				else {
 					launch_exact_sweep<FT>(dir, A, stream, &launches);
 					launch_merge<FT>(s->L, s->role[dir], s->clayer(next_layer), s->layer(CMC_LAYER_TEMP), stream, &launches);
+				}
+			}
+			{   // debug facility: CMC_DEBUG_SYNC=1 synchronises after every sweep and reports the kernel that faulted
+				static const bool dbg = getenv("CMC_DEBUG_SYNC") != nullptr;
+				if (dbg) {
+					const cudaError_t e = cudaStreamSynchronize(stream);
+					if (e != cudaSuccess) {
+						char buf[160];
+						snprintf(buf, sizeof buf, "sweep along %c (kernel kind %d, local iteration %d) failed: %s", "xyz"[dir], kernel_kind(dir), it, cudaGetErrorString(e));
+						return fail(CMC_ERR_CUDA, buf);
+					}
 				}
 			}
 			// (after ALL slabs are launched: the push targets above are computed from the neighbours' buffer roles)
@@ -1123,7 +1169,23 @@ int cmc_adi3d_set_nodes(cmc_adi3d *h, const int32_t *type, const int32_t *bc_vel
 {
 	H_CHECK(h);
 	if (!type || !bc_vel || !bc_temp || !vx || !vy || !vz || !T) return fail(CMC_ERR_INVALID, "set_nodes: null array");
-	return h->set_nodes(type, bc_vel, bc_temp, vx, vy, vz, T, 0);
+	return h->set_nodes(type, bc_vel, bc_temp, vx, vy, vz, T, 0, false);
+}
+
+int cmc_adi3d_update_nodes(cmc_adi3d *h, const int32_t *type, const int32_t *bc_vel, const int32_t *bc_temp,
+                           const void *vx, const void *vy, const void *vz, const void *T)
+{
+	H_CHECK(h);
+	if (!type || !bc_vel || !bc_temp || !vx || !vy || !vz || !T) return fail(CMC_ERR_INVALID, "update_nodes: null array");
+	return h->set_nodes(type, bc_vel, bc_temp, vx, vy, vz, T, 0, true);
+}
+
+int cmc_adi3d_update_nodes_aos(cmc_adi3d *h, const void *nodes, size_t stride)
+{
+	H_CHECK(h);
+	if (!nodes) return fail(CMC_ERR_INVALID, "update_nodes_aos: null array");
+	if (stride < (size_t)((h->fp == 8 ? 16 : 12) + 4 * h->fp)) return fail(CMC_ERR_INVALID, "update_nodes_aos: stride smaller than a Node");
+	return h->set_nodes((const int32_t *)nodes, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stride, true);
 }
 
 int cmc_adi3d_set_nodes_aos(cmc_adi3d *h, const void *nodes, size_t stride)
@@ -1131,7 +1193,7 @@ int cmc_adi3d_set_nodes_aos(cmc_adi3d *h, const void *nodes, size_t stride)
 	H_CHECK(h);
 	if (!nodes) return fail(CMC_ERR_INVALID, "set_nodes_aos: null array");
 	if (stride < (size_t)((h->fp == 8 ? 16 : 12) + 4 * h->fp)) return fail(CMC_ERR_INVALID, "set_nodes_aos: stride smaller than a Node");
-	return h->set_nodes((const int32_t *)nodes, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stride);
+	return h->set_nodes((const int32_t *)nodes, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stride, false);
 }
 
 int cmc_adi3d_build_lines(cmc_adi3d *h) { H_CHECK(h); return h->build_lines(); }

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 64 && DIR == 2 && GP == 6
 		const int rc = min(r0, L.nzp - M);
 #pragma unroll
 		for (int i = 0; i < M; i++) off[i] = (int)base + rc + i;
-		off_lo = (int)base + max(r0 - 1, 0);
+		off_lo = (int)base + max(min(r0 - 1, n - 1), 0);
 		off_hi = (int)base + min(r0 + M, n - 1);
 	} else {
 		// (a chunk never straddles a y-block: one block offset per chunk, rows nzp apart inside it)
@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 64 && DIR == 2 && GP == 6
 #pragma unroll
 		for (int i = 0; i < M; i++) off[i] = off0 + min(i, rmax) * (int)stride;
 		// rows -1 and n exist for a slab inside a decomposed grid (halo planes): its first / last row can be interior
-		off_lo = (int)base + rowoff(max(r0 - 1, MODE != 0 ? -1 : 0));
+		// (padding chunks - r0 past the end of the line - must stay inside the buffer too: along x a row is a whole plane)
+		off_lo = (int)base + rowoff(max(min(r0 - 1, n - 1), MODE != 0 ? -1 : 0));
 		off_hi = (int)base + rowoff(min(r0 + M, MODE != 0 ? n : n - 1));
 	}
 	// ptxas schedules inside basic blocks only.  These never-taken branches (`one` is always 1) split the kernel where

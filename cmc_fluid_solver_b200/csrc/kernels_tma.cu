@@ -148,6 +148,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 		}
 	}
 }
+// Orders this thread's earlier shared-memory reads (generic proxy) before bulk copies (async proxy) that are issued after
+// the next barrier and overwrite the same slot.  __syncthreads() alone orders the threads among themselves, not against
+// the copy engine: a shared-memory load that is still queued in the load/store unit when the barrier resolves can be
+// overtaken by the incoming copy (seen as one corrupted tile in ~10^5 with two CTAs per SM; PTX memory model, proxies).
+__device__ __forceinline__ void slot_reads_done() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, int c2, int c3, int c4)
 {
 	asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
@@ -155,10 +161,46 @@ __device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, u
 	             "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d_hint(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, int c2, int c3, int c4,
+                                                 unsigned long long policy)
+{
+	asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+	             ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)),
+	             "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy) : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_evict_first()
+{
+	unsigned long long p;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+__device__ __forceinline__ unsigned long long l2_evict_last()
+{
+	unsigned long long p;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+
+// result stores: written once, read again only by the next sweep (17 GB later at 512^3): streaming (L2 evict-first), so
+// that they do not push the temp tiles that neighbouring tiles are about to re-read out of L2
+template <typename FT>
+__device__ __forceinline__ void store8_stream(FT *__restrict__ p, const int (&off)[M], unsigned mask, const FT (&v)[M], int streaming)
+{
+	if (streaming) {
+#pragma unroll
+		for (int i = 0; i < M; i++)
+			if (mask & (1u << i)) __stcs(p + off[i], v[i]);
+	} else {
+#pragma unroll
+		for (int i = 0; i < M; i++)
+			if (mask & (1u << i)) p[off[i]] = v[i];
+	}
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------------------------------
 template <typename FT, int DIR, int GP>
 __global__ void __launch_bounds__(GP * 8, GP >= 64 ? 1 : 2)
-k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant__ TmaMaps TM, const int ntiles)
+k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant__ TmaMaps TM, const int ntiles, const int hints)
 {
 	static_assert(DIR == 0 || DIR == 1, "strided axes only (z lines are contiguous: kernels_fast.cu)");
 	constexpr int NL = 8;
@@ -176,6 +218,7 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 	FT *headx = sys + reduced_scratch_elems<3, GP, NL>();                           // heads that cross a warp: 5 x (NW * 8)
 	uint8_t *roles = reinterpret_cast<uint8_t *>(headx + 5 * NW * 8);               // descriptor bytes of the tile: 8 * STR
 	unsigned long long *full = reinterpret_cast<unsigned long long *>(roles + 8 * STR);   // 6 mbarriers
+	int *next_box = reinterpret_cast<int *>(full + 6);                                    // the tile after the current one
 #define SLOTP(k) (slots + (k) * SLOT)
 
 	const Layout &L = A.L;
@@ -199,22 +242,28 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 	unsigned ph = 0;                                // phase parity of every slot's mbarrier
 #define WAIT_SLOT(s) do { mbar_wait(full + (s), (ph >> (s)) & 1u); ph ^= 1u << (s); } while (0)
 
+	// L2 policies (hints bit 0): the `cur` fields are read exactly once per sweep -> evict-first; the temp fields are
+	// read again within a tile time (the cross-line neighbours of the adjacent tiles, the second copy of temp.T) -> evict-last
+	const unsigned long long pol_once = l2_evict_first(), pol_keep = l2_evict_last();
+	const int streaming = hints & 2;               // hints bit 1: streaming result stores
 	// box coordinates of (field tile, cross-line shift dj) of a tile
-	auto issue = [&](int s, const CUtensorMap *map, int tile, int shift) {
+	auto issue = [&](int s, const CUtensorMap *map, int tile, int shift, int keep) {
 		const int a = tile / ktiles, k0 = (tile - a * ktiles) * NL;       // a = j (x lines) or i (y lines)
 		mbar_expect_tx(full + s, SLOT_BYTES);
+		int c3, c4;
 		if (DIR == 0) {
 			const int j = min(max(a + shift, 0), L.ny - 1);
-			tma_load_5d(SLOTP(s), map, full + s, k0, 0, 0, j & L.jbm, j >> L.jbs);
-		} else
-			tma_load_5d(SLOTP(s), map, full + s, k0, 0, 0, 0, a + 1 + shift);
+			c3 = j & L.jbm; c4 = j >> L.jbs;
+		} else { c3 = 0; c4 = a + 1 + shift; }
+		if (hints & 1) tma_load_5d_hint(SLOTP(s), map, full + s, k0, 0, 0, c3, c4, keep ? pol_keep : pol_once);
+		else tma_load_5d(SLOTP(s), map, full + s, k0, 0, 0, c3, c4);
 	};
 	auto issue_A = [&](int tile) {                 // u,v,w phase inputs
-		issue(0, &TM.temp[DIR], tile, 0);
-		issue(1, &TM.temp[3], tile, 0);
-		issue(2, &TM.cur[0], tile, 0);
-		issue(3, &TM.cur[1], tile, 0);
-		issue(4, &TM.cur[2], tile, 0);
+		issue(0, &TM.temp[DIR], tile, 0, 1);
+		issue(1, &TM.temp[3], tile, 0, 1);
+		issue(2, &TM.cur[0], tile, 0, 0);
+		issue(3, &TM.cur[1], tile, 0, 0);
+		issue(4, &TM.cur[2], tile, 0, 0);
 	};
 	// descriptor bytes: 8 per tile row, thread <-> tile row
 	auto issue_roles = [&](int tile) {
@@ -225,14 +274,20 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 		cp_async_commit();
 	};
 
+	// Tiles are handed out dynamically (the first gridDim.x statically, then in index order through an atomic counter):
+	// SMs that run a little faster take more tiles, and - what matters for HBM traffic - tiles that are neighbours in
+	// memory (adjacent k-tiles share their 128-byte lines, adjacent rows are each other's cross-line neighbours) are in
+	// flight at about the same time on different SMs, so the second request for a line finds it in L2.  With a static
+	// stride the CTAs drift apart and every line is fetched from HBM twice (ncu: 15.5 GB read against 8.7 algorithmic).
 	int tile = blockIdx.x;
 	if (tile < ntiles) {
-		if (t == 0) { issue_A(tile); issue(5, &TM.cur[3], tile, 0); }
+		if (t == 0) { issue_A(tile); issue(5, &TM.cur[3], tile, 0, 0); }
 		issue_roles(tile);
 	}
 
-	for (; tile < ntiles; tile += gridDim.x) {
-		const int next_tile = tile + (int)gridDim.x;
+	while (tile < ntiles) {
+		if (t == 0) *next_box = (int)gridDim.x + atomicAdd(A.tile_counter, 1);
+		// (read after the first barrier of the iteration; next_box is rewritten only after the last barrier of it)
 		const int a = tile / ktiles, k0 = (tile - a * ktiles) * NL;
 		const int k = k0 + l;
 		const bool line_ok = k < L.nz;
@@ -253,6 +308,7 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 		cp_async_wait_all();
 		WAIT_SLOT(0); WAIT_SLOT(1); WAIT_SLOT(2); WAIT_SLOT(3); WAIT_SLOT(4);
 		__syncthreads();            // roles (cp.async of every thread) have landed
+		const int next_tile = *next_box;
 
 		unsigned rw0 = 0, rw1 = 0;
 #pragma unroll
@@ -287,12 +343,42 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 				dp[2][i] = SLOTP(4)[i * STR + e];
 			}
 			const FT Tlo = SLOTP(1)[e_lo], Thi = SLOTP(1)[e_hi];
+#ifdef CMC_TMA_DEBUG
+			// debug build: what the copies delivered against plain global loads of the same cells
+			if (rowmask) {
+				int bad = 0, badslot = -1, badrow = -1;
+#pragma unroll
+				for (int i = 0; i < M; i++) {
+					if (V[i] != A.temp[DIR][off[i]]) { bad++; badslot = 0; badrow = r0 + i; }
+					if (Tl[i] != A.temp[3][off[i]]) { bad++; badslot = 1; badrow = r0 + i; }
+					if (dp[0][i] != A.cur[0][off[i]]) { bad++; badslot = 2; badrow = r0 + i; }
+					if (dp[1][i] != A.cur[1][off[i]]) { bad++; badslot = 3; badrow = r0 + i; }
+					if (dp[2][i] != A.cur[2][off[i]]) { bad++; badslot = 4; badrow = r0 + i; }
+				}
+				if (bad) {
+					const int old = atomicAdd(A.tile_counter + 1, bad);
+					// look again a little later: has the data arrived meanwhile?
+					const long long t0 = clock64();
+					while (clock64() - t0 < 20000) { }
+					int still = 0;
+#pragma unroll
+					for (int i = 0; i < M; i++) {
+						const FT *sq = badslot == 0 ? SLOTP(0) : badslot == 1 ? SLOTP(1) : badslot == 2 ? SLOTP(2) : badslot == 3 ? SLOTP(3) : SLOTP(4);
+						const FT *gq = badslot == 0 ? A.temp[DIR] : badslot == 1 ? A.temp[3] : A.cur[badslot - 2];
+						if (sq[i * STR + e] != gq[off[i]]) still++;
+					}
+					if (old == 0) printf("[tma debug] tile %d (a %d k0 %d) thread %d (g %d l %d): %d mismatches, last in slot %d row %d; %d still differ 20k cycles later; ph %x\n",
+					                     tile, a, k0, t, g, l, bad, badslot, badrow, still, ph);
+				}
+			}
+#endif
+			slot_reads_done();
 			__syncthreads();        // every thread has its inputs in registers: slots 1-4 are free (slot 0 stays)
 			if (t == 0) {
-				issue(1, &TM.temp[QO1], tile, 0);
-				issue(2, &TM.temp[QO2], tile, 0);
-				issue(3, &TM.temp[DIR], tile, -1);
-				issue(4, &TM.temp[DIR], tile, +1);
+				issue(1, &TM.temp[QO1], tile, 0, 1);
+				issue(2, &TM.temp[QO2], tile, 0, 1);
+				issue(3, &TM.temp[DIR], tile, -1, 1);
+				issue(4, &TM.temp[DIR], tile, +1, 1);
 			}
 #pragma unroll
 			for (int i = 0; i < M; i++) {
@@ -386,8 +472,8 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 					if (holes & (1u << i)) x[i] = A.next[q][off[i]];
 			}
 			relax8<FT, DIR>(tq, x, inmask, A.extra_merge);
-			store8<FT, DIR>(A.temp_out[q], off, full_m, tq);
-			store8<FT, DIR>(A.next[q], off, segfull, x);
+			store8_stream<FT>(A.temp_out[q], off, full_m, tq, streaming);
+			store8_stream<FT>(A.next[q], off, segfull, x, streaming);
 			push_planes<FT, DIR, 0>(A, q, a, g, GP, off, full_m, segfull, tq, x);
 		}
 
@@ -455,9 +541,10 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 			WAIT_SLOT(5);
 #pragma unroll
 			for (int i = 0; i < M; i++) cT[i] = SLOTP(5)[i * STR + e];
+			slot_reads_done();
 			__syncthreads();        // every slot has been consumed
 			if (t == 0) {
-				issue(5, &TM.temp[3], tile, 0);
+				issue(5, &TM.temp[3], tile, 0, 0);       // last use of this tile's temp.T
 				if (next_tile < ntiles) issue_A(next_tile);
 			}
 			if (next_tile < ntiles) issue_roles(next_tile);
@@ -508,18 +595,20 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 			WAIT_SLOT(5);
 #pragma unroll
 			for (int i = 0; i < M; i++) tq[i] = SLOTP(5)[i * STR + e];
+			slot_reads_done();
 			__syncthreads();        // slot 5 consumed (and sol / headx are free for the next tile)
-			if (t == 0 && next_tile < ntiles) issue(5, &TM.cur[3], next_tile, 0);
+			if (t == 0 && next_tile < ntiles) issue(5, &TM.cur[3], next_tile, 0, 0);
 			if (holes) {
 #pragma unroll
 				for (int i = 0; i < M; i++)
 					if (holes & (1u << i)) x[i] = A.next[3][off[i]];
 			}
 			relax8<FT, DIR>(tq, x, inmask, A.extra_merge);
-			store8<FT, DIR>(A.temp_out[3], off, full_m, tq);
-			store8<FT, DIR>(A.next[3], off, segfull, x);
+			store8_stream<FT>(A.temp_out[3], off, full_m, tq, streaming);
+			store8_stream<FT>(A.next[3], off, segfull, x, streaming);
 			push_planes<FT, DIR, 0>(A, 3, a, g, GP, off, full_m, segfull, tq, x);
 		}
+		tile = next_tile;
 	}
 	cp_async_wait_all();
 #undef ROLE
@@ -532,7 +621,7 @@ template <typename FT, int GP>
 static size_t tma_smem_bytes()
 {
 	const size_t STR = (size_t)GP * 8;
-	return sizeof(FT) * (6 * STR * M + reduced_scratch_elems<3, GP, 8>() + 5 * (STR / 32) * 8) + 8 * STR + 6 * sizeof(unsigned long long);
+	return sizeof(FT) * (6 * STR * M + reduced_scratch_elems<3, GP, 8>() + 5 * (STR / 32) * 8) + 8 * STR + 6 * sizeof(unsigned long long) + 16;
 }
 
 bool tma_sweep_supported(const Layout &L, int dir)
@@ -566,10 +655,14 @@ static bool launch_tma_one(const SweepArgs<FT> &A, cudaStream_t s)
 		int per_sm = 0, sms = 0;
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tma_sweep<FT, DIR, GP>, GP * 8, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return false; }
+		if (getenv("CMC_TMA_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("CMC_TMA_CTAS"))));    // (experiments)
 		ctas_of[dev] = per_sm * sms;
 	}
 	FastConst<FT> K; K.init(A, DIR);
-	k_tma_sweep<FT, DIR, GP><<<std::min(ctas_of[dev], ntiles), GP * 8, smem, s>>>(A, K, TM, ntiles);
+	// CMC_TMA_HINTS: bit 0 = L2 eviction hints on the bulk copies, bit 1 = streaming result stores (measured: neither helps)
+	static const int hints = getenv("CMC_TMA_HINTS") ? atoi(getenv("CMC_TMA_HINTS")) : 0;
+	if (!A.tile_counter || cudaMemsetAsync(A.tile_counter, 0, sizeof(int), s) != cudaSuccess) return false;
+	k_tma_sweep<FT, DIR, GP><<<std::min(ctas_of[dev], ntiles), GP * 8, smem, s>>>(A, K, TM, ntiles, hints);
 	return true;
 }
 

@@ -96,6 +96,15 @@ class AdiSolver3D:
         _check(lib.cmc_adi3d_set_nodes(h, *[_ptr(a) for a in arr_i], *[_ptr(a) for a in arr_f]))
         return self
 
+    def UpdateNodes(self, case: Case):
+        """Grid3D::Prepare(t): new node types / boundary kinds / boundary values, time layers untouched.  Rebuilds the line
+        descriptors on the device (the 2D solver's per-step CreateSegments, AdiSolver2D.cpp:279-283)."""
+        arr_i = [np.ascontiguousarray(a, dtype=np.int32) for a in (case.type, case.bc_vel, case.bc_temp)]
+        arr_f = [np.ascontiguousarray(a, dtype=self.ft) for a in (case.vx, case.vy, case.vz, case.T)]
+        _check(load_library().cmc_adi3d_update_nodes(self._h, *[_ptr(a) for a in arr_i], *[_ptr(a) for a in arr_f]))
+        self.case = case
+        self.CreateSegments()
+
     def set_mode(self, mode):
         m = {"fast": MODE_FAST, "exact": MODE_EXACT}[mode] if isinstance(mode, str) else int(mode)
         _check(load_library().cmc_adi3d_set_option(self._h, b"mode", m))

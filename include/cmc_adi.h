@@ -106,6 +106,14 @@ int cmc_adi3d_set_nodes(cmc_adi3d *h, const int32_t *type, const int32_t *bc_vel
  * (28 bytes in the fp32 build; 48 in fp64, where the FTYPE members start at offset 16) */
 int cmc_adi3d_set_nodes_aos(cmc_adi3d *h, const void *nodes, size_t node_stride_bytes);
 
+/* ---- moving boundaries: Grid3D::Prepare(t) (Grid3D.cpp:900-945, ComputeSubframeInfo; the driver's hook is
+ * FluidSolver3D.cpp:237) rewrites the Node[] array between steps - types, boundary kinds and boundary values - and the
+ * solver keeps its time layers.  Same arrays as cmc_adi3d_set_nodes / _aos; the layers are NOT touched.  Call
+ * cmc_adi3d_build_lines afterwards: the line descriptors are rebuilt on the device (a scan per grid line, < 1 % of a step). */
+int cmc_adi3d_update_nodes(cmc_adi3d *h, const int32_t *type, const int32_t *bc_vel, const int32_t *bc_temp,
+                           const void *vx, const void *vy, const void *vz, const void *T);
+int cmc_adi3d_update_nodes_aos(cmc_adi3d *h, const void *nodes, size_t node_stride_bytes);
+
 /* ---- AdiSolver3D::CreateSegments (AdiSolver3D.cpp:553-562; Grid3D::GenerateListSegments, Grid3D.cpp:47-127):
  * builds the per-direction line descriptors (segment roles + boundary rows) on the device. */
 int cmc_adi3d_build_lines(cmc_adi3d *h);

@@ -360,6 +360,20 @@ void *FN(oracle3d_create)(int dimx, int dimy, int dimz, double dx, double dy, do
 	return o;
 }
 
+/* Moving boundaries: Grid3D::Prepare(t) (Grid3D.cpp:900-945, ComputeSubframeInfo) rewrites the Node[] array between steps
+ * and the solver reads it through its grid pointer; the time layers are left as they are.  The segment lists must be
+ * rebuilt afterwards (create_segments): the 2D solver does so inside every TimeStep (AdiSolver2D.cpp:279-283), the 3D
+ * driver has the Prepare call commented out (FluidSolver3D.cpp:237). */
+void FN(oracle3d_update_nodes)(void *h, const int *type, const int *bc_vel, const int *bc_temp,
+                               const FT *vx, const FT *vy, const FT *vz, const FT *T)
+{
+	Oracle *o = (Oracle *)h;
+	const size_t N = (size_t)o->dimx * o->dimy * o->dimz;
+	memcpy(o->type, type, N * 4); memcpy(o->bc_vel, bc_vel, N * 4); memcpy(o->bc_temp, bc_temp, N * 4);
+	memcpy(o->nvx, vx, N * sizeof(FT)); memcpy(o->nvy, vy, N * sizeof(FT));
+	memcpy(o->nvz, vz, N * sizeof(FT)); memcpy(o->nT, T, N * sizeof(FT));
+}
+
 void FN(oracle3d_destroy)(void *h)
 {
 	Oracle *o = (Oracle *)h;

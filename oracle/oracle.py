@@ -173,6 +173,16 @@ class Oracle3D:
         except Exception:
             pass
 
+    def update_nodes(self, case: Case):
+        """Grid3D::Prepare(t): new Node[] contents, layers untouched; call create_segments() afterwards."""
+        f = self._fn("oracle3d_update_nodes")
+        IP = C.POINTER(C.c_int)
+        f.argtypes = [C.c_void_p] + [IP] * 3 + [self._FP] * 4
+        arrs_i = [np.ascontiguousarray(a, dtype=np.int32) for a in (case.type, case.bc_vel, case.bc_temp)]
+        arrs_f = [np.ascontiguousarray(a, dtype=self.ft) for a in (case.vx, case.vy, case.vz, case.T)]
+        f(self.h, *[a.ctypes.data_as(IP) for a in arrs_i], *[a.ctypes.data_as(self._FP) for a in arrs_f])
+        self.case = case
+
     def create_segments(self):
         f = self._fn("oracle3d_create_segments")
         f.argtypes = [C.c_void_p]

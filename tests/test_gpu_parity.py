@@ -325,3 +325,28 @@ def test_in_node_carrying_free_flags(oracle_mod):
             s.UpdateBoundaries(); s.TimeStep(case.dt, 2, 2, False)
         _check_fields(O, o, s, case, mode, "IN nodes with FREE flags")
         s.close()
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("fp", [8, 4])
+def test_moving_boundary_update_nodes(oracle_mod, mode, fp):
+    """3D dynamic grid (Grid3D::Prepare(t) between steps): a baffle that moves one cell along x per step.  The node arrays
+    are replaced, the time layers are kept, the line descriptors are rebuilt on the device - against the oracle doing the
+    same (update_nodes + create_segments)."""
+    O = oracle_mod
+    from cmc_fluid_solver_b200.cases import moving_baffle_case
+    case = moving_baffle_case(40, 32, 24, fp_bytes=fp, shift=0)
+    ora = O.Oracle3D(case); ora.create_segments()
+    s = AdiSolver3D().Init(case, mode=mode); s.CreateSegments()
+    for step in range(5):
+        if step:
+            case = moving_baffle_case(40, 32, 24, fp_bytes=fp, shift=step)
+            ora.update_nodes(case); ora.create_segments()
+            s.UpdateNodes(case)
+            assert [s.numSegs(d) for d in range(3)] == [len(ora.segments(d)) for d in range(3)]
+        ora.update_boundaries(); s.UpdateBoundaries()
+        e_ref = ora.time_step(case.dt, case.num_global, case.num_local, True)
+        e = s.TimeStep(case.dt, case.num_global, case.num_local, True)
+        assert abs(e - e_ref) <= (1e-5 if fp == 4 else 1e-9) * abs(e_ref)
+        _check_fields(O, ora, s, case, mode, f"moving baffle, step {step}")
+    s.close()

@@ -8,11 +8,12 @@ run() { # label, env...
 import json,sys
 d=json.loads(sys.stdin.readline())
 p=d['roofline']['per_direction']
-print('%-28s x %.3f (%s)  y %.3f (%s)  z %.3f  ms/step %.2f  value %.1f  residual %.6e' % ('$label', p['sweep_x']['ms_per_launch'], d['roofline']['per_direction']['sweep_x'].get('kernel','?'), p['sweep_y']['ms_per_launch'], p['sweep_y'].get('kernel','?'), p['sweep_z']['ms_per_launch'], d['ms_per_step'], d['value'], d['residual']))
+print('%-34s x %.3f (%s)  y %.3f (%s)  z %.3f  ms/step %.2f  value %.1f  residual %.9e' % ('$label', p['sweep_x']['ms_per_launch'], p['sweep_x'].get('kernel','?'), p['sweep_y']['ms_per_launch'], p['sweep_y'].get('kernel','?'), p['sweep_z']['ms_per_launch'], d['ms_per_step'], d['value'], d['residual']))
 " || tail -5 /tmp/bench_err.log
 }
 EXTRA=("$@")
 run "direct (round 1)" CMC_TMA=
-run "tma x" CMC_TMA=x
-run "tma y" CMC_TMA=y
-run "tma xy" CMC_TMA=xy
+run "tma xy, no hints" CMC_TMA=xy CMC_TMA_HINTS=0
+run "tma xy, L2 hints on copies" CMC_TMA=xy CMC_TMA_HINTS=1
+run "tma xy, streaming stores" CMC_TMA=xy CMC_TMA_HINTS=2
+run "tma xy, hints + streaming stores" CMC_TMA=xy CMC_TMA_HINTS=3
