@@ -285,9 +285,13 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 		issue_roles(tile);
 	}
 
+	// (thread 0 asks for the next tile at the top of an iteration and first looks at the answer when it issues that tile's
+	// copies, half a tile later: the latency of the atomic is never waited for; the other threads learn the index behind
+	// the next barrier)
 	while (tile < ntiles) {
-		if (t == 0) *next_box = (int)gridDim.x + atomicAdd(A.tile_counter, 1);
-		// (read after the first barrier of the iteration; next_box is rewritten only after the last barrier of it)
+		int fetched = 0;
+		if (t == 0) fetched = (int)gridDim.x + atomicAdd(A.tile_counter, 1);
+		int next_tile = ntiles;
 		const int a = tile / ktiles, k0 = (tile - a * ktiles) * NL;
 		const int k = k0 + l;
 		const bool line_ok = k < L.nz;
@@ -308,7 +312,6 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 		cp_async_wait_all();
 		WAIT_SLOT(0); WAIT_SLOT(1); WAIT_SLOT(2); WAIT_SLOT(3); WAIT_SLOT(4);
 		__syncthreads();            // roles (cp.async of every thread) have landed
-		const int next_tile = *next_box;
 
 		unsigned rw0 = 0, rw1 = 0;
 #pragma unroll
@@ -489,6 +492,7 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 				FT c1[M], c2[M];
 				{
 					// second cross direction (k +- 1): the neighbouring lines of the tile, the two edge lines from L2 / HBM
+					// (issuing those loads earlier costs more in spills than it hides in latency: measured)
 					FT p2[M], m2[M];
 					if (l == NL - 1) {
 #pragma unroll
@@ -545,9 +549,9 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 			__syncthreads();        // every slot has been consumed
 			if (t == 0) {
 				issue(5, &TM.temp[3], tile, 0, 0);       // last use of this tile's temp.T
-				if (next_tile < ntiles) issue_A(next_tile);
+				if (fetched < ntiles) issue_A(fetched);
+				*next_box = fetched;                     // read by everybody after the next barrier
 			}
-			if (next_tile < ntiles) issue_roles(next_tile);
 #pragma unroll
 			for (int i = 0; i < M; i++) {
 				const unsigned r = ROLE(i);
@@ -581,6 +585,8 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 				headx[0 * (NW * 8) + warp * 8 + lane] = y0; headx[3 * (NW * 8) + warp * 8 + lane] = v0; headx[4 * (NW * 8) + warp * 8 + lane] = w0;
 			}
 			__syncthreads();
+			next_tile = *next_box;
+			if (next_tile < ntiles) issue_roles(next_tile);
 			FT ny0, nv, nw;
 			NEXT_HEAD(ny0, y0, 0); NEXT_HEAD(nv, v0, 3); NEXT_HEAD(nw, w0, 4);
 			const FT a7 = lp[M - 1], c7 = cp[M - 1];

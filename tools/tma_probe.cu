@@ -1,0 +1,139 @@
+// tma_probe.cu - micro-benchmark: how fast can persistent CTAs pull x / y sweep tiles out of HBM with bulk-tensor copies?
+// Same tensor maps and box shapes as kernels_tma.cu (5-D boxes that gather 64-byte row segments), no arithmetic: every
+// CTA keeps NSLOT copies in flight round-robin over 8 "fields" and hands tiles out with an atomic counter.
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o build/tma_probe tools/tma_probe.cu
+//   build/tma_probe            # prints GB/s for (x | y) x (64-byte | 128-byte rows) x (slots in flight)
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Maps { CUtensorMap m[8]; };
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int NSLOT>
+__global__ void __launch_bounds__(128, 1) k_probe(const __grid_constant__ Maps TM, int ntiles, int ktiles, int dir, int kw, int *counter, int slot_bytes,
+                                                 int jbm, int jbs, long long *sink)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	unsigned long long *full = reinterpret_cast<unsigned long long *>(smem + (size_t)NSLOT * slot_bytes);
+	__shared__ int next_box;
+	const int t = threadIdx.x;
+	if (t == 0) {
+		for (int s = 0; s < NSLOT; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(full + s)));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	__syncthreads();
+	if (t != 0) return;          // one thread drives the copies: this measures the copy engine + memory system only
+	unsigned ph = 0;
+	int issued = 0, waited = 0;
+	long long acc = 0;
+	int tile = blockIdx.x;
+	while (tile < ntiles) {
+		const int a = tile / ktiles, k0 = (tile - a * ktiles) * kw;
+		for (int f = 0; f < 11; f++) {                  // 11 copies per tile like the sweep kernel (8 fields + 3 repeats)
+			const int s = issued % NSLOT;
+			if (issued >= NSLOT) {                       // slot busy: wait for its previous copy
+				const unsigned par = (ph >> s) & 1u;
+				unsigned ok = 0;
+				while (!ok)
+					asm volatile("{ .reg .pred P1; mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x100000; selp.u32 %0, 1, 0, P1; }"
+					             : "=r"(ok) : "r"(smem_u32(full + s)), "r"(par) : "memory");
+				ph ^= 1u << s;
+				acc += *reinterpret_cast<const long long *>(smem + (size_t)s * slot_bytes);
+				waited++;
+			}
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(full + s)), "r"(slot_bytes) : "memory");
+			int c3, c4;
+			if (dir == 0) { c3 = a & jbm; c4 = a >> jbs; } else { c3 = 0; c4 = a + 1; }
+			asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+			             ::"r"(smem_u32(smem + (size_t)s * slot_bytes)), "l"(reinterpret_cast<unsigned long long>(&TM.m[f % 8])), "r"(smem_u32(full + s)),
+			             "r"(k0), "r"(0), "r"(0), "r"(c3), "r"(c4) : "memory");
+			issued++;
+		}
+		tile = (int)gridDim.x + atomicAdd(counter, 1);
+	}
+	while (waited < issued) {
+		const int s = waited % NSLOT;
+		const unsigned par = (ph >> s) & 1u;
+		unsigned ok = 0;
+		while (!ok)
+			asm volatile("{ .reg .pred P1; mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x100000; selp.u32 %0, 1, 0, P1; }"
+			             : "=r"(ok) : "r"(smem_u32(full + s)), "r"(par) : "memory");
+		ph ^= 1u << s;
+		waited++;
+	}
+	if (acc == 0x7fffffffffffffffll) *sink = acc;
+	(void)next_box;
+}
+
+int main()
+{
+	const int nx = 512, ny = 512, nz = 512, nzp = 512, jb = 64, jbs = 6, jbm = 63;
+	const long long plane = (long long)jb * nzp, bstride = (long long)(nx + 2) * plane, total = (ny / jb) * bstride;
+	void *p = nullptr;
+	cudaDriverEntryPointQueryResult q;
+	CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+	EncodeTiledFn enc = (EncodeTiledFn)p;
+	double *fields[8];
+	for (int f = 0; f < 8; f++) { CK(cudaMalloc(&fields[f], sizeof(double) * total)); CK(cudaMemset(fields[f], 0, sizeof(double) * total)); }
+	int *counter; long long *sink;
+	CK(cudaMalloc(&counter, 4)); CK(cudaMalloc(&sink, 8));
+	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+	for (int dir = 0; dir < 2; dir++)
+		for (int kw = 8; kw <= 16; kw *= 2) {               // 64-byte rows (the sweep tile) / 128-byte rows (half as many chunks per box)
+			const int GP = 64 * 8 / kw;                     // chunks per box so that a box stays 32 KB
+			Maps TM;
+			for (int f = 0; f < 8; f++) {
+				cuuint64_t dims[5], strides[4]; cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+				void *base;
+				if (dir == 0) {
+					dims[0] = nzp; dims[1] = nx / 8; dims[2] = 8; dims[3] = jb; dims[4] = ny / jb;
+					strides[0] = 8 * plane * 8; strides[1] = plane * 8; strides[2] = nzp * 8; strides[3] = bstride * 8;
+					box[0] = kw; box[1] = GP; box[2] = 8; box[3] = 1; box[4] = 1;
+					base = fields[f] + plane;
+				} else {
+					dims[0] = nzp; dims[1] = jb / 8; dims[2] = ny / jb; dims[3] = 8; dims[4] = nx + 2;
+					strides[0] = 8 * nzp * 8; strides[1] = bstride * 8; strides[2] = nzp * 8; strides[3] = plane * 8;
+					box[0] = kw; box[1] = jb / 8; box[2] = GP / (jb / 8); box[3] = 8; box[4] = 1;
+					base = fields[f];
+				}
+				CUresult r = enc(&TM.m[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+				                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+				if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 1; }
+			}
+			const int ktiles = nz / kw;
+			// 64 chunks of the line per tile: a 128-byte-row tile is two boxes high; count bytes, not tiles
+			const int ntiles = (dir == 0 ? ny : nx) * ktiles;
+			const int slot_bytes = kw * GP * 8 * 8;
+			auto run = [&](auto kern, int nslot) {
+				const size_t smem = (size_t)nslot * slot_bytes + 64;
+				CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				float best = 1e9f;
+				for (int rep = 0; rep < 3; rep++) {
+					CK(cudaMemset(counter, 0, 4));
+					cudaEventRecord(e0);
+					kern<<<148, 128, smem>>>(TM, ntiles, ktiles, dir, kw, counter, slot_bytes, jbm, jbs, sink);
+					cudaEventRecord(e1);
+					CK(cudaDeviceSynchronize());
+					float ms; cudaEventElapsedTime(&ms, e0, e1);
+					if (ms < best) best = ms;
+				}
+				const double bytes = (double)ntiles * 11 * slot_bytes;
+				printf("dir %c  row %3d B  box %d x %d chunks  %d slots in flight: %.3f ms  %.0f GB/s delivered to shared memory (11 copies per tile, 8 distinct fields)\n",
+				       "xy"[dir], kw * 8, kw, GP, nslot, best, bytes / best / 1e6);
+			};
+			run(k_probe<2>, 2); run(k_probe<4>, 4); run(k_probe<6>, 6);
+		}
+	return 0;
+}
