@@ -10,7 +10,7 @@ LIB_PATH = PKG / "libcmcadi.so"
 # every symbol include/cmc_adi.h declares (checked by tests/test_abi.py against the header text)
 SYMBOLS = [
     "cmc_last_error", "cmc_abi_version", "cmc_device_count",
-    "cmc_adi3d_create", "cmc_nccl_unique_id", "cmc_adi3d_create_dist", "cmc_adi3d_create_emulated", "cmc_adi3d_destroy", "cmc_adi3d_slab",
+    "cmc_adi3d_create", "cmc_nccl_unique_id", "cmc_adi3d_create_dist", "cmc_adi3d_create_emulated", "cmc_adi3d_create_multi", "cmc_adi3d_destroy", "cmc_adi3d_slab",
     "cmc_adi3d_set_nodes", "cmc_adi3d_set_nodes_aos", "cmc_adi3d_update_nodes", "cmc_adi3d_update_nodes_aos", "cmc_adi3d_build_lines", "cmc_adi3d_num_segments",
     "cmc_adi3d_update_boundaries", "cmc_adi3d_time_step", "cmc_adi3d_get_layer",
     "cmc_adi3d_set_option", "cmc_adi3d_get_option",
@@ -55,6 +55,7 @@ def load_library() -> C.CDLL:
         "cmc_nccl_unique_id": [vp],
         "cmc_adi3d_create_dist": [P(GridDesc), P(FluidParams), i32, i32, i32, i32, vp, P(vp)],
         "cmc_adi3d_create_emulated": [P(GridDesc), P(FluidParams), i32, i32, i32, P(vp)],
+        "cmc_adi3d_create_multi": [P(GridDesc), P(FluidParams), i32, P(i32), i32, P(vp)],
         "cmc_adi3d_destroy": [vp],
         "cmc_adi3d_slab": [vp, P(i32), P(i32)],
         "cmc_adi3d_set_nodes": [vp, vp, vp, vp, vp, vp, vp, vp],

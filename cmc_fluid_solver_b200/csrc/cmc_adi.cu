@@ -95,13 +95,15 @@ struct cmc_adi3d {
 	{
 		if (!profile) return;
 		Span sp; sp.kind = kind;
+		cudaSetDevice(device);                  // (a handle with slabs on several devices may have left another one current)
 		cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
-		cudaEventRecord(sp.a, stream);
+		cudaEventRecord(sp.a, stream);          // (slabs on several devices: the first slab's stream)
 		spans.push_back(sp);
 	}
 	void span_end()
 	{
 		if (!profile || spans.empty()) return;
+		cudaSetDevice(device);
 		cudaEventRecord(spans.back().b, stream);
 	}
 	void spans_collect()
@@ -163,6 +165,8 @@ struct Slab {
 	double *d_partials = nullptr, *d_err2 = nullptr, *d_sums8 = nullptr;
 	unsigned long long *d_segcount = nullptr;
 	int *d_tilectr = nullptr;      // tile counter of the persistent sweep kernels
+	cudaEvent_t done = nullptr;    // slabs on different devices of ONE process: "everything enqueued so far" of this slab
+	bool owns_stream = false;
 	FT *d_outvel = nullptr;
 	double *d_outT = nullptr;
 	size_t out_cap = 0;
@@ -183,6 +187,8 @@ struct Slab {
 		if (arena) cudaFree(arena);
 		for (auto &p : nodev) if (p) cudaFree(p);
 		for (auto &p : role) if (p) cudaFree(p);
+		if (done) cudaEventDestroy(done);
+		if (owns_stream && stream) cudaStreamDestroy(stream);
 		void *misc[] = {cv, cT, d_partials, d_err2, d_sums8, d_segcount, d_tilectr, d_outvel, d_outT, ncode, xcoef_send, xbnd_send};
 		for (void *p : misc) if (p) cudaFree(p);
 	}
@@ -314,9 +320,36 @@ struct Engine : cmc_adi3d {
 	unsigned epoch = 0;                // ordering of peer stores: last epoch this rank has published
 	int *d_timeout = nullptr;
 	bool halos_dirty = true;           // the guard planes of `cur` may not match the neighbours' boundary planes
+	// all slabs in ONE process on DIFFERENT devices (cmc_adi3d_create_multi: the reference's "GPU <n>" mode, one host
+	// thread driving n devices, FluidSolver3D.cpp:88-95, GPUplan.cpp:35-77): every slab has its own stream on its own
+	// device, the sweeps store into the neighbours' buffers through peer access, and ordering between the slabs' streams
+	// is by events - publish() records one per slab, await() makes the slabs' streams wait for their neighbours' (or for
+	// everybody's)
+	bool multi_device = false;
+	std::vector<int> slab_devices;
+
+	void use(const Slab<FT> *s) const { if (multi_device) cudaSetDevice(s->device); }
+	int sync_all()
+	{
+		for (auto *s : slabs) {
+			use(s);
+			const cudaError_t e = cudaStreamSynchronize(s->stream);
+			if (e != cudaSuccess) return fail(CMC_ERR_CUDA, std::string("cudaStreamSynchronize failed on device ") + std::to_string(s->device) + ": " + cudaGetErrorString(e));
+		}
+		if (multi_device) cudaSetDevice(device);
+		return CMC_OK;
+	}
+	// every slab's stream waits for what all slabs have enqueued so far (exchanges that run outside the sweeps)
+	void join_streams()
+	{
+		if (!multi_device) return;
+		for (auto *s : slabs) { use(s); cudaEventRecord(s->done, s->stream); }
+		for (auto *s : slabs) { use(s); for (auto *r : slabs) if (r != s) cudaStreamWaitEvent(s->stream, r->done, 0); }
+	}
 
 	~Engine() override
 	{
+		if (multi_device) sync_all();
 		cudaSetDevice(device);
 		if (p2p && stream) {
 			// the neighbours' last sweeps may still be storing into this rank's arena: every rank publishes once more
@@ -335,7 +368,7 @@ struct Engine : cmc_adi3d {
 	}
 
 	bool multi() const { return nslabs_total > 1; }
-	int exchange_kind() const override { return !multi() ? 0 : !push_mode() ? 1 : nccl ? 3 : 2; }
+	int exchange_kind() const override { return !multi() ? 0 : !push_mode() ? 1 : nccl ? 3 : multi_device ? 4 : 2; }
 	// (stores into another slab's buffers assume its layout equals this slab's: equal numbers of planes)
 	bool equal_slabs() const { return G.nx % nslabs_total == 0; }
 	bool push_mode() const { return multi() && equal_slabs() && (!nccl || p2p); }
@@ -351,6 +384,7 @@ struct Engine : cmc_adi3d {
 	// peer ordering (processes): publish `epoch` after this rank's kernel / wait for the ranks in `mask`
 	void publish()
 	{
+		if (multi_device) { for (auto *s : slabs) { use(s); cudaEventRecord(s->done, s->stream); } return; }
 		if (!p2p) return;
 		epoch++;
 		peer_signal(pm, slabs[0]->flag_off, epoch, stream);
@@ -358,6 +392,18 @@ struct Engine : cmc_adi3d {
 	}
 	void await(unsigned mask)
 	{
+		if (multi_device) {
+			// (mask is built for `rank`, the first slab: neighbour_mask() / all_mask(); here it only says which of the two)
+			const bool all = mask == all_mask();
+			for (size_t i = 0; i < slabs.size(); i++) {
+				use(slabs[i]);
+				for (size_t r = 0; r < slabs.size(); r++) {
+					if (r == i) continue;
+					if (all || r + 1 == i || r == i + 1) cudaStreamWaitEvent(slabs[i]->stream, slabs[r]->done, 0);
+				}
+			}
+			return;
+		}
 		if (!p2p) return;
 		peer_wait(pm, slabs[0]->flag_off, mask, epoch, d_timeout, stream);
 		launches++;
@@ -397,12 +443,37 @@ struct Engine : cmc_adi3d {
 			auto *s = new (std::nothrow) Slab<FT>();
 			if (!s) return fail(CMC_ERR_INVALID, "out of host memory");
 			slabs.push_back(s);
-			int rc = s->init(G, x0, nx, device, stream, first_slab + i, ntotal);
+			int sdev = device;
+			cudaStream_t sstream = stream;
+			if (multi_device && i > 0) {              // (slab 0 lives on the handle's own device and stream: the timing spans see it)
+				sdev = slab_devices[i];
+				{ const int device = sdev; CU_TRY(cudaSetDevice(sdev)); CU_TRY(cudaStreamCreateWithFlags(&sstream, cudaStreamNonBlocking)); }
+				s->owns_stream = true;
+			}
+			int rc = s->init(G, x0, nx, sdev, sstream, first_slab + i, ntotal);
 			if (rc) return rc;
+			if (multi_device) { const int device = sdev; CU_TRY(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming)); }
 			dev_bytes += s->bytes;
 		}
+		if (multi_device) {
+			// every device stores into every other device's slab buffers (guard planes, interface tables)
+			for (size_t i = 0; i < slabs.size(); i++) {
+				cudaSetDevice(slabs[i]->device);
+				for (size_t j = 0; j < slabs.size(); j++) {
+					if (i == j || slabs[i]->device == slabs[j]->device) continue;
+					int can = 0;
+					cudaDeviceCanAccessPeer(&can, slabs[i]->device, slabs[j]->device);
+					if (!can) return fail(CMC_ERR_UNSUPPORTED, "create_multi: the devices cannot access each other's memory (peer access)");
+					const cudaError_t e = cudaDeviceEnablePeerAccess(slabs[j]->device, 0);
+					if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+						return fail(CMC_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+					cudaGetLastError();
+				}
+			}
+			cudaSetDevice(device);
+		}
 		L = G; L.x0 = lo; L.shape(hi - lo, G.ny, G.nz, G.nzp, G.jbs);
-		CU_TRY(cudaHostAlloc((void **)&h_err2, 2 * sizeof(double) * nlocal * kErrRing, cudaHostAllocDefault));
+		CU_TRY(cudaHostAlloc((void **)&h_err2, 2 * sizeof(double) * nlocal * kErrRing, cudaHostAllocPortable));
 		memset(h_err2, 0, 2 * sizeof(double) * nlocal * kErrRing);
 		CU_TRY(cudaMalloc((void **)&d_timeout, sizeof(int)));
 		CU_TRY(cudaMemsetAsync(d_timeout, 0, sizeof(int), stream));
@@ -439,17 +510,20 @@ struct Engine : cmc_adi3d {
 			if (nccl_exchange(nccl, ops.data(), (int)ops.size(), stream)) return fail(CMC_ERR_COMM, nccl_error());
 			launches += 1;
 		} else {
+			join_streams();          // (slabs on different devices: the copies below read what the other streams produced)
 			for (size_t i = 0; i + 1 < slabs.size(); i++) {
 				Slab<FT> *a = slabs[i], *b = slabs[i + 1];
+				use(a);
 				for (int q = 0; q < 4; q++) {
 					FT *fa = a->field[a->slot[logical]][q], *fb = b->field[b->slot[logical]][q];
 					for (int k = 0; k < nb; k++) {
 						const long long ao = (long long)k * a->L.bstride, bo = (long long)k * b->L.bstride;
-						CU_TRY(cudaMemcpyAsync(fb + bo + b->L.idx(-1, 0, 0), fa + ao + a->L.idx(a->L.nx - 1, 0, 0), pb, cudaMemcpyDeviceToDevice, stream));
-						CU_TRY(cudaMemcpyAsync(fa + ao + a->L.idx(a->L.nx, 0, 0), fb + bo + b->L.idx(0, 0, 0), pb, cudaMemcpyDeviceToDevice, stream));
+						CU_TRY(cudaMemcpyAsync(fb + bo + b->L.idx(-1, 0, 0), fa + ao + a->L.idx(a->L.nx - 1, 0, 0), pb, cudaMemcpyDefault, a->stream));
+						CU_TRY(cudaMemcpyAsync(fa + ao + a->L.idx(a->L.nx, 0, 0), fb + bo + b->L.idx(0, 0, 0), pb, cudaMemcpyDefault, a->stream));
 					}
 				}
 			}
+			join_streams();
 		}
 		span_end();
 		return CMC_OK;
@@ -470,9 +544,13 @@ struct Engine : cmc_adi3d {
 			if (nccl_exchange(nccl, ops.data(), (int)ops.size(), stream)) return fail(CMC_ERR_COMM, nccl_error());
 			launches += 1;
 		} else {
-			for (size_t i = 0; i < slabs.size(); i++)
+			join_streams();
+			for (size_t i = 0; i < slabs.size(); i++) {
+				use(slabs[i]);
 				for (size_t j = 0; j < slabs.size(); j++)
-					CU_TRY(cudaMemcpyAsync((slabs[j]->*recv) + i * block_elems, (slabs[i]->*send) + j * block_elems, bb, cudaMemcpyDeviceToDevice, stream));
+					CU_TRY(cudaMemcpyAsync((slabs[j]->*recv) + i * block_elems, (slabs[i]->*send) + j * block_elems, bb, cudaMemcpyDefault, slabs[i]->stream));
+			}
+			join_streams();
 		}
 		span_end();
 		return CMC_OK;
@@ -522,10 +600,11 @@ struct Engine : cmc_adi3d {
 			if (bad == 2) return fail(CMC_ERR_INVALID, "set_nodes: boundary-condition type out of range");
 		}
 		for (auto *s : slabs) {
+			use(s);
 			int rc = s->upload_nodes(code.data(), N, src, keep_layers);
 			if (rc) return rc;
 		}
-		CU_TRY(cudaStreamSynchronize(stream));
+		{ int rc = sync_all(); if (rc) return rc; }
 		halos_dirty = true;
 		have_nodes = true; have_lines = false;
 		if (!keep_layers) { diffError = 0.0; err_pending = 0; worst_err = 0.0; }
@@ -538,6 +617,8 @@ struct Engine : cmc_adi3d {
 		CU_TRY(cudaSetDevice(device));
 		for (int d = 0; d < 3; d++) { num_segs[d] = 0; shared_free[d] = 0; }
 		for (auto *s : slabs) {
+			use(s);
+			cudaStream_t stream = s->stream;
 			CU_TRY(cudaMemsetAsync(s->d_segcount, 0, 8 * sizeof(unsigned long long), stream));
 			for (int d = 0; d < 3; d++) CU_TRY(cudaMemsetAsync(s->role[d], 0, (size_t)s->L.total, stream));
 			launch_role_type_bits(G, s->ncode, s->L, s->role[0], s->role[1], s->role[2], stream, &launches);
@@ -579,10 +660,13 @@ struct Engine : cmc_adi3d {
 	{
 		if (!have_lines) return fail(CMC_ERR_INVALID, "update_boundaries: call cmc_adi3d_build_lines first");
 		CU_TRY(cudaSetDevice(device));
+		// (slabs on several devices: the neighbours' last sweep stores into the guard planes that are refreshed here)
+		if (multi_device) await(neighbour_mask());
 		span_begin(CMC_TIMING_BOUNDARY);
 		for (auto *s : slabs) {
+			use(s);
 			ConstLayerPtrs<FT> nv; for (int q = 0; q < 4; q++) nv.f[q] = s->nodev[q];
-			launch_update_boundaries<FT>(s->L, s->role[2], nv, s->layer(CMC_LAYER_CUR), stream, &launches);
+			launch_update_boundaries<FT>(s->L, s->role[2], nv, s->layer(CMC_LAYER_CUR), s->stream, &launches);
 		}
 		span_end();
 		return CMC_OK;
@@ -683,7 +767,8 @@ struct Engine : cmc_adi3d {
 					SweepArgs<FT> A = sweep_args(s, dir, dt, cur_layer, next_layer);
 					if (t_is_c)
 						for (int q = 0; q < 4; q++) A.temp[q] = s->field[s->slot[CMC_LAYER_CUR]][q];
-					if (!launch_x_spike<FT>(A, stream, &launches)) return fail(CMC_ERR_UNSUPPORTED, "x-spike pass: unsupported slab shape");
+					use(s);
+					if (!launch_x_spike<FT>(A, s->stream, &launches)) return fail(CMC_ERR_UNSUPPORTED, "x-spike pass: unsupported slab shape");
 				}
 				span_end();
 				const size_t lpo = slabs[0]->lines_per_owner(nslabs_total);
@@ -697,7 +782,8 @@ struct Engine : cmc_adi3d {
 					FT *to[MAX_SLABS] = {};
 					for (int r = 0; r < nslabs_total; r++)
 						to[r] = push_mode() ? in_slab(s, r, s->xbnd_recv) + (size_t)s->index * 8 * lpo : s->xbnd_send + (size_t)r * 8 * lpo;
-					launch_x_interface<FT>(nslabs_total, (int)lpo, owned, s->xcoef_recv, to, stream, &launches);
+					use(s);
+					launch_x_interface<FT>(nslabs_total, (int)lpo, owned, s->xcoef_recv, to, s->stream, &launches);
 				}
 				span_end();
 				if (push_mode()) { span_begin(CMC_TIMING_COMM); publish(); await(all_mask()); span_end(); }
@@ -707,6 +793,8 @@ struct Engine : cmc_adi3d {
 			std::vector<char> swapped(slabs.size(), 0);
 			for (size_t si = 0; si < slabs.size(); si++) {
 				Slab<FT> *s = slabs[si];
+				use(s);
+				cudaStream_t stream = s->stream;
 				SweepArgs<FT> A = sweep_args(s, dir, dt, cur_layer, next_layer);
 				if (t_is_c)
 					for (int q = 0; q < 4; q++) A.temp[q] = s->field[s->slot[CMC_LAYER_CUR]][q];
@@ -729,7 +817,8 @@ struct Engine : cmc_adi3d {
 			{   // debug facility: CMC_DEBUG_SYNC=1 synchronises after every sweep and reports the kernel that faulted
 				static const bool dbg = getenv("CMC_DEBUG_SYNC") != nullptr;
 				if (dbg) {
-					const cudaError_t e = cudaStreamSynchronize(stream);
+					cudaError_t e = cudaSuccess;
+					for (auto *s : slabs) { use(s); const cudaError_t es = cudaStreamSynchronize(s->stream); if (es != cudaSuccess) e = es; }
 					if (e != cudaSuccess) {
 						char buf[160];
 						snprintf(buf, sizeof buf, "sweep along %c (kernel kind %d, local iteration %d) failed: %s", "xyz"[dir], kernel_kind(dir), it, cudaGetErrorString(e));
@@ -755,8 +844,9 @@ struct Engine : cmc_adi3d {
 		// cur -> next on BOUND and VALVE cells (AdiSolver3D.cpp:310-311); temp <- cur (:320)
 		span_begin(CMC_TIMING_COPY);
 		for (auto *s : slabs) {
-			launch_copy_masked<FT>(s->L, s->role[2], R_BV, s->clayer(CMC_LAYER_CUR), s->layer(CMC_LAYER_NEXT), stream, &launches);
-			if (copy_temp) launch_copy_full<FT>(s->L, s->clayer(CMC_LAYER_CUR), s->layer(CMC_LAYER_TEMP), stream, &launches);
+			use(s);
+			launch_copy_masked<FT>(s->L, s->role[2], R_BV, s->clayer(CMC_LAYER_CUR), s->layer(CMC_LAYER_NEXT), s->stream, &launches);
+			if (copy_temp) launch_copy_full<FT>(s->L, s->clayer(CMC_LAYER_CUR), s->layer(CMC_LAYER_TEMP), s->stream, &launches);
 		}
 		span_end();
 		return CMC_OK;
@@ -777,6 +867,8 @@ struct Engine : cmc_adi3d {
 		}
 		for (size_t i = 0; i < slabs.size(); i++) {
 			Slab<FT> *s = slabs[i];
+			use(s);
+			cudaStream_t stream = s->stream;
 			const int l = s->slot[logical_layer];
 			launch_div_error<FT>(s->L, s->role[2], s->field[l][0], s->field[l][1], s->field[l][2], (FT)dx, (FT)dy, (FT)dz,
 			                     s->d_partials, Slab<FT>::kMaxErrBlocks, s->d_err2, stream, &launches);
@@ -801,7 +893,7 @@ struct Engine : cmc_adi3d {
 	{
 		worst_err = diffError;
 		if (err_pending) {
-			CU_TRY(cudaStreamSynchronize(stream));
+			{ int rc = sync_all(); if (rc) return rc; }
 			worst_err = 0.0;
 			for (int k = err_pending; k >= 1; k--) {
 				const double e = err_from_host((err_head - k + 2 * kErrRing) % kErrRing);
@@ -856,8 +948,10 @@ struct Engine : cmc_adi3d {
 			if (!fold_merge) {
 				// update non-linear layer once more (:354): temp = (temp + next) / 2 on NODE_IN
 				span_begin(CMC_TIMING_MERGE);
-				for (auto *s : slabs)
-					launch_merge<FT>(s->L, s->role[2], s->clayer(CMC_LAYER_NEXT), s->layer(CMC_LAYER_TEMP), stream, &launches);
+				for (auto *s : slabs) {
+					use(s);
+					launch_merge<FT>(s->L, s->role[2], s->clayer(CMC_LAYER_NEXT), s->layer(CMC_LAYER_TEMP), s->stream, &launches);
+				}
 				span_end();
 			}
 		}
@@ -869,7 +963,7 @@ struct Engine : cmc_adi3d {
 		}
 		if (!async) {
 			if ((rc = fetch_error())) return rc;
-			CU_TRY(cudaStreamSynchronize(stream));
+			if ((rc = sync_all())) return rc;
 			CU_TRY(cudaGetLastError());
 			if ((rc = check_peers())) return rc;
 			if (err) *err = diffError;
@@ -888,7 +982,7 @@ struct Engine : cmc_adi3d {
 		CU_TRY(cudaSetDevice(device));
 		int rc = fetch_error();
 		if (rc) return rc;
-		CU_TRY(cudaStreamSynchronize(stream));
+		if ((rc = sync_all())) return rc;
 		CU_TRY(cudaGetLastError());
 		if ((rc = check_peers())) return rc;
 		if (err) *err = diffError;
@@ -913,7 +1007,7 @@ struct Engine : cmc_adi3d {
 		halos_dirty = true;
 		int rc = solve_direction_impl(dir, (FT)dt, nl, cur_layer, next_layer);
 		if (rc) return rc;
-		CU_TRY(cudaStreamSynchronize(stream));
+		if ((rc = sync_all())) return rc;
 		CU_TRY(cudaGetLastError());
 		return CMC_OK;
 	}
@@ -940,6 +1034,8 @@ struct Engine : cmc_adi3d {
 		double tot[8] = {};
 		for (auto *s : slabs) {
 			// (d_partials holds 2 doubles per block for the residual: use a quarter of the blocks here)
+			use(s);
+			cudaStream_t stream = s->stream;
 			launch_field_sums<FT>(s->L, s->role[2], s->clayer(logical), s->d_partials, Slab<FT>::kMaxErrBlocks / 4, s->d_sums8, stream, &launches);
 			if (nccl && nccl_allreduce_sum_f64(nccl, s->d_sums8, 8, stream)) return fail(CMC_ERR_COMM, nccl_error());
 			double h8[8];
@@ -975,6 +1071,8 @@ struct Engine : cmc_adi3d {
 			}
 		}
 		for (auto *s : slabs) {
+			use(s);
+			cudaStream_t stream = s->stream;
 			launch_clear_out<FT>(s->L, s->role[2], s->layer(CMC_LAYER_NEXT), (FT)CMC_MISSING_VALUE, stream, &launches);
 			const size_t need = (nccl && rank == 0) ? outN : (size_t)std::max(0, hi[s->index] - lo[s->index]) * rowN;
 			if (need > s->out_cap) {
@@ -1016,12 +1114,13 @@ struct Engine : cmc_adi3d {
 			for (auto *s : slabs) {
 				const int oi0 = lo[s->index], oi1 = hi[s->index];
 				if (oi1 <= oi0) continue;
+				use(s);
 				const size_t o0 = (size_t)oi0 * rowN, cnt = (size_t)(oi1 - oi0) * rowN;
-				CU_TRY(cudaMemcpyAsync((FT *)vel + 3 * o0, s->d_outvel, cnt * 3 * sizeof(FT), cudaMemcpyDeviceToHost, stream));
-				CU_TRY(cudaMemcpyAsync(T + o0, s->d_outT, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+				CU_TRY(cudaMemcpyAsync((FT *)vel + 3 * o0, s->d_outvel, cnt * 3 * sizeof(FT), cudaMemcpyDeviceToHost, s->stream));
+				CU_TRY(cudaMemcpyAsync(T + o0, s->d_outT, cnt * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
 			}
 		}
-		CU_TRY(cudaStreamSynchronize(stream));
+		{ int rc = sync_all(); if (rc) return rc; }
 		CU_TRY(cudaGetLastError());
 		return check_peers();
 	}
@@ -1032,10 +1131,11 @@ struct Engine : cmc_adi3d {
 		if (logical < 0 || logical > 3 || var < 0 || var > 3) return fail(CMC_ERR_INVALID, "read_field: bad layer/var");
 		CU_TRY(cudaSetDevice(device));
 		for (auto *s : slabs) {
+			use(s);
 			int rc = s->copy_planes(s->field[s->slot[logical]][var], nullptr, (FT *)dst, 0, s->L.nx, L.x0);
 			if (rc) return rc;
 		}
-		CU_TRY(cudaStreamSynchronize(stream));
+		{ int rc = sync_all(); if (rc) return rc; }
 		return CMC_OK;
 	}
 
@@ -1045,10 +1145,11 @@ struct Engine : cmc_adi3d {
 		CU_TRY(cudaSetDevice(device));
 		halos_dirty = true;
 		for (auto *s : slabs) {
+			use(s);
 			int rc = s->copy_planes(s->field[s->slot[logical]][var], (const FT *)src, nullptr, 0, s->L.nx, L.x0);
 			if (rc) return rc;
 		}
-		CU_TRY(cudaStreamSynchronize(stream));
+		{ int rc = sync_all(); if (rc) return rc; }
 		return CMC_OK;
 	}
 };
@@ -1069,7 +1170,8 @@ static int check_device(int device)
 
 // first_slab / nlocal / ntotal: which slabs of the x-split this handle holds
 static int create_impl(const cmc_grid_desc *grid, const cmc_fluid_params *params, int fp_bytes, int device,
-                       int first_slab, int nlocal, int ntotal, const void *nccl_id, cmc_adi3d **out)
+                       int first_slab, int nlocal, int ntotal, const void *nccl_id, cmc_adi3d **out,
+                       const int *devices = nullptr)
 {
 	if (!grid || !params || !out) return fail(CMC_ERR_INVALID, "create: null argument");
 	*out = nullptr;
@@ -1080,6 +1182,14 @@ static int create_impl(const cmc_grid_desc *grid, const cmc_fluid_params *params
 	if (ntotal > grid->dimx) return fail(CMC_ERR_INVALID, "create: more slabs than x-planes");
 	int rc = check_device(device);
 	if (rc) return rc;
+	std::vector<int> devs;
+	if (devices) {
+		for (int i = 0; i < nlocal; i++) {
+			if ((rc = check_device(devices[i]))) return rc;
+			for (int j = 0; j < i; j++) if (devices[j] == devices[i]) return fail(CMC_ERR_INVALID, "create_multi: a device is listed twice");
+			devs.push_back(devices[i]);
+		}
+	}
 	cmc_adi3d *h = nullptr;
 	NcclComm *comm = nullptr;
 	if (nccl_id) {
@@ -1091,12 +1201,14 @@ static int create_impl(const cmc_grid_desc *grid, const cmc_fluid_params *params
 		auto *s = new (std::nothrow) Engine<float>();
 		if (!s) return fail(CMC_ERR_INVALID, "out of host memory");
 		s->device = device; s->fp = 4; s->nccl = comm;
+		if (devs.size() > 1) { s->multi_device = true; s->slab_devices = devs; }
 		rc = s->init(grid, params, first_slab, nlocal, ntotal);
 		h = s;
 	} else {
 		auto *s = new (std::nothrow) Engine<double>();
 		if (!s) return fail(CMC_ERR_INVALID, "out of host memory");
 		s->device = device; s->fp = 8; s->nccl = comm;
+		if (devs.size() > 1) { s->multi_device = true; s->slab_devices = devs; }
 		rc = s->init(grid, params, first_slab, nlocal, ntotal);
 		h = s;
 	}
@@ -1134,6 +1246,14 @@ int cmc_adi3d_create_emulated(const cmc_grid_desc *grid, const cmc_fluid_params 
                               int n_slabs, cmc_adi3d **out)
 {
 	return create_impl(grid, params, fp_bytes, device, 0, n_slabs, n_slabs, nullptr, out);
+}
+
+int cmc_adi3d_create_multi(const cmc_grid_desc *grid, const cmc_fluid_params *params, int fp_bytes, const int *devices, int n_devices,
+                           cmc_adi3d **out)
+{
+	if (!devices || n_devices < 1) return fail(CMC_ERR_INVALID, "create_multi: no devices");
+	if (n_devices == 1) return create_impl(grid, params, fp_bytes, devices[0], 0, 1, 1, nullptr, out);
+	return create_impl(grid, params, fp_bytes, devices[0], 0, n_devices, n_devices, nullptr, out, devices);
 }
 
 int cmc_nccl_unique_id(void *id128)

@@ -9,7 +9,7 @@
 
 namespace FluidSolver3D
 {
-	B200AdiSolver3D::B200AdiSolver3D(int _mode, int _device) : h(NULL), mode(_mode), device(_device), diffError(0.0)
+	B200AdiSolver3D::B200AdiSolver3D(int _mode, int _device, int _num_gpus) : h(NULL), mode(_mode), device(_device), num_gpus(_num_gpus), diffError(0.0)
 	{
 		grid = NULL;
 		cur = NULL;      // the time layers live on the device behind the C ABI
@@ -38,7 +38,15 @@ namespace FluidSolver3D
 		params = _params;
 		cmc_grid_desc g = { dimx, dimy, dimz, grid->dx, grid->dy, grid->dz };
 		cmc_fluid_params p = { params.v_T, params.v_vis, params.t_vis, params.t_phi };
-		check(cmc_adi3d_create(&g, &p, (int)sizeof(FTYPE), device, &h), "cmc_adi3d_create");
+		if (num_gpus > 1) {
+			// "GPU <n>": one host thread, n devices (GPUplan::init, src/Common/GPUplan.cpp:35-77)
+			int devices[16];
+			const int n = num_gpus > 16 ? 16 : num_gpus;
+			for (int i = 0; i < n; i++) devices[i] = device + i;
+			check(cmc_adi3d_create_multi(&g, &p, (int)sizeof(FTYPE), devices, n, &h), "cmc_adi3d_create_multi");
+			printf("B200AdiSolver3D: %d devices, x-slabs of %d planes\n", n, dimx / n);
+		} else
+			check(cmc_adi3d_create(&g, &p, (int)sizeof(FTYPE), device, &h), "cmc_adi3d_create");
 		check(cmc_adi3d_set_option(h, "mode", mode), "cmc_adi3d_set_option");
 		// the reference's Node[] goes across the ABI as it is (Grid3D.h:73-88)
 		check(cmc_adi3d_set_nodes_aos(h, grid->GetNodesCPU(), sizeof(Node)), "cmc_adi3d_set_nodes_aos");

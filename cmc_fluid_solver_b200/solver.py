@@ -69,8 +69,9 @@ class AdiSolver3D:
 
     # -- Solver3D::Init ------------------------------------------------------------------------------------
     def Init(self, case: Case, device: int = 0, mode: str = "fast", rank: int = 0, nranks: int = 1, nccl_id: bytes = None,
-             emulate_slabs: int = 0):
-        """rank/nranks/nccl_id: one x-slab per process (NCCL).  emulate_slabs=N: all N slabs in this handle, on one GPU."""
+             emulate_slabs: int = 0, devices=None):
+        """rank/nranks/nccl_id: one x-slab per process (NCCL).  emulate_slabs=N: all N slabs in this handle, on one GPU.
+        devices=[d0, d1, ...]: all slabs in this handle, one per device (the reference's "GPU <n>" mode)."""
         lib = load_library()
         self.case = case
         self.fp = case.fp_bytes
@@ -78,7 +79,10 @@ class AdiSolver3D:
         g = GridDesc(case.dimx, case.dimy, case.dimz, case.dx, case.dy, case.dz)
         p = FluidParams(case.v_T, case.v_vis, case.t_vis, case.t_phi)
         h = C.c_void_p()
-        if emulate_slabs > 1:
+        if devices is not None and len(devices) > 1:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(lib.cmc_adi3d_create_multi(C.byref(g), C.byref(p), self.fp, arr, len(devices), C.byref(h)))
+        elif emulate_slabs > 1:
             _check(lib.cmc_adi3d_create_emulated(C.byref(g), C.byref(p), self.fp, device, emulate_slabs, C.byref(h)))
         elif nranks > 1:
             buf = C.create_string_buffer(nccl_id, 128)
@@ -245,7 +249,7 @@ class AdiSolver3D:
     def exchange_kind(self) -> str:
         v = C.c_int64(0)
         _check(load_library().cmc_adi3d_get_option(self._h, b"exchange", C.byref(v)))
-        return ("none", "nccl", "fused-stores", "fused-stores-peer-memory")[v.value]
+        return ("none", "nccl", "fused-stores", "fused-stores-peer-memory", "fused-stores-peer-access")[v.value]
 
     def device_bytes(self) -> int:
         n = C.c_int64(0)

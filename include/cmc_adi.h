@@ -91,6 +91,13 @@ int cmc_adi3d_create_dist(const cmc_grid_desc *grid, const cmc_fluid_params *par
  * counterpart of the reference's MGPU_EMU switch, src/Common/GPUplan.h:10-15). */
 int cmc_adi3d_create_emulated(const cmc_grid_desc *grid, const cmc_fluid_params *params,
                               int fp_bytes, int device, int n_slabs, cmc_adi3d **out);
+/* ONE process, ONE host thread, n devices - the reference's own multi-GPU mode ("GPU <n>" on its command line:
+ * FluidSolver3D.cpp:88-95, GPUplan::init enables peer access between the devices, GPUplan.cpp:35-77).  The handle holds
+ * all n x-slabs, slab i on devices[i]; every slab has its own stream; the sweeps store their boundary planes and
+ * interface systems straight into the neighbouring devices' buffers through peer access (NVLink), ordering is by CUDA
+ * events.  All other entry points work as on a single-GPU handle (whole-grid arrays in, whole layers out). */
+int cmc_adi3d_create_multi(const cmc_grid_desc *grid, const cmc_fluid_params *params, int fp_bytes,
+                           const int *devices, int n_devices, cmc_adi3d **out);
 int cmc_adi3d_destroy(cmc_adi3d *h);           /* ~AdiSolver3D (AdiSolver3D.cpp:153-158) */
 
 /* planes held by this handle: global x range [x0, x0+nx) */
@@ -140,7 +147,8 @@ int cmc_adi3d_get_layer(cmc_adi3d *h, void *vel_xyz, double *T, int outdimx, int
  * 1 direct-load partition kernel, 2 cp.async ring kernel, 3 TMA-staged tile kernel, 4 slab-coupled x-sweep),
  * "nzp" (padded z-line length), "jb" (rows per y-block of the field storage, 0 = one block), "exchange" (how slabs exchange planes and interface systems: 0 single slab,
  * 1 NCCL send/recv groups, 2 stores fused into the sweep kernels (slabs on one device), 3 the same into peer memory
- * over NVLink - every rank maps the other ranks' exchange arena with CUDA IPC) */
+ * over NVLink - every rank maps the other ranks' exchange arena with CUDA IPC, 4 the same between the devices of one
+ * process - cmc_adi3d_create_multi) */
 int cmc_adi3d_set_option(cmc_adi3d *h, const char *key, int64_t value);
 int cmc_adi3d_get_option(const cmc_adi3d *h, const char *key, int64_t *value);
 

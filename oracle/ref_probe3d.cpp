@@ -162,7 +162,7 @@ int main(int argc, char **argv)
 #ifdef WITH_B200
 		B200AdiSolver3D *b200 = NULL;
 		if (which != "cpu") {
-			b200 = new B200AdiSolver3D(which == "b200exact" ? CMC_MODE_EXACT : CMC_MODE_FAST, 0);
+			b200 = new B200AdiSolver3D(which == "b200exact" ? CMC_MODE_EXACT : CMC_MODE_FAST, 0, ngpus);      // gpus=<n>: the reference CLI's "GPU <n>"
 			b200->Init(GPU, false, grid, *params, false, 1);
 		}
 #else
