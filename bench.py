@@ -388,6 +388,7 @@ def main():
                "what": "write_field x4 (pinned host -> HBM, every rank its slab), UpdateBoundaries, TimeStep(computeError), GetLayer full "
                        "resolution (HBM -> pinned host on rank 0); host wall clock between barriers, max over ranks"}
 
+    # the reported CPU baseline: rank 0 runs the reference solver on the host cores while the other ranks wait at a barrier
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         try:
@@ -396,6 +397,7 @@ def main():
                 cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": cpu_sample_text(r)}
         except Exception as ex:      # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "reference", "sample": f"failed: {ex}"}
+    barrier()
 
     if rank == 0:
         line = {
