@@ -10,7 +10,7 @@ LIB_PATH = PKG / "libcmcadi.so"
 # every symbol include/cmc_adi.h declares (checked by tests/test_abi.py against the header text)
 SYMBOLS = [
     "cmc_last_error", "cmc_abi_version", "cmc_device_count",
-    "cmc_adi3d_create", "cmc_nccl_unique_id", "cmc_adi3d_create_dist", "cmc_adi3d_create_emulated", "cmc_adi3d_create_multi", "cmc_adi3d_destroy", "cmc_adi3d_slab",
+    "cmc_adi3d_create", "cmc_nccl_unique_id", "cmc_adi3d_create_dist", "cmc_adi3d_create_emulated", "cmc_adi3d_create_multi", "cmc_adi3d_create_ex", "cmc_split_planes", "cmc_adi3d_destroy", "cmc_adi3d_slab",
     "cmc_adi3d_set_nodes", "cmc_adi3d_set_nodes_aos", "cmc_adi3d_update_nodes", "cmc_adi3d_update_nodes_aos", "cmc_adi3d_build_lines", "cmc_adi3d_num_segments",
     "cmc_adi3d_update_boundaries", "cmc_adi3d_time_step", "cmc_adi3d_get_layer",
     "cmc_adi3d_set_option", "cmc_adi3d_get_option",
@@ -25,6 +25,11 @@ SYMBOLS = [
 class GridDesc(C.Structure):
     _fields_ = [("dimx", C.c_int32), ("dimy", C.c_int32), ("dimz", C.c_int32),
                 ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double)]
+
+
+class Decomp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("device", C.c_int32), ("n_slabs", C.c_int32), ("rank", C.c_int32),
+                ("nccl_unique_id", C.c_void_p), ("devices", C.POINTER(C.c_int32)), ("planes", C.POINTER(C.c_int32))]
 
 
 class FluidParams(C.Structure):
@@ -56,6 +61,8 @@ def load_library() -> C.CDLL:
         "cmc_adi3d_create_dist": [P(GridDesc), P(FluidParams), i32, i32, i32, i32, vp, P(vp)],
         "cmc_adi3d_create_emulated": [P(GridDesc), P(FluidParams), i32, i32, i32, P(vp)],
         "cmc_adi3d_create_multi": [P(GridDesc), P(FluidParams), i32, P(i32), i32, P(vp)],
+        "cmc_adi3d_create_ex": [P(GridDesc), P(FluidParams), i32, P(Decomp), P(vp)],
+        "cmc_split_planes": [i32, P(GridDesc), vp, i32, P(C.c_int32)],
         "cmc_adi3d_destroy": [vp],
         "cmc_adi3d_slab": [vp, P(i32), P(i32)],
         "cmc_adi3d_set_nodes": [vp, vp, vp, vp, vp, vp, vp, vp],

@@ -140,12 +140,21 @@ static void parallel_for(size_t n, F body)
 	for (auto &th : pool) th.join();
 }
 
-// GPUplan::splitEven1D (reference GPUplan.cpp:122-141): dimx / n planes each, remainder spread over the first slabs
-static void split_even(int dimx, int n, int r, int &x0, int &nx)
+// Default x-split of a grid over n slabs: the even split of GPUplan::splitEven1D (reference GPUplan.cpp:122-141) with the
+// cut positions moved to multiples of 8 planes - the partitioned x-sweep works on 8-row chunks, so every slab but the
+// last holds a multiple of 8 planes; the last one takes what is left.  (n == 1: the whole grid.)
+static void split_default(int dimx, int n, std::vector<int> &planes)
 {
-	const int base = dimx / n, rem = dimx % n;
-	nx = base + (r < rem ? 1 : 0);
-	x0 = r * base + (r < rem ? r : rem);
+	planes.assign(n, 0);
+	int prev = 0;
+	for (int r = 0; r < n; r++) {
+		int cut = r + 1 == n ? dimx : (int)(((long long)dimx * (r + 1) / n + 4) / 8 * 8);
+		if (cut < prev + 8) cut = prev + 8;
+		if (cut > dimx) cut = dimx;
+		planes[r] = cut - prev;
+		prev = cut;
+	}
+	if (n == 1) planes[0] = dimx;
 }
 
 // ---- one x-slab: every device buffer of the planes [x0, x0 + nx) ------------------------------------------------
@@ -202,10 +211,10 @@ struct Slab {
 		return CMC_OK;
 	}
 
-	int init(const Layout &g, int x0, int nx, int dev, cudaStream_t s, int idx, int nslabs)
+	int init(const Layout &g, int x0, int nx, int alloc_nx, int dev, cudaStream_t s, int idx, int nslabs)
 	{
 		device = dev; stream = s; G = g; index = idx;
-		L = G; L.x0 = x0; L.shape(nx, G.ny, G.nz, G.nzp, G.jbs);
+		L = G; L.x0 = x0; L.shape(nx, G.ny, G.nz, G.nzp, G.jbs, alloc_nx);
 		int rc;
 		{
 			auto up = [](size_t v) { return (v + 255) / 256 * 256; };
@@ -327,6 +336,9 @@ struct Engine : cmc_adi3d {
 	// everybody's)
 	bool multi_device = false;
 	std::vector<int> slab_devices;
+	// the x-split of the grid over ALL slabs (local or not): planes per slab and first plane of every slab
+	std::vector<int> split_nx, split_x0;
+	std::vector<int> planes_arg;       // caller-supplied split (cmc_adi3d_create_*_split), empty = the default
 
 	void use(const Slab<FT> *s) const { if (multi_device) cudaSetDevice(s->device); }
 	int sync_all()
@@ -370,8 +382,7 @@ struct Engine : cmc_adi3d {
 	bool multi() const { return nslabs_total > 1; }
 	int exchange_kind() const override { return !multi() ? 0 : !push_mode() ? 1 : nccl ? 3 : multi_device ? 4 : 2; }
 	// (stores into another slab's buffers assume its layout equals this slab's: equal numbers of planes)
-	bool equal_slabs() const { return G.nx % nslabs_total == 0; }
-	bool push_mode() const { return multi() && equal_slabs() && (!nccl || p2p); }
+	bool push_mode() const { return multi() && (!nccl || p2p); }
 
 	// the address, in the slab that holds slab index `r`, of the buffer that is `mine` in slab `s`
 	FT *in_slab(Slab<FT> *s, int r, FT *mine) const
@@ -434,10 +445,18 @@ struct Engine : cmc_adi3d {
 			G.shape(g->dimx, g->dimy, g->dimz, round_up(g->dimz, 16), jbs);
 		}
 		nslabs_total = ntotal; rank = first_slab; nranks = ntotal;
+		if ((int)planes_arg.size() == ntotal) split_nx = planes_arg; else split_default(G.nx, ntotal, split_nx);
+		split_x0.assign(ntotal, 0);
+		int nx_max = 0, covered = 0;
+		for (int r = 0; r < ntotal; r++) {
+			split_x0[r] = covered; covered += split_nx[r];
+			nx_max = std::max(nx_max, split_nx[r]);
+			if (split_nx[r] < 1) return fail(CMC_ERR_INVALID, "create: a slab without planes (grid too small for this many slabs, or a bad split)");
+		}
+		if (covered != G.nx) return fail(CMC_ERR_INVALID, "create: the slab sizes do not add up to dimx");
 		int lo = 0, hi = 0;
 		for (int i = 0; i < nlocal; i++) {
-			int x0, nx;
-			split_even(G.nx, ntotal, first_slab + i, x0, nx);
+			const int x0 = split_x0[first_slab + i], nx = split_nx[first_slab + i];
 			if (i == 0) lo = x0;
 			hi = x0 + nx;
 			auto *s = new (std::nothrow) Slab<FT>();
@@ -450,7 +469,7 @@ struct Engine : cmc_adi3d {
 				{ const int device = sdev; CU_TRY(cudaSetDevice(sdev)); CU_TRY(cudaStreamCreateWithFlags(&sstream, cudaStreamNonBlocking)); }
 				s->owns_stream = true;
 			}
-			int rc = s->init(G, x0, nx, sdev, sstream, first_slab + i, ntotal);
+			int rc = s->init(G, x0, nx, ntotal > 1 ? nx_max : nx, sdev, sstream, first_slab + i, ntotal);
 			if (rc) return rc;
 			if (multi_device) { const int device = sdev; CU_TRY(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming)); }
 			dev_bytes += s->bytes;
@@ -479,8 +498,9 @@ struct Engine : cmc_adi3d {
 		CU_TRY(cudaMemsetAsync(d_timeout, 0, sizeof(int), stream));
 		CU_TRY(cudaStreamSynchronize(stream));
 		if (nccl) {
-			// peer memory needs the same arena layout on every rank (equal slabs); CMC_P2P=0 keeps the NCCL transport
-			const bool want = !(getenv("CMC_P2P") && atoi(getenv("CMC_P2P")) == 0) && G.nx % ntotal == 0;
+			// (every rank's arena has the layout of the largest slab, so one mapping per peer addresses everything);
+			// CMC_P2P=0 keeps the NCCL transport
+			const bool want = !(getenv("CMC_P2P") && atoi(getenv("CMC_P2P")) == 0);
 			if (want) p2p = peer_map_arenas(nccl, slabs[0]->arena, slabs[0]->arena_bytes, rank, nranks, &pm, stream) == 0;
 		}
 		return CMC_OK;
@@ -646,9 +666,9 @@ struct Engine : cmc_adi3d {
 			shared_free[1] = (long long)w[0]; shared_free[2] = (long long)w[1];
 		}
 		if (multi()) {
-			for (auto *s : slabs)
-				if (s->L.nx % 8 != 0 || s->L.nx > 512 || s->L.nx < 8)
-					return fail(CMC_ERR_UNSUPPORTED, "slab-decomposed runs need 8 <= planes per slab <= 512 and a multiple of 8");
+			for (int r = 0; r < nslabs_total; r++)
+				if (split_nx[r] > 512 || split_nx[r] < 8 || (split_nx[r] % 8 != 0 && r + 1 < nslabs_total))
+					return fail(CMC_ERR_UNSUPPORTED, "slab-decomposed runs need 8 <= planes per slab <= 512, and a multiple of 8 in every slab but the last");
 			if (!fast_sweep_supported(slabs[0]->L, 1) || !fast_sweep_supported(slabs[0]->L, 2))
 				return fail(CMC_ERR_UNSUPPORTED, "slab-decomposed runs need 8 <= dimy, dimz <= 512");
 		}
@@ -697,8 +717,9 @@ struct Engine : cmc_adi3d {
 			const size_t lpo = (size_t)A.lpo;
 			const int me = s->index;
 			if (push_mode()) {
-				// all slabs have the same shape here (emulation splits evenly or the caller's shapes are checked in build_lines)
-				const long long hi_plane = s->L.idx(s->L.nx, 0, 0), lo_plane = s->L.idx(-1, 0, 0);
+				// element (plane p, block 0, row 0, k 0) has the same offset in every slab's buffers (common block stride): the
+				// lower neighbour's upper guard plane is ITS plane nx, the upper neighbour's lower guard plane is plane -1
+				const long long hi_plane = me > 0 ? (long long)(split_nx[me - 1] + 1) * s->L.plane : 0, lo_plane = s->L.idx(-1, 0, 0);
 				for (int q = 0; q < 4; q++) {
 					if (me > 0) {
 						A.push_lo[q] = in_slab(s, me - 1, s->field[s->spare][q]) + hi_plane;
@@ -1063,8 +1084,7 @@ struct Engine : cmc_adi3d {
 		std::vector<int> lo(nslabs_total, ox), hi(nslabs_total, 0);
 		// output rows i whose source plane x = i*dimx/outdimx lies in slab r (TimeLayer3D.h:842-854)
 		for (int r = 0; r < nslabs_total; r++) {
-			int x0, nx;
-			split_even(G.nx, nslabs_total, r, x0, nx);
+			const int x0 = split_x0[r], nx = split_nx[r];
 			for (int i = 0; i < ox; i++) {
 				const int x = (int)((long long)i * G.nx / ox);
 				if (x >= x0 && x < x0 + nx) { if (i < lo[r]) lo[r] = i; if (i + 1 > hi[r]) hi[r] = i + 1; }
@@ -1171,7 +1191,7 @@ static int check_device(int device)
 // first_slab / nlocal / ntotal: which slabs of the x-split this handle holds
 static int create_impl(const cmc_grid_desc *grid, const cmc_fluid_params *params, int fp_bytes, int device,
                        int first_slab, int nlocal, int ntotal, const void *nccl_id, cmc_adi3d **out,
-                       const int *devices = nullptr)
+                       const int *devices = nullptr, const int *planes = nullptr)
 {
 	if (!grid || !params || !out) return fail(CMC_ERR_INVALID, "create: null argument");
 	*out = nullptr;
@@ -1202,6 +1222,7 @@ static int create_impl(const cmc_grid_desc *grid, const cmc_fluid_params *params
 		if (!s) return fail(CMC_ERR_INVALID, "out of host memory");
 		s->device = device; s->fp = 4; s->nccl = comm;
 		if (devs.size() > 1) { s->multi_device = true; s->slab_devices = devs; }
+		if (planes) s->planes_arg.assign(planes, planes + ntotal);
 		rc = s->init(grid, params, first_slab, nlocal, ntotal);
 		h = s;
 	} else {
@@ -1209,6 +1230,7 @@ static int create_impl(const cmc_grid_desc *grid, const cmc_fluid_params *params
 		if (!s) return fail(CMC_ERR_INVALID, "out of host memory");
 		s->device = device; s->fp = 8; s->nccl = comm;
 		if (devs.size() > 1) { s->multi_device = true; s->slab_devices = devs; }
+		if (planes) s->planes_arg.assign(planes, planes + ntotal);
 		rc = s->init(grid, params, first_slab, nlocal, ntotal);
 		h = s;
 	}
@@ -1254,6 +1276,89 @@ int cmc_adi3d_create_multi(const cmc_grid_desc *grid, const cmc_fluid_params *pa
 	if (!devices || n_devices < 1) return fail(CMC_ERR_INVALID, "create_multi: no devices");
 	if (n_devices == 1) return create_impl(grid, params, fp_bytes, devices[0], 0, 1, 1, nullptr, out);
 	return create_impl(grid, params, fp_bytes, devices[0], 0, n_devices, n_devices, nullptr, out, devices);
+}
+
+int cmc_adi3d_create_ex(const cmc_grid_desc *grid, const cmc_fluid_params *params, int fp_bytes, const cmc_decomp *d, cmc_adi3d **out)
+{
+	if (!d) return fail(CMC_ERR_INVALID, "create_ex: null decomposition");
+	const int n = d->n_slabs < 1 ? 1 : d->n_slabs;
+	switch (d->kind) {
+	case 0: return create_impl(grid, params, fp_bytes, d->device, 0, 1, 1, nullptr, out);
+	case 1: return create_impl(grid, params, fp_bytes, d->device, 0, n, n, nullptr, out, nullptr, d->planes);
+	case 2:
+		if (n > 1 && !d->nccl_unique_id) return fail(CMC_ERR_INVALID, "create_ex: nccl_unique_id required when n_slabs > 1");
+		return create_impl(grid, params, fp_bytes, d->device, d->rank, 1, n, n > 1 ? d->nccl_unique_id : nullptr, out, nullptr, d->planes);
+	case 3:
+		if (!d->devices) return fail(CMC_ERR_INVALID, "create_ex: no devices");
+		if (n == 1) return create_impl(grid, params, fp_bytes, d->devices[0], 0, 1, 1, nullptr, out);
+		return create_impl(grid, params, fp_bytes, d->devices[0], 0, n, n, nullptr, out, d->devices, d->planes);
+	}
+	return fail(CMC_ERR_INVALID, "create_ex: unknown decomposition kind");
+}
+
+// Grid3D::SplitSegments_X (reference Grid3D.cpp:148-235) with the cuts on multiples of 8 planes
+int cmc_split_planes(int policy, const cmc_grid_desc *grid, const int32_t *type, int n, int32_t *planes_out)
+{
+	if (!grid || !planes_out || n < 1) return fail(CMC_ERR_INVALID, "split_planes: bad argument");
+	const int dimx = grid->dimx, dimy = grid->dimy, dimz = grid->dimz;
+	if (dimx < 8 * n && n > 1) return fail(CMC_ERR_UNSUPPORTED, "split_planes: fewer than 8 planes per slab");
+	std::vector<int> planes;
+	if (policy == CMC_SPLIT_EVEN_X || n == 1) {
+		split_default(dimx, n, planes);
+	} else {
+		if (!type) return fail(CMC_ERR_INVALID, "split_planes: node types required for this policy");
+		std::vector<double> w((size_t)dimx, 0.0);
+		double total = 0.0;
+		auto T = [&](int i, int j, int k) { return type[((size_t)i * dimy + j) * dimz + k]; };
+		if (policy == CMC_SPLIT_EVEN_VOLUME) {
+			for (int i = 0; i < dimx; i++) {
+				double c = 0.0;
+				for (size_t id = (size_t)i * dimy * dimz, e = id + (size_t)dimy * dimz; id < e; id++) c += type[id] == CMC_NODE_IN;
+				w[i] = c; total += c;
+			}
+		} else if (policy == CMC_SPLIT_EVEN_SEGMENTS) {
+			// the segment rule of GenerateListSegments (Grid3D.cpp:47-127): a run of NODE_IN cells closed by a non-IN cell
+			auto scan = [&](int len, auto cell, auto emit) {
+				int state = 0, start = 0;
+				for (int p = 0; p + 1 < len; p++) {
+					if (cell(p + 1) == CMC_NODE_IN) { if (!state) start = p; state = 1; }
+					else if (state) { emit(start, p + 1); state = 0; }
+				}
+			};
+			for (int i = 0; i < dimx; i++) {
+				for (int k = 0; k < dimz; k++) scan(dimy, [&](int p) { return T(i, p, k); }, [&](int, int) { w[i] += 1.0; total += 1.0; });
+				for (int j = 0; j < dimy; j++) scan(dimz, [&](int p) { return T(i, j, p); }, [&](int, int) { w[i] += 1.0; total += 1.0; });
+			}
+			for (int j = 0; j < dimy; j++)
+				for (int k = 0; k < dimz; k++)
+					scan(dimx, [&](int p) { return T(p, j, k); }, [&](int a, int b) {
+						const double sz = (double)(b - a + 1);
+						for (int i = a; i <= b; i++) w[i] += 1.0 / sz;
+						total += 1.0;
+					});
+		} else
+			return fail(CMC_ERR_INVALID, "split_planes: unknown policy");
+		// the reference cuts where the running load passes total / n (Grid3D.cpp:214-229); here: cut r where the cumulated
+		// load reaches r * total / n, moved to the nearest multiple of 8 that leaves every slab at least 8 planes
+		const double per = total / n;
+		planes.assign(n, 0);
+		int prev = 0, i = 0;
+		double cum = 0.0;
+		for (int r = 1; r < n; r++) {
+			while (i < dimx && cum + w[i] <= per * r) cum += w[i++];
+			int cut = (i + 4) / 8 * 8;
+			if (cut < prev + 8) cut = prev + 8;
+			const int room = dimx - 8 * (n - r);               // the slabs still to come need 8 planes each
+			if (cut > room) cut = room / 8 * 8;
+			if (cut < prev + 8) return fail(CMC_ERR_UNSUPPORTED, "split_planes: the grid is too small for this many slabs");
+			planes[r - 1] = cut - prev;
+			prev = cut;
+		}
+		planes[n - 1] = dimx - prev;
+		if (planes[n - 1] < 8) return fail(CMC_ERR_UNSUPPORTED, "split_planes: the grid is too small for this many slabs");
+	}
+	for (int r = 0; r < n; r++) planes_out[r] = planes[r];
+	return CMC_OK;
 }
 
 int cmc_nccl_unique_id(void *id128)

@@ -46,13 +46,16 @@ struct Layout {
 	{
 		return ((j & jbm) == 0 && j > 0) ? bstride - (long long)jbm * nzp : (long long)nzp;
 	}
-	// geometry of a slab of `lnx` planes of a grid ny x nz (block height 2^jbs_, or one block when jbs_ >= 30)
-	__host__ void shape(int lnx, int ny_, int nz_, int nzp_, int jbs_)
+	// geometry of a slab of `lnx` planes of a grid ny x nz (block height 2^jbs_, or one block when jbs_ >= 30).  alloc_nx
+	// (>= lnx): planes a y-block has room for - the slabs of one grid may hold different numbers of planes but share the
+	// block stride of the largest one, so that an element has the same offset in every slab's buffers (stores into a
+	// neighbouring slab's guard planes, SweepArgs::push_*, need nothing but the neighbour's plane count)
+	__host__ void shape(int lnx, int ny_, int nz_, int nzp_, int jbs_, int alloc_nx = 0)
 	{
 		nx = lnx; ny = ny_; nz = nz_; nzp = nzp_;
 		if (jbs_ >= 30 || (1 << jbs_) >= ny_) { jbs = 30; jbm = (1 << 30) - 1; nblk = 1; plane = (long long)ny_ * nzp_; }
 		else { jbs = jbs_; jbm = (1 << jbs_) - 1; nblk = (ny_ + jbm) >> jbs_; plane = (long long)(1 << jbs_) * nzp_; }
-		bstride = (long long)(lnx + 2) * plane;
+		bstride = (long long)((alloc_nx > lnx ? alloc_nx : lnx) + 2) * plane;
 		total = (long long)nblk * bstride;
 	}
 };

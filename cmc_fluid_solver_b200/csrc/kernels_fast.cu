@@ -83,7 +83,9 @@ __global__ void __launch_bounds__(GP * NL, (GP * NL <= 64 && DIR == 2 && GP == 6
 	// slab-coupled x-lines: global line id, its owner rank for the interface solve, and the first / last chunk
 	int xo = 0;                     // element offset of this line's interface values: owner * 8 * lpo + line_in_owner
 	FT *cto = nullptr;              // MODE 1: this line's slot in its owner's coefficient table
-	const int GL = (MODE != 0) ? A.L.nx / M : GP;    // chunks that hold real rows (nx % 8 == 0 is required)
+	// chunks that hold real rows (every slab but the last holds a multiple of 8 planes; the ragged last chunk of the last
+	// slab ends in identity rows and has no neighbour above, so its "last row" coupling is zero by construction)
+	const int GL = (MODE != 0) ? (A.L.nx + M - 1) / M : GP;
 	if (MODE != 0) {
 		const int ktiles = (L.nz + NL - 1) / NL;
 		const int j = blockIdx.x / ktiles, k = min((blockIdx.x % ktiles) * NL + l, L.nz - 1);
@@ -536,9 +538,10 @@ template <typename FT, int MODE>
 static bool launch_x_mode(const SweepArgs<FT> &A, cudaStream_t s)
 {
 	const Layout &L = A.L;
-	if (!fast_sweep_supported(L, 0) || L.nx % M != 0) return false;
+	const bool last_slab = L.x0 + L.nx == L.gx;
+	if (!fast_sweep_supported(L, 0) || (L.nx % M != 0 && !last_slab)) return false;
 	int GP = 4;
-	while (GP < L.nx / M) GP <<= 1;
+	while (GP < (L.nx + M - 1) / M) GP <<= 1;
 	switch (GP) {
 	case 4: launch_one<FT, 0, 4, MODE>(A, s, nullptr, false); break;
 	case 8: launch_one<FT, 0, 8, MODE>(A, s, nullptr, false); break;

@@ -65,7 +65,7 @@ static EncodeTiledFn encode_fn()
 // One map per (field buffer, direction, layout): the layers rotate through a handful of physical buffers, so the maps
 // are built once and cached.
 struct MapKey {
-	const void *ptr; int dir, fp, gp, nx, ny, nz, jbs;
+	const void *ptr; long long bstride; int dir, fp, gp, nx, ny, nz, jbs;
 	bool operator<(const MapKey &o) const { return memcmp(this, &o, sizeof(MapKey)) < 0; }
 };
 
@@ -76,7 +76,7 @@ static bool tensor_map_for(const FT *field, const Layout &L, int dir, int GP, CU
 	static std::mutex mu;
 	MapKey key;
 	memset(&key, 0, sizeof key);
-	key.ptr = field; key.dir = dir; key.fp = (int)sizeof(FT); key.gp = GP; key.nx = L.nx; key.ny = L.ny; key.nz = L.nz; key.jbs = L.jbs;
+	key.ptr = field; key.bstride = L.bstride; key.dir = dir; key.fp = (int)sizeof(FT); key.gp = GP; key.nx = L.nx; key.ny = L.ny; key.nz = L.nz; key.jbs = L.jbs;
 	std::lock_guard<std::mutex> lock(mu);
 	auto it = cache.find(key);
 	if (it != cache.end()) { *out = it->second; return true; }

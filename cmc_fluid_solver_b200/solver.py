@@ -19,7 +19,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import FluidParams, GridDesc, LIB_PATH, load_library
+from ._lib import Decomp, FluidParams, GridDesc, LIB_PATH, load_library
 from .cases import Case
 
 CMC_OK, CMC_ERR_DIVERGED = 0, 1
@@ -69,9 +69,10 @@ class AdiSolver3D:
 
     # -- Solver3D::Init ------------------------------------------------------------------------------------
     def Init(self, case: Case, device: int = 0, mode: str = "fast", rank: int = 0, nranks: int = 1, nccl_id: bytes = None,
-             emulate_slabs: int = 0, devices=None):
+             emulate_slabs: int = 0, devices=None, planes=None):
         """rank/nranks/nccl_id: one x-slab per process (NCCL).  emulate_slabs=N: all N slabs in this handle, on one GPU.
-        devices=[d0, d1, ...]: all slabs in this handle, one per device (the reference's "GPU <n>" mode)."""
+        devices=[d0, d1, ...]: all slabs in this handle, one per device (the reference's "GPU <n>" mode).
+        planes=[n0, n1, ...]: x-planes per slab (e.g. from split_planes()); default = even split on multiples of 8."""
         lib = load_library()
         self.case = case
         self.fp = case.fp_bytes
@@ -79,7 +80,21 @@ class AdiSolver3D:
         g = GridDesc(case.dimx, case.dimy, case.dimz, case.dx, case.dy, case.dz)
         p = FluidParams(case.v_T, case.v_vis, case.t_vis, case.t_phi)
         h = C.c_void_p()
-        if devices is not None and len(devices) > 1:
+        if planes is not None:
+            nsl = len(planes)
+            pl = (C.c_int32 * nsl)(*planes)
+            d = Decomp()
+            d.n_slabs, d.device, d.rank, d.planes = nsl, device, rank, pl
+            if devices is not None and len(devices) > 1:
+                dv = (C.c_int32 * len(devices))(*devices)
+                d.kind, d.devices = 3, dv
+            elif nranks > 1:
+                buf = C.create_string_buffer(nccl_id, 128)
+                d.kind, d.nccl_unique_id = 2, C.cast(buf, C.c_void_p)
+            else:
+                d.kind = 1
+            _check(lib.cmc_adi3d_create_ex(C.byref(g), C.byref(p), self.fp, C.byref(d), C.byref(h)))
+        elif devices is not None and len(devices) > 1:
             arr = (C.c_int * len(devices))(*devices)
             _check(lib.cmc_adi3d_create_multi(C.byref(g), C.byref(p), self.fp, arr, len(devices), C.byref(h)))
         elif emulate_slabs > 1:
@@ -349,6 +364,18 @@ def solve_tridiagonal_batch(a, b, c, d, mode="exact"):
     m = {"fast": MODE_FAST, "exact": MODE_EXACT}[mode]
     _check(load_library().cmc_solve_tridiagonal_batch(a.itemsize, m, nsys, n, _ptr(a), _ptr(b), _ptr(c), _ptr(d), _ptr(x)))
     return x
+
+
+SPLIT_EVEN_X, SPLIT_EVEN_SEGMENTS, SPLIT_EVEN_VOLUME = 0, 1, 2
+
+
+def split_planes(case: Case, n_slabs: int, policy: int = SPLIT_EVEN_X):
+    """x-planes per slab for `n_slabs` slabs (Grid3D::Split: EVEN_X / EVEN_SEGMENTS / EVEN_VOLUME, cuts on multiples of 8)."""
+    g = GridDesc(case.dimx, case.dimy, case.dimz, case.dx, case.dy, case.dz)
+    t = np.ascontiguousarray(case.type, dtype=np.int32)
+    out = (C.c_int32 * n_slabs)()
+    _check(load_library().cmc_split_planes(policy, C.byref(g), _ptr(t), n_slabs, out))
+    return list(out)
 
 
 def nccl_unique_id() -> bytes:

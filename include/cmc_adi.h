@@ -98,6 +98,29 @@ int cmc_adi3d_create_emulated(const cmc_grid_desc *grid, const cmc_fluid_params 
  * events.  All other entry points work as on a single-GPU handle (whole-grid arrays in, whole layers out). */
 int cmc_adi3d_create_multi(const cmc_grid_desc *grid, const cmc_fluid_params *params, int fp_bytes,
                            const int *devices, int n_devices, cmc_adi3d **out);
+/* ---- how the grid is cut into x-slabs: Grid3D::Split / SplitSegments_X (Grid3D.cpp:148-235), GPUplan::splitEven1D
+ * (GPUplan.cpp:122-141), PARAplan::split1D (PARAplan.cpp:89-126).  planes_out[r] = x-planes of slab r.  The cut positions of
+ * every policy are moved to multiples of 8 planes (the partitioned x-sweep works on 8-row chunks), the last slab takes the
+ * rest; every slab holds at least 8 planes.
+ *   CMC_SPLIT_EVEN_X        equal numbers of planes (the default of every cmc_adi3d_create_* without a split)
+ *   CMC_SPLIT_EVEN_SEGMENTS equal numbers of line segments: a plane weighs the y- and z-segments that start in it plus its
+ *                           share 1/size of every x-segment that crosses it (Grid3D.cpp:167-187)
+ *   CMC_SPLIT_EVEN_VOLUME   equal numbers of NODE_IN cells (Grid3D.cpp:189-202)
+ * `type` = the node types of the whole grid (dimx*dimy*dimz, CMC_NODE_*); not read for CMC_SPLIT_EVEN_X. */
+enum { CMC_SPLIT_EVEN_X = 0, CMC_SPLIT_EVEN_SEGMENTS = 1, CMC_SPLIT_EVEN_VOLUME = 2 };
+int cmc_split_planes(int policy, const cmc_grid_desc *grid, const int32_t *type, int n_slabs, int32_t *planes_out);
+
+/* the general constructor: any of the decompositions above with a caller-supplied split (planes[n_slabs], e.g. from
+ * cmc_split_planes; NULL = CMC_SPLIT_EVEN_X).  kind: 0 one slab on `device`; 1 n_slabs emulated on `device`; 2 slab `rank`
+ * of n_slabs in this process on `device`, the others in other processes (nccl_unique_id); 3 all n_slabs in this process,
+ * slab i on devices[i]. */
+typedef struct cmc_decomp {
+	int32_t kind, device, n_slabs, rank;
+	const void *nccl_unique_id;
+	const int32_t *devices;
+	const int32_t *planes;
+} cmc_decomp;
+int cmc_adi3d_create_ex(const cmc_grid_desc *grid, const cmc_fluid_params *params, int fp_bytes, const cmc_decomp *decomp, cmc_adi3d **out);
 int cmc_adi3d_destroy(cmc_adi3d *h);           /* ~AdiSolver3D (AdiSolver3D.cpp:153-158) */
 
 /* planes held by this handle: global x range [x0, x0+nx) */

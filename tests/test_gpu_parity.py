@@ -276,11 +276,61 @@ def test_slab_decomposition_emulated(oracle_mod, nslabs, fp):
 
 
 def test_slab_decomposition_rejects_unsupported_shapes():
-    case = channel_case(36, 24, 24, baffle=False)          # 18 planes per slab: not a multiple of 8
+    case = channel_case(12, 24, 24, baffle=False)          # 2 slabs of 8 + 4 planes: fewer than 8 planes in a slab
     s = AdiSolver3D().Init(case, emulate_slabs=2)
     with pytest.raises(CmcError) as ei:
         s.CreateSegments()
     assert ei.value.code == -4
+    s.close()
+
+
+@pytest.mark.parametrize("fp", [8, 4])
+@pytest.mark.parametrize("planes", [None, [16, 32, 21], [40, 8, 21], "segments", "volume"])
+def test_unequal_slabs_against_oracle(oracle_mod, planes, fp):
+    """Slabs of different sizes (every slab but the last a multiple of 8 planes, the last one ragged): default split of a
+    69-plane grid, hand-made splits, and the reference's load-balancing policies (Grid3D::SplitSegments_X: EVEN_SEGMENTS,
+    EVEN_VOLUME) - fused guard-plane stores into neighbours of a different size, partitioned x-solve with a ragged last
+    chunk, distributed residual and readback - against the oracle and the single-slab run."""
+    from cmc_fluid_solver_b200.solver import SPLIT_EVEN_SEGMENTS, SPLIT_EVEN_VOLUME, split_planes
+    O = oracle_mod
+    case = channel_case(69, 40, 44, fp_bytes=fp, depth_var=0.25)
+    case.outdims = (9, 7, 5)
+    if planes == "segments":
+        planes = split_planes(case, 3, SPLIT_EVEN_SEGMENTS)
+    elif planes == "volume":
+        planes = split_planes(case, 3, SPLIT_EVEN_VOLUME)
+    ora = O.Oracle3D(case); ora.create_segments()
+    one = AdiSolver3D().Init(case, mode="fast"); one.CreateSegments()
+    many = AdiSolver3D().Init(case, mode="fast", emulate_slabs=3, planes=planes) if planes else AdiSolver3D().Init(case, mode="fast", emulate_slabs=3)
+    many.CreateSegments()
+    assert [many.numSegs(d) for d in range(3)] == [len(ora.segments(d)) for d in range(3)]
+    for i in range(4):
+        ora.update_boundaries(); one.UpdateBoundaries(); many.UpdateBoundaries()
+        e_ref = ora.time_step(case.dt, case.num_global, case.num_local, True)
+        e1 = one.TimeStep(case.dt, case.num_global, case.num_local, True)
+        e = many.TimeStep(case.dt, case.num_global, case.num_local, True)
+        assert abs(e - e_ref) <= (1e-5 if fp == 4 else 1e-9) * abs(e_ref) and abs(e - e1) <= (1e-5 if fp == 4 else 1e-9) * abs(e1)
+        if i == 1:
+            v_ref, T_ref = ora.get_layer(*case.outdims)
+            v, T = many.GetLayer(*case.outdims)
+            assert np.allclose(v, v_ref, rtol=0, atol=TOL[fp] * 1e5) and np.allclose(T, T_ref, rtol=0, atol=TOL[fp] * 1e5)
+            one.GetLayer(*case.outdims)
+        _check_fields(O, ora, many, case, "fast", f"3 unequal slabs {planes}, step {i}")
+        _assert_close([one.read_field(LAYER_CUR, q) for q in range(4)], [many.read_field(LAYER_CUR, q) for q in range(4)], fp, "1 slab vs 3")
+    one.close(); many.close()
+
+
+@pytest.mark.parametrize("name", ["nupipe_f64", "nupipe_f32"])
+def test_reference_case_on_three_slabs(name):
+    """The reference's own shipped case data/3D/example_tests/non_uniform_pipe (53 x 53 x 52 / 54 x 54 x 52: not divisible
+    by anything) cut into three slabs, against the golden vector written by the reference CPU solver."""
+    case, exp = load_golden(name)
+    s = AdiSolver3D().Init(case, mode="fast", emulate_slabs=3)
+    s.CreateSegments()
+    errs, layers = drive(s, case, exp["steps"])
+    got = [s.read_field(LAYER_CUR, q).ravel() for q in range(4)]
+    _assert_close(exp["last"], got, case.fp_bytes, name + " on 3 slabs")
+    assert np.allclose(errs, exp["err"], rtol=1e-5 if case.fp_bytes == 4 else 1e-9, atol=0)
     s.close()
 
 
