@@ -11,7 +11,7 @@ LIB_PATH = PKG / "libcmcadi.so"
 SYMBOLS = [
     "cmc_last_error", "cmc_abi_version", "cmc_device_count",
     "cmc_adi3d_create", "cmc_nccl_unique_id", "cmc_adi3d_create_dist", "cmc_adi3d_create_emulated", "cmc_adi3d_create_multi", "cmc_adi3d_create_ex", "cmc_split_planes", "cmc_adi3d_destroy", "cmc_adi3d_slab",
-    "cmc_adi3d_set_nodes", "cmc_adi3d_set_nodes_aos", "cmc_adi3d_update_nodes", "cmc_adi3d_update_nodes_aos", "cmc_adi3d_build_lines", "cmc_adi3d_num_segments",
+    "cmc_adi3d_set_nodes", "cmc_adi3d_set_nodes_aos", "cmc_adi3d_set_nodes_slab", "cmc_adi3d_update_nodes", "cmc_adi3d_update_nodes_aos", "cmc_adi3d_build_lines", "cmc_adi3d_num_segments",
     "cmc_adi3d_update_boundaries", "cmc_adi3d_time_step", "cmc_adi3d_get_layer",
     "cmc_adi3d_set_option", "cmc_adi3d_get_option",
     "cmc_adi3d_read_field", "cmc_adi3d_write_field", "cmc_adi3d_step_prologue", "cmc_adi3d_solve_direction",
@@ -67,6 +67,7 @@ def load_library() -> C.CDLL:
         "cmc_adi3d_slab": [vp, P(i32), P(i32)],
         "cmc_adi3d_set_nodes": [vp, vp, vp, vp, vp, vp, vp, vp],
         "cmc_adi3d_set_nodes_aos": [vp, vp, C.c_size_t],
+        "cmc_adi3d_set_nodes_slab": [vp, vp, vp, vp, vp, vp, vp, vp, i32],
         "cmc_adi3d_update_nodes": [vp, vp, vp, vp, vp, vp, vp, vp],
         "cmc_adi3d_update_nodes_aos": [vp, vp, C.c_size_t],
         "cmc_adi3d_build_lines": [vp],

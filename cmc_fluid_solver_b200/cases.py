@@ -44,6 +44,9 @@ class Case:
     baseT: float = 1.0
     outdims: tuple = (0, 0, 0)
     snapshots: list = field(default_factory=list)
+    # slab-local cases: the node arrays cover only the x-planes [x_lo, x_hi) of the dimx x dimy x dimz grid
+    x_lo: int = None
+    x_hi: int = None
 
     @property
     def shape(self):
@@ -61,6 +64,11 @@ class Case:
     def n_in(self):
         return int((self.type == NODE_IN).sum())
 
+    @property
+    def planes(self):
+        """x-planes the node arrays cover (dimx unless the case is slab-local)."""
+        return self.dimx if self.x_lo is None else self.x_hi - self.x_lo
+
 
 def fluid_params(Re=200.0, Pr=0.72, lam=1.4, fp_bytes=8):
     """Common::FluidParams(Re, Pr, lambda) (reference src/Common/Geometry.h:545-552), rounded to FTYPE."""
@@ -71,11 +79,13 @@ def fluid_params(Re=200.0, Pr=0.72, lam=1.4, fp_bytes=8):
 
 def channel_case(dimx, dimy, dimz, fp_bytes=8, baffle=True, depth_var=0.2, h=None, dt=0.1,
                  num_global=4, num_local=2, Re=200.0, Pr=0.72, lam=1.4, active_dimz=None,
-                 inflow=1.0, baseT=1.0) -> Case:
+                 inflow=1.0, baseT=1.0, x_range=None) -> Case:
     """Synthetic masked channel: inflow valve at low x, free outflow valve at high x, no-slip side walls,
     optional wall-attached baffle (obstacle; keeps <= 2 segments per row) and the reference's bottom
     perturbation (`depth_var`), extruded along z exactly like Grid3D::Prepare2D.  A NODE_OUT shell is kept
-    on every domain face.  Deterministic - no RNG."""
+    on every domain face.  Deterministic - no RNG.
+    x_range=(lo, hi): only the x-planes [lo, hi) of the same grid (a slab-local case for cmc_adi3d_set_nodes_slab: no
+    process has to build the whole grid)."""
     ft = np.float32 if fp_bytes == 4 else np.float64
     if h is None:
         h = 1.1 / max(dimx, dimy, dimz)
@@ -103,18 +113,22 @@ def channel_case(dimx, dimy, dimz, fp_bytes=8, baffle=True, depth_var=0.2, h=Non
         t2[i1, 1:j1 + 1] = NODE_BOUND
         t2[i0:i1 + 1, j1] = NODE_BOUND
         t2[i0:i1 + 1, 1] = NODE_BOUND
-    N = dimx * dimy * dimz
-    typ = np.full((dimx, dimy, dimz), NODE_OUT, dtype=np.int32)
-    bcv = np.zeros((dimx, dimy, dimz), dtype=np.int32)
-    bct = np.zeros((dimx, dimy, dimz), dtype=np.int32)
-    vx = np.zeros((dimx, dimy, dimz), dtype=ft)
-    T = np.zeros((dimx, dimy, dimz), dtype=ft)
     ii, jj = np.meshgrid(np.arange(dimx), np.arange(dimy), indexing="ij")
     x = -1 + 2 * ii / dimx
     y = -1 + 2 * jj / dimy
     z = 1.0 - (x * x + y * y) * 0.5
     height = max(az - 2 - 2, 0)
     bottom = 1 + (depth_var * z * height).astype(np.int64)
+    # the 2D outline is cheap and always built whole; the extrusion along z covers the requested planes only
+    lo, hi = x_range if x_range is not None else (0, dimx)
+    t2, vel2, bottom = t2[lo:hi], vel2[lo:hi], bottom[lo:hi]
+    px = hi - lo
+    N = px * dimy * dimz
+    typ = np.full((px, dimy, dimz), NODE_OUT, dtype=np.int32)
+    bcv = np.zeros((px, dimy, dimz), dtype=np.int32)
+    bct = np.zeros((px, dimy, dimz), dtype=np.int32)
+    vx = np.zeros((px, dimy, dimz), dtype=ft)
+    T = np.zeros((px, dimy, dimz), dtype=ft)
     kk = np.arange(dimz)[None, None, :]
     col = (t2 != NODE_OUT)[:, :, None]
     bot = bottom[:, :, None]
@@ -140,7 +154,8 @@ def channel_case(dimx, dimy, dimz, fp_bytes=8, baffle=True, depth_var=0.2, h=Non
     zero = np.zeros(N, dtype=ft)
     return Case(dimx, dimy, dimz, h, h, h, p["v_T"], p["v_vis"], p["t_vis"], p["t_phi"], float(ft(dt)),
                 num_global, num_local, fp_bytes, type=typ.ravel(), bc_vel=bcv.ravel(), bc_temp=bct.ravel(),
-                vx=vx.ravel(), vy=zero, vz=zero.copy(), T=T.ravel(), baseT=baseT)
+                vx=vx.ravel(), vy=zero, vz=zero.copy(), T=T.ravel(), baseT=baseT,
+                x_lo=None if x_range is None else lo, x_hi=None if x_range is None else hi)
 
 
 def moving_baffle_case(dimx, dimy, dimz, fp_bytes=8, shift=0, **kw) -> Case:

@@ -51,6 +51,8 @@ struct cmc_adi3d {
 	virtual ~cmc_adi3d() {}
 	virtual int set_nodes(const int32_t *type, const int32_t *bc_vel, const int32_t *bc_temp,
 	                      const void *vx, const void *vy, const void *vz, const void *T, size_t aos_stride, bool keep_layers) = 0;
+	virtual int set_nodes_slab(const int32_t *type, const int32_t *bc_vel, const int32_t *bc_temp,
+	                           const void *vx, const void *vy, const void *vz, const void *T, int halo, bool keep_layers) = 0;
 	virtual int build_lines() = 0;
 	virtual int update_boundaries() = 0;
 	virtual int time_step(double dt, int ng, int nl, int ce, double *err, bool async) = 0;
@@ -84,6 +86,7 @@ struct cmc_adi3d {
 		return (strchr(env, 'x') ? 1 : 0) | (strchr(env, 'y') ? 2 : 0);
 	}
 	bool have_nodes = false, have_lines = false;
+	bool window_counts = false;     // the x-segment count was taken per slab (slab-local node arrays)
 
 	// optional per-kernel-kind device timing (cmc_adi3d_set_option "profile"): CUDA event pairs on `stream`
 	int profile = 0;
@@ -169,7 +172,9 @@ struct Slab {
 	int spare = 4;
 	FT *nodev[4] = {};
 	uint8_t *role[3] = {};
-	uint8_t *ncode = nullptr;      // whole-grid node codes (only until the line descriptors are built)
+	uint8_t *ncode = nullptr;      // node codes (only until the line descriptors are built): the whole grid, or a window of it
+	int ncode_w0 = 0;              // global plane held by plane 0 of ncode
+	bool ncode_window = false;     // ncode covers [x0 - 2, x0 + nx + 2) (clipped to the grid) instead of the whole grid
 	FT *cv = nullptr, *cT = nullptr;
 	double *d_partials = nullptr, *d_err2 = nullptr, *d_sums8 = nullptr;
 	unsigned long long *d_segcount = nullptr;
@@ -284,15 +289,17 @@ struct Slab {
 	}
 
 	// dense host (whole grid) -> padded device slab, plus the neighbour planes into the guard (halo) planes
-	int upload_nodes(const uint8_t *code, size_t N, const FT *const src[4], bool keep_layers)
+	// w0 = global plane of host plane 0 (0: the arrays cover the whole grid)
+	int upload_nodes(const uint8_t *code, size_t N, const FT *const src[4], bool keep_layers, int w0 = 0, bool window = false)
 	{
 		if (ncode) { cudaFree(ncode); ncode = nullptr; }
 		CU_TRY(cudaMalloc((void **)&ncode, N));
 		CU_TRY(cudaMemcpyAsync(ncode, code, N, cudaMemcpyHostToDevice, stream));
+		ncode_w0 = w0; ncode_window = window;
 		for (int q = 0; q < 4; q++) {
 			CU_TRY(cudaMemsetAsync(nodev[q], 0, sizeof(FT) * (size_t)L.total, stream));
 			const int p0 = L.x0 > 0 ? -1 : 0, p1 = L.x0 + L.nx < G.nx ? L.nx + 1 : L.nx;   // include the halo planes that exist
-			int rc = copy_planes(nodev[q], src[q], nullptr, p0, p1, 0);
+			int rc = copy_planes(nodev[q], src[q], nullptr, p0, p1, w0);
 			if (rc) return rc;
 		}
 		if (keep_layers) return CMC_OK;        // Grid3D::Prepare(t): new nodes, same time layers
@@ -631,6 +638,42 @@ struct Engine : cmc_adi3d {
 		return CMC_OK;
 	}
 
+	// cmc_adi3d_set_nodes_slab: the arrays cover the planes [x0 - hlo, x0 + nx + hhi) of the grid only, hlo = min(halo, x0),
+	// hhi = min(halo, dimx - x0 - nx), halo >= 2 (the line descriptors of a cell look two cells ahead, the guard planes
+	// need one) - what Grid3D::Init_GPU uploads per device (node slices, Grid3D.cpp:567-596)
+	int set_nodes_slab(const int32_t *type, const int32_t *bc_vel, const int32_t *bc_temp,
+	                   const void *vx, const void *vy, const void *vz, const void *T, int halo, bool keep_layers) override
+	{
+		if (slabs.size() != 1) return fail(CMC_ERR_INVALID, "set_nodes_slab: the handle holds several slabs (it takes whole-grid arrays: cmc_adi3d_set_nodes)");
+		if (halo < 2) return fail(CMC_ERR_INVALID, "set_nodes_slab: halo must be at least 2 planes");
+		if (keep_layers && !have_nodes) return fail(CMC_ERR_INVALID, "update_nodes_slab: call cmc_adi3d_set_nodes_slab first");
+		CU_TRY(cudaSetDevice(device));
+		Slab<FT> *s = slabs[0];
+		const int hlo = std::min(halo, s->L.x0), hhi = std::min(halo, G.nx - s->L.x0 - s->L.nx);
+		const int w0 = s->L.x0 - hlo, planes = hlo + s->L.nx + hhi;
+		const size_t N = (size_t)planes * G.ny * G.nz;
+		std::vector<uint8_t> code(N);
+		uint8_t *cd = code.data();
+		std::atomic<int> bad(0);
+		parallel_for(N, [&](size_t a, size_t b) {
+			for (size_t id = a; id < b; id++) {
+				if (type[id] < 0 || type[id] > 3) bad = 1;
+				if ((bc_vel[id] != CMC_BC_NOSLIP && bc_vel[id] != CMC_BC_FREE) || (bc_temp[id] != CMC_BC_NOSLIP && bc_temp[id] != CMC_BC_FREE)) bad = 2;
+				cd[id] = (uint8_t)((type[id] & 3) | (bc_vel[id] == CMC_BC_FREE ? 4 : 0) | (bc_temp[id] == CMC_BC_FREE ? 8 : 0));
+			}
+		});
+		if (bad == 1) return fail(CMC_ERR_INVALID, "set_nodes_slab: node type out of range");
+		if (bad == 2) return fail(CMC_ERR_INVALID, "set_nodes_slab: boundary-condition type out of range");
+		const FT *src[4] = {(const FT *)vx, (const FT *)vy, (const FT *)vz, (const FT *)T};
+		int rc = s->upload_nodes(code.data(), N, src, keep_layers, w0, true);
+		if (rc) return rc;
+		CU_TRY(cudaStreamSynchronize(stream));
+		halos_dirty = true;
+		have_nodes = true; have_lines = false;
+		if (!keep_layers) { diffError = 0.0; err_pending = 0; worst_err = 0.0; }
+		return CMC_OK;
+	}
+
 	int build_lines() override
 	{
 		if (!have_nodes) return fail(CMC_ERR_INVALID, "build_lines: call cmc_adi3d_set_nodes first");
@@ -641,29 +684,43 @@ struct Engine : cmc_adi3d {
 			cudaStream_t stream = s->stream;
 			CU_TRY(cudaMemsetAsync(s->d_segcount, 0, 8 * sizeof(unsigned long long), stream));
 			for (int d = 0; d < 3; d++) CU_TRY(cudaMemsetAsync(s->role[d], 0, (size_t)s->L.total, stream));
-			launch_role_type_bits(G, s->ncode, s->L, s->role[0], s->role[1], s->role[2], stream, &launches);
-			for (int d = 0; d < 3; d++) launch_build_roles(d, G, s->ncode, s->L, s->role[d], s->d_segcount + d, stream, &launches);
+			// the kernels address the node codes by GLOBAL plane: a window is handed over with its base shifted accordingly
+			// (only planes inside the window are touched)
+			const uint8_t *nc = s->ncode - (long long)s->ncode_w0 * G.ny * G.nz;
+			launch_role_type_bits(G, nc, s->L, s->role[0], s->role[1], s->role[2], stream, &launches);
+			if (s->ncode_window) {
+				// x-lines leave the window: local rule instead of the scan; valid when no fluid cell lies on an x-face of the grid
+				if (s->L.x0 == 0) launch_count_in_plane(G, nc, 0, s->d_segcount + 7, stream);
+				if (s->L.x0 + s->L.nx == G.nx) launch_count_in_plane(G, nc, G.nx - 1, s->d_segcount + 7, stream);
+				launch_build_roles_x_local(G, nc, s->L, s->role[0], s->d_segcount + 0, stream, &launches);
+				for (int d = 1; d < 3; d++) launch_build_roles(d, G, nc, s->L, s->role[d], s->d_segcount + d, stream, &launches);
+			} else
+				for (int d = 0; d < 3; d++) launch_build_roles(d, G, nc, s->L, s->role[d], s->d_segcount + d, stream, &launches);
 			unsigned long long h[8];
 			CU_TRY(cudaMemcpyAsync(h, s->d_segcount, sizeof h, cudaMemcpyDeviceToHost, stream));
 			CU_TRY(cudaStreamSynchronize(stream));
 			CU_TRY(cudaGetLastError());
-			// x-lines are scanned over the whole grid by every slab (same count everywhere); y/z-lines per slab
-			num_segs[0] = (long long)h[0]; shared_free[0] = (long long)h[4];
+			if (s->ncode_window && h[7])
+				return fail(CMC_ERR_UNSUPPORTED, "set_nodes_slab: NODE_IN cells on an x-face of the grid (slab-local node arrays need the NODE_OUT rim the reference's loaders produce; use cmc_adi3d_set_nodes)");
+			window_counts = s->ncode_window;
+			// x-lines are scanned over the whole grid by every slab (same count everywhere) - or, from a window, counted by
+			// the slab that holds their end cell; y/z-lines per slab
+			if (s->ncode_window) { num_segs[0] += (long long)h[0]; shared_free[0] += (long long)h[4]; }
+			else { num_segs[0] = (long long)h[0]; shared_free[0] = (long long)h[4]; }
 			for (int d = 1; d < 3; d++) { num_segs[d] += (long long)h[d]; shared_free[d] += (long long)h[4 + d]; }
 			cudaFree(s->ncode); s->ncode = nullptr;          // the descriptors carry everything from here on
 		}
-		if (nccl) {      // y / z counts of the other ranks
-			double *tmp = slabs[0]->d_err2;
-			double v[2] = {(double)num_segs[1], (double)num_segs[2]}, w[2] = {(double)shared_free[1], (double)shared_free[2]};
-			for (int pass = 0; pass < 2; pass++) {
-				double *hv = pass == 0 ? v : w;
-				CU_TRY(cudaMemcpyAsync(tmp, hv, 2 * sizeof(double), cudaMemcpyHostToDevice, stream));
-				if (nccl_allreduce_sum_f64(nccl, tmp, 2, stream)) return fail(CMC_ERR_COMM, nccl_error());
-				CU_TRY(cudaMemcpyAsync(hv, tmp, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
-				CU_TRY(cudaStreamSynchronize(stream));
-			}
+		if (nccl) {      // y / z counts of the other ranks (and the x counts when every rank counted its own window)
+			double *tmp = slabs[0]->d_sums8;
+			double v[6] = {(double)num_segs[1], (double)num_segs[2], (double)shared_free[1], (double)shared_free[2],
+			               window_counts ? (double)num_segs[0] : 0.0, window_counts ? (double)shared_free[0] : 0.0};
+			CU_TRY(cudaMemcpyAsync(tmp, v, sizeof v, cudaMemcpyHostToDevice, stream));
+			if (nccl_allreduce_sum_f64(nccl, tmp, 6, stream)) return fail(CMC_ERR_COMM, nccl_error());
+			CU_TRY(cudaMemcpyAsync(v, tmp, sizeof v, cudaMemcpyDeviceToHost, stream));
+			CU_TRY(cudaStreamSynchronize(stream));
 			num_segs[1] = (long long)v[0]; num_segs[2] = (long long)v[1];
-			shared_free[1] = (long long)w[0]; shared_free[2] = (long long)w[1];
+			shared_free[1] = (long long)v[2]; shared_free[2] = (long long)v[3];
+			if (window_counts) { num_segs[0] = (long long)v[4]; shared_free[0] = (long long)v[5]; }
 		}
 		if (multi()) {
 			for (int r = 0; r < nslabs_total; r++)
@@ -1397,6 +1454,14 @@ int cmc_adi3d_set_nodes(cmc_adi3d *h, const int32_t *type, const int32_t *bc_vel
 	H_CHECK(h);
 	if (!type || !bc_vel || !bc_temp || !vx || !vy || !vz || !T) return fail(CMC_ERR_INVALID, "set_nodes: null array");
 	return h->set_nodes(type, bc_vel, bc_temp, vx, vy, vz, T, 0, false);
+}
+
+int cmc_adi3d_set_nodes_slab(cmc_adi3d *h, const int32_t *type, const int32_t *bc_vel, const int32_t *bc_temp,
+                             const void *vx, const void *vy, const void *vz, const void *T, int halo)
+{
+	H_CHECK(h);
+	if (!type || !bc_vel || !bc_temp || !vx || !vy || !vz || !T) return fail(CMC_ERR_INVALID, "set_nodes_slab: null array");
+	return h->set_nodes_slab(type, bc_vel, bc_temp, vx, vy, vz, T, halo, false);
 }
 
 int cmc_adi3d_update_nodes(cmc_adi3d *h, const int32_t *type, const int32_t *bc_vel, const int32_t *bc_temp,

@@ -39,6 +39,10 @@ bool launch_pcr_batch(int nsys, int n, const FT *a, const FT *b, const FT *c, co
 // line descriptors (Grid3D::GenerateListSegments, reference Grid3D.cpp:47-127)
 void launch_build_roles(int dir, const Layout &G, const uint8_t *ncode_global, const Layout &L, uint8_t *role,
                         unsigned long long *seg_count, cudaStream_t s, long long *launches);
+// x-direction descriptors from a window of the node codes (no NODE_IN on the x-faces of the grid): purely local rule
+void launch_build_roles_x_local(const Layout &G, const uint8_t *ncode_by_global_plane, const Layout &L, uint8_t *role,
+                                unsigned long long *seg_count, cudaStream_t s, long long *launches);
+void launch_count_in_plane(const Layout &G, const uint8_t *ncode_by_global_plane, int gplane_index, unsigned long long *out, cudaStream_t s);
 // adds the type bits (R_IN / R_BV / R_OUT / R_VFREE / R_TFREE) to all three role arrays
 void launch_role_type_bits(const Layout &G, const uint8_t *ncode_global, const Layout &L,
                            uint8_t *rx, uint8_t *ry, uint8_t *rz, cudaStream_t s, long long *launches);

@@ -91,6 +91,73 @@ void launch_build_roles(int dir, const Layout &G, const uint8_t *ncode, const La
 	if (launches) (*launches)++;
 }
 
+// The same descriptors for the x direction from a WINDOW of the node codes (cmc_adi3d_set_nodes_slab: a rank that only
+// knows its own planes plus two on either side).  Needs no scan: with no NODE_IN cell on the two x-faces of the grid (the
+// reference's loaders always leave a NODE_OUT rim; checked by the caller) every run of fluid cells is closed
+// inside the grid, and a cell's role follows from its own type and those of the cells at -1, +1, +2:
+//   interior  : IN                          start : not IN, next IN            end : not IN, previous IN
+//   R_PRE     : IN, next not IN, next-but-one IN (the next cell is shared by two segments; its boundary kinds ride here)
+// `ncode` is addressed by GLOBAL plane (the caller passes the window's base shifted by its first plane).
+__global__ void k_build_roles_x_local(const Layout G, const uint8_t *__restrict__ ncode, const Layout L, uint8_t *role,
+                                      unsigned long long *seg_count)
+{
+	const long long rows = (long long)L.nx * L.ny;
+	unsigned long long count = 0, shared_free = 0;
+	const long long gplane = (long long)G.ny * G.nz;
+	for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+		const int i = (int)(row / L.ny), j = (int)(row % L.ny);
+		const int p = i + L.x0;
+		const uint8_t *c0 = ncode + ((long long)p * G.ny + j) * G.nz;
+		const long long dst = L.idx(i, j, 0);
+		for (int k = threadIdx.x; k < L.nz; k += blockDim.x) {
+			auto code = [&](int d) -> unsigned { const int q = p + d; return (q < 0 || q >= G.nx) ? 1u /* NODE_OUT */ : (unsigned)c0[(long long)d * gplane + k]; };
+			const unsigned cm = code(-1), c = code(0), cp = code(1), cpp = code(2);
+			const bool in = code_type(c) == 0u, inm = code_type(cm) == 0u, inp = code_type(cp) == 0u, inpp = code_type(cpp) == 0u;
+			unsigned bits = 0;
+			if (in) {
+				bits |= R_INT;
+				if (!inp && inpp) bits |= R_PRE | ((cp & 4u) ? R_VFREE : 0u) | ((cp & 8u) ? R_TFREE : 0u);
+			} else {
+				if (inp) bits |= R_START;
+				if (inm) { bits |= R_END; count++; }
+				if (inp && inm && (c & 12u)) shared_free++;
+			}
+			if (bits) role[dst + k] |= (uint8_t)bits;
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		count += __shfl_down_sync(0xffffffffu, count, o);
+		shared_free += __shfl_down_sync(0xffffffffu, shared_free, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		if (count) atomicAdd(seg_count, count);
+		if (shared_free) atomicAdd(seg_count + 4, shared_free);
+	}
+}
+
+void launch_build_roles_x_local(const Layout &G, const uint8_t *ncode_by_global_plane, const Layout &L, uint8_t *role,
+                                unsigned long long *seg_count, cudaStream_t s, long long *launches)
+{
+	k_build_roles_x_local<<<grid_for((long long)L.nx * L.ny, 1), 128, 0, s>>>(G, ncode_by_global_plane, L, role, seg_count);
+	if (launches) (*launches)++;
+}
+
+// number of NODE_IN cells in one global x-plane of the (windowed) node codes
+__global__ void k_count_in_plane(const Layout G, const uint8_t *__restrict__ ncode, int gplane_index, unsigned long long *out)
+{
+	const long long n = (long long)G.ny * G.nz;
+	const uint8_t *src = ncode + (long long)gplane_index * n;
+	unsigned long long c = 0;
+	for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) c += code_type(src[t]) == 0u;
+	for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+	if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+void launch_count_in_plane(const Layout &G, const uint8_t *ncode_by_global_plane, int gplane_index, unsigned long long *out, cudaStream_t s)
+{
+	k_count_in_plane<<<64, 256, 0, s>>>(G, ncode_by_global_plane, gplane_index, out);
+}
+
 __global__ void k_role_type_bits(const Layout G, const uint8_t *__restrict__ ncode, const Layout L,
                                  uint8_t *rx, uint8_t *ry, uint8_t *rz)
 {

@@ -112,7 +112,15 @@ class AdiSolver3D:
         self.set_mode(mode)
         arr_i = [np.ascontiguousarray(a, dtype=np.int32) for a in (case.type, case.bc_vel, case.bc_temp)]
         arr_f = [np.ascontiguousarray(a, dtype=self.ft) for a in (case.vx, case.vy, case.vz, case.T)]
-        _check(lib.cmc_adi3d_set_nodes(h, *[_ptr(a) for a in arr_i], *[_ptr(a) for a in arr_f]))
+        if case.x_lo is not None:
+            # slab-local case: the arrays cover this rank's planes plus `halo` planes either side (clipped to the grid)
+            halo = max(self.x0 - case.x_lo, case.x_hi - self.x0 - self.nx)
+            want = slab_window(case.dimx, self.x0, self.nx, halo)
+            if (case.x_lo, case.x_hi) != want:
+                raise ValueError(f"slab-local case covers planes [{case.x_lo}, {case.x_hi}), the slab [{self.x0}, {self.x0 + self.nx}) needs {want}")
+            _check(lib.cmc_adi3d_set_nodes_slab(h, *[_ptr(a) for a in arr_i], *[_ptr(a) for a in arr_f], halo))
+        else:
+            _check(lib.cmc_adi3d_set_nodes(h, *[_ptr(a) for a in arr_i], *[_ptr(a) for a in arr_f]))
         return self
 
     def UpdateNodes(self, case: Case):
@@ -367,6 +375,24 @@ def solve_tridiagonal_batch(a, b, c, d, mode="exact"):
 
 
 SPLIT_EVEN_X, SPLIT_EVEN_SEGMENTS, SPLIT_EVEN_VOLUME = 0, 1, 2
+NODE_HALO = 2          # planes a slab-local node array carries on either side (cmc_adi3d_set_nodes_slab)
+
+
+def slab_window(dimx, x0, nx, halo=NODE_HALO):
+    """Planes [lo, hi) a slab-local case of the slab [x0, x0 + nx) has to cover."""
+    return max(x0 - halo, 0), min(x0 + nx + halo, dimx)
+
+
+def default_split(dimx, dimy, dimz, n_slabs):
+    """(x0, nx) of every slab of the default split (even, cuts on multiples of 8 planes) - what cmc_adi3d_create_dist uses."""
+    g = GridDesc(dimx, dimy, dimz, 1.0, 1.0, 1.0)
+    out = (C.c_int32 * n_slabs)()
+    _check(load_library().cmc_split_planes(SPLIT_EVEN_X, C.byref(g), None, n_slabs, out))
+    x0, res = 0, []
+    for n in out:
+        res.append((x0, n)); x0 += n
+    return res
+
 
 
 def split_planes(case: Case, n_slabs: int, policy: int = SPLIT_EVEN_X):

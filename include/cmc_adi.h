@@ -136,6 +136,14 @@ int cmc_adi3d_set_nodes(cmc_adi3d *h, const int32_t *type, const int32_t *bc_vel
  * (28 bytes in the fp32 build; 48 in fp64, where the FTYPE members start at offset 16) */
 int cmc_adi3d_set_nodes_aos(cmc_adi3d *h, const void *nodes, size_t node_stride_bytes);
 
+/* the same for ONE slab of a distributed run, from node arrays that cover only the planes [x0 - hlo, x0 + nx + hhi) of
+ * the grid (x0, nx: cmc_adi3d_slab; hlo = min(halo, x0), hhi = min(halo, dimx - x0 - nx); halo >= 2) - no rank has to hold
+ * the whole grid.  This is what Grid3D::Init_GPU does per device (node slices with their halo, Grid3D.cpp:567-596).  Needs
+ * a grid without NODE_IN cells on its two x-faces (every grid the reference's loaders produce; CMC_ERR_UNSUPPORTED
+ * otherwise). */
+int cmc_adi3d_set_nodes_slab(cmc_adi3d *h, const int32_t *type, const int32_t *bc_vel, const int32_t *bc_temp,
+                             const void *vx, const void *vy, const void *vz, const void *T, int halo_planes);
+
 /* ---- moving boundaries: Grid3D::Prepare(t) (Grid3D.cpp:900-945, ComputeSubframeInfo; the driver's hook is
  * FluidSolver3D.cpp:237) rewrites the Node[] array between steps - types, boundary kinds and boundary values - and the
  * solver keeps its time layers.  Same arrays as cmc_adi3d_set_nodes / _aos; the layers are NOT touched.  Call

@@ -400,3 +400,52 @@ def test_moving_boundary_update_nodes(oracle_mod, mode, fp):
         assert abs(e - e_ref) <= (1e-5 if fp == 4 else 1e-9) * abs(e_ref)
         _check_fields(O, ora, s, case, mode, f"moving baffle, step {step}")
     s.close()
+
+
+def _xline_case(line_types, bc_free_cells=(), fp=8):
+    """n x 3 x 3 grid whose centre x-line has the given node types (the x twin of _line_case)."""
+    n = len(line_types)
+    t = np.full((n, 3, 3), 1, dtype=np.int32)
+    t[:, 1, 1] = line_types
+    bcv = np.zeros(t.shape, np.int32); bct = np.zeros(t.shape, np.int32)
+    for i in bc_free_cells:
+        bcv[i, 1, 1] = 1; bct[i, 1, 1] = 1
+    ft = np.float32 if fp == 4 else np.float64
+    vx = np.zeros(t.shape, ft); T = np.ones(t.shape, ft)
+    vx[:, 1, 1] = np.linspace(0.2, 1.0, n)
+    z = np.zeros(t.size, ft)
+    c = Case(n, 3, 3, .05, .05, .05, 1.0, 0.005, 0.007, 0.0014, 0.05, 2, 2, fp, type=t.ravel(), bc_vel=bcv.ravel(),
+             bc_temp=bct.ravel(), vx=vx.ravel(), vy=z, vz=vx.ravel().copy(), T=T.ravel())
+    return c
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_slab_local_node_arrays_single_slab(oracle_mod, mode):
+    """cmc_adi3d_set_nodes_slab on a one-slab handle (the window is the whole grid): the x-line descriptors come from the
+    local rule (k_build_roles_x_local) instead of the scan - same segment counts and fields as the oracle, on the masked
+    channel and on an x-line with shared cells, minimum-length segments and valves inside the line."""
+    O = oracle_mod
+    O.set_threads(1)
+    cases = [channel_case(40, 36, 32, fp_bytes=8, depth_var=0.25)]
+    line = [1, 2, 0, 2, 0, 0, 2, 1, 2, 0, 2, 1, 1, 2, 0, 0, 0, 3, 0, 0, 0, 0, 3, 0, 0, 2, 1, 1]
+    cases += [_xline_case(line, free) for free in ((), (22,), (3, 22))]
+    for case in cases:
+        ora = O.Oracle3D(case); ora.create_segments()
+        case.x_lo, case.x_hi = 0, case.dimx
+        s = AdiSolver3D().Init(case, mode=mode); s.CreateSegments()
+        assert [s.numSegs(d) for d in range(3)] == [len(ora.segments(d)) for d in range(3)]
+        for i in range(3):
+            ora.update_boundaries(); s.UpdateBoundaries()
+            ora.time_step(case.dt, 2, 2, False); s.TimeStep(case.dt, 2, 2, False)
+        _check_fields(O, ora, s, case, mode, "slab-local node arrays")
+        s.close()
+    O.set_threads(0)
+    # a fluid cell on an x-face of the grid: the local rule cannot know whether its run is ever closed
+    bad = channel_case(16, 12, 12, baffle=False)
+    bad.type.reshape(bad.shape)[0, 5, 5] = 0
+    bad.x_lo, bad.x_hi = 0, 16
+    s = AdiSolver3D().Init(bad)
+    with pytest.raises(CmcError) as ei:
+        s.CreateSegments()
+    assert ei.value.code == -4
+    s.close()

@@ -60,6 +60,19 @@ def main():
         ok &= good
         print(f"rank {rank}/{world} fp{fp * 8}: planes [{many.x0},{many.x0 + many.nx}) err {e:.6e} (1 GPU {e1:.6e}) "
               f"linf_vel {errs[0]:.2e} l2_vel {errs[1]:.2e} linf_T {errs[2]:.2e} l2_T {errs[3]:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+        # the same run from slab-local node arrays (cmc_adi3d_set_nodes_slab): no rank builds the whole grid
+        from cmc_fluid_solver_b200.solver import default_split, slab_window
+        x0, nx = default_split(case.dimx, case.dimy, case.dimz, world)[rank]
+        local = channel_case(case.dimx, 40, 48, fp_bytes=fp, depth_var=0.25, x_range=slab_window(case.dimx, x0, nx))
+        loc = AdiSolver3D().Init(local, device=lr, mode="fast", rank=rank, nranks=world, nccl_id=fresh_id()); loc.CreateSegments()
+        assert [loc.numSegs(d) for d in range(3)] == [one.numSegs(d) for d in range(3)], "segment counts differ (slab-local)"
+        for i in range(4):
+            loc.UpdateBoundaries()
+            e2 = loc.TimeStep(case.dt, 4, 2, True)
+        assert e2 == e, ("slab-local run differs from the whole-grid one", e2, e)
+        for q in range(4):
+            assert np.array_equal(loc.read_field(0, q), many.read_field(0, q)), f"slab-local field {q} differs"
+        loc.close()
         one.close(); many.close()
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
