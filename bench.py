@@ -252,9 +252,22 @@ def main():
         nccl_id = bytes(idt.cpu().numpy().tobytes())
 
     DX, DY, DZ = grid_dims(args, world)
-    case = channel_case(DX, DY, DZ, fp_bytes=args.fp, depth_var=0.2)
+    if world > 1:
+        # every rank builds only its own x-planes (+ 2 halo planes either side): cmc_adi3d_set_nodes_slab
+        from cmc_fluid_solver_b200.solver import default_split, slab_window
+        x0, nxl = default_split(DX, DY, DZ, world)[rank]
+        lo, hi = slab_window(DX, x0, nxl)
+        case = channel_case(DX, DY, DZ, fp_bytes=args.fp, depth_var=0.2, x_range=(lo, hi))
+        n_in = int((case.type.reshape(hi - lo, DY, DZ)[x0 - lo:x0 - lo + nxl] == 0).sum())
+        import torch.distributed as dist
+        tn = torch.tensor([n_in], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tn)
+        n_in = int(tn.item())
+    else:
+        case = channel_case(DX, DY, DZ, fp_bytes=args.fp, depth_var=0.2)
+        n_in = case.n_in
     ncells = case.ncells
-    fluid = case.n_in / ncells
+    fluid = n_in / ncells
     sol = AdiSolver3D().Init(case, device=local_rank, mode=args.mode, rank=rank, nranks=world, nccl_id=nccl_id)
     sol.CreateSegments()
     stream = torch.cuda.ExternalStream(sol.stream(), device=local_rank)
@@ -352,41 +365,78 @@ def main():
     }
 
     # ---- e2e: the same step through the public API with HOST buffers (H2D state, D2H layer) inside the timed region ----
+    # Every step copies its inputs (the four fields of the layer the caller owns) from pinned host memory and reads its
+    # result (residual + the full-resolution layer of GetLayer) back.  The copies are overlapped with the compute the way a
+    # production driver would: the inputs of step n+1 are uploaded on the copy stream while step n runs
+    # (cmc_adi3d_write_layer_async / _commit), the layer read back by step n lands while step n+1 runs
+    # (cmc_adi3d_get_layer_async / _wait).  `serial` is the same loop with blocking calls (round 1's e2e).
     e2e = None
     if not args.no_e2e:
-        # every rank feeds its own slab from pinned host memory; rank 0 receives the full layer (GetLayer gathers)
         ft = torch.float32 if fpb == 4 else torch.float64
         host_in = [torch.empty(local_cells, dtype=ft).pin_memory() for _ in range(4)]
         for q in range(4):
             host_in[q].numpy()[:] = sol.read_field(0, q).ravel()
-        host_vel = torch.empty(ncells * 3 if rank == 0 else 3, dtype=ft).pin_memory()
-        host_T = torch.empty(ncells if rank == 0 else 1, dtype=torch.float64).pin_memory()
+        host_vel = [torch.empty(ncells * 3 if rank == 0 else 3, dtype=ft).pin_memory() for _ in range(2)]
+        host_T = [torch.empty(ncells if rank == 0 else 1, dtype=torch.float64).pin_memory() for _ in range(2)]
         h2d = 4 * ncells * fpb                                   # all ranks together
         d2h = ncells * (3 * fpb + 8) + 16
+        ins = [h.numpy() for h in host_in]
 
-        def e2e_step():
+        def serial_step(i):
             for q in range(4):
-                sol.write_field(0, q, host_in[q].numpy())            # host -> device: the layer the caller owns
+                sol.write_field(0, q, ins[q])                        # host -> device: the layer the caller owns
             sol.UpdateBoundaries()
             sol.TimeStep(case.dt, NUM_GLOBAL, NUM_LOCAL, True)       # residual read back
-            sol.GetLayer(0, 0, 0, vel=host_vel.numpy().reshape(-1, 3), T=host_T.numpy())   # device -> host: full layer
+            sol.GetLayer(0, 0, 0, vel=host_vel[0].numpy().reshape(-1, 3), T=host_T[0].numpy())   # device -> host: full layer
 
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        barrier()
-        e2e_ms = (time.perf_counter() - t0) * 1e3
-        if world > 1:
-            import torch.distributed as dist
-            t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
+        def timed(fn, nsteps, before=None, after=None):
+            if before:
+                before()
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(nsteps):
+                fn(i)
+            if after:
+                after()
+            barrier()
+            ms_ = (time.perf_counter() - t0) * 1e3
+            if world > 1:
+                import torch.distributed as dist
+                t = torch.tensor([ms_], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_ = float(t.item())
+            return ms_
+
+        serial_step(0)
+        serial_ms = timed(serial_step, 2)
+
+        def piped_step(i):
+            sol.write_layer_commit(0)                                # this step's inputs (upload started during the previous step)
+            sol.UpdateBoundaries()
+            sol.TimeStepAsync(case.dt, NUM_GLOBAL, NUM_LOCAL, True)
+            sol.write_layer_async(*ins)                              # the next step's inputs: host -> device behind the compute
+            k = i & 1
+            sol.GetLayerWait()                                       # the previous readback has landed: its host buffer is free
+            sol.GetLayerAsync(host_vel[k].numpy().reshape(-1, 3), host_T[k].numpy())     # device -> host behind the next step
+            sol.Sync()                                               # the residual of this step (host-visible every step)
+
+        def piped_start():
+            sol.write_layer_async(*ins)
+
+        def piped_end():
+            sol.GetLayerWait()
+            sol.write_layer_commit(0)                                # (consume the last upload)
+            sol.Sync()
+
+        timed(piped_step, 2, piped_start, piped_end)                 # warm-up: staging buffers, copy streams
+        e2e_ms = timed(piped_step, args.e2e_steps, piped_start, piped_end)
         e2e = {"value": ncells * args.e2e_steps / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": e2e_ms / args.e2e_steps, "steps": args.e2e_steps,
-               "what": "write_field x4 (pinned host -> HBM, every rank its slab), UpdateBoundaries, TimeStep(computeError), GetLayer full "
-                       "resolution (HBM -> pinned host on rank 0); host wall clock between barriers, max over ranks"}
+               "serial": {"value": ncells * 2 / (serial_ms * 1e-3) / 1e6, "ms_per_step": serial_ms / 2, "steps": 2,
+                          "what": "the same step with blocking calls: write_field x4, UpdateBoundaries, TimeStep(computeError), GetLayer"},
+               "what": "per step: inputs of the step from pinned host memory (write_layer_async during the previous step, write_layer_commit), "
+                       "UpdateBoundaries, TimeStep(computeError) with the residual read back, GetLayer at full resolution into pinned host memory "
+                       "(get_layer_async, landing during the next step; rank 0 receives); host wall clock between barriers, max over ranks"}
 
     # the reported CPU baseline: rank 0 runs the reference solver on the host cores while the other ranks wait at a barrier
     cpu = None
@@ -406,6 +456,7 @@ def main():
             "dtype": "f64" if fpb == 8 else "f32", "data": "synthetic",
             "config": bench_config(args, world),
             "implementation": {"mode": args.mode, "exchange": sol.exchange_kind(), "fluid_fraction": round(fluid, 4),
+                               "node_arrays": "slab-local (own planes + 2 halo planes per rank)" if world > 1 else "whole grid",
                                "storage": f"SoA, y-blocked ({sol.storage_block_rows()} rows per block)" if sol.storage_block_rows() else "SoA [i][j][k]"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clk, "residual": err, "checksums": checksums, "device_bytes": sol.device_bytes(),

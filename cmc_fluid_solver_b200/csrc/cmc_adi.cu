@@ -58,6 +58,10 @@ struct cmc_adi3d {
 	virtual int time_step(double dt, int ng, int nl, int ce, double *err, bool async) = 0;
 	virtual int sync(double *err) = 0;
 	virtual int get_layer(void *vel, double *T, int ox, int oy, int oz) = 0;
+	virtual int get_layer_async(void *vel, double *T, int ox, int oy, int oz) = 0;
+	virtual int get_layer_wait() = 0;
+	virtual int write_layer_async(const void *const src[4]) = 0;
+	virtual int write_layer_commit(int layer) = 0;
 	virtual int read_field(int layer, int var, void *dst) = 0;
 	virtual int write_field(int layer, int var, const void *src) = 0;
 	virtual int step_prologue() = 0;
@@ -181,9 +185,19 @@ struct Slab {
 	int *d_tilectr = nullptr;      // tile counter of the persistent sweep kernels
 	cudaEvent_t done = nullptr;    // slabs on different devices of ONE process: "everything enqueued so far" of this slab
 	bool owns_stream = false;
-	FT *d_outvel = nullptr;
+	// GetLayer staging (device): two sets, so that the device-to-host copy of one readback can still be running - on the
+	// slab's copy stream - while the next one is produced
+	FT *d_outvel2[2] = {nullptr, nullptr};
+	double *d_outT2[2] = {nullptr, nullptr};
+	size_t out_cap2[2] = {0, 0};
+	FT *d_outvel = nullptr;        // the set in use by the current readback
 	double *d_outT = nullptr;
-	size_t out_cap = 0;
+	int out_idx = 0;
+	cudaStream_t io_out = nullptr, io_in = nullptr;      // copy streams: results to the host / inputs from the host
+	cudaEvent_t ev_filtered = nullptr, ev_out_done[2] = {nullptr, nullptr}, ev_in_done = nullptr, ev_in_free = nullptr;
+	bool out_pending[2] = {false, false};
+	FT *d_stage_in[4] = {nullptr, nullptr, nullptr, nullptr};   // dense [nx][ny][nz] staging of an asynchronously uploaded layer
+	bool in_pending = false;
 	// partitioned x-sweep exchange buffers: [peer][16 | 8][lpo].  The *_recv tables are filled by the other slabs'
 	// kernels directly (they live in the arena); the *_send staging buffers exist only for the NCCL transport.
 	FT *xcoef_send = nullptr, *xcoef_recv = nullptr, *xbnd_send = nullptr, *xbnd_recv = nullptr;
@@ -203,7 +217,12 @@ struct Slab {
 		for (auto &p : role) if (p) cudaFree(p);
 		if (done) cudaEventDestroy(done);
 		if (owns_stream && stream) cudaStreamDestroy(stream);
-		void *misc[] = {cv, cT, d_partials, d_err2, d_sums8, d_segcount, d_tilectr, d_outvel, d_outT, ncode, xcoef_send, xbnd_send};
+		if (io_out) { cudaStreamSynchronize(io_out); cudaStreamDestroy(io_out); }
+		if (io_in) { cudaStreamSynchronize(io_in); cudaStreamDestroy(io_in); }
+		cudaEvent_t evs[] = {ev_filtered, ev_out_done[0], ev_out_done[1], ev_in_done, ev_in_free};
+		for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+		void *misc[] = {cv, cT, d_partials, d_err2, d_sums8, d_segcount, d_tilectr, d_outvel2[0], d_outT2[0], d_outvel2[1], d_outT2[1],
+		                d_stage_in[0], d_stage_in[1], d_stage_in[2], d_stage_in[3], ncode, xcoef_send, xbnd_send};
 		for (void *p : misc) if (p) cudaFree(p);
 	}
 
@@ -251,6 +270,16 @@ struct Slab {
 			if ((rc = dalloc(xcoef_send, lpo * 16 * nslabs))) return rc;
 			if ((rc = dalloc(xbnd_send, lpo * 8 * nslabs))) return rc;
 		}
+		return CMC_OK;
+	}
+
+	int io_setup()
+	{
+		if (io_out) return CMC_OK;
+		CU_TRY(cudaStreamCreateWithFlags(&io_out, cudaStreamNonBlocking));
+		CU_TRY(cudaStreamCreateWithFlags(&io_in, cudaStreamNonBlocking));
+		cudaEvent_t *evs[] = {&ev_filtered, &ev_out_done[0], &ev_out_done[1], &ev_in_done, &ev_in_free};
+		for (cudaEvent_t *e : evs) CU_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 		return CMC_OK;
 	}
 
@@ -1127,7 +1156,27 @@ struct Engine : cmc_adi3d {
 	}
 
 	// Solver3D::GetLayer (Solver3D.cpp:21-25)
-	int get_layer(void *vel, double *T, int ox, int oy, int oz) override
+	int get_layer(void *vel, double *T, int ox, int oy, int oz) override { return get_layer_impl(vel, T, ox, oy, oz, false); }
+	int get_layer_async(void *vel, double *T, int ox, int oy, int oz) override { return get_layer_impl(vel, T, ox, oy, oz, true); }
+
+	// waits for every readback started by get_layer_async
+	int get_layer_wait() override
+	{
+		for (auto *s : slabs) {
+			use(s);
+			for (int k = 0; k < 2; k++)
+				if (s->out_pending[k]) { CU_TRY(cudaEventSynchronize(s->ev_out_done[k])); s->out_pending[k] = false; }
+		}
+		if (multi_device) cudaSetDevice(device);
+		CU_TRY(cudaGetLastError());
+		return CMC_OK;
+	}
+
+	// async: the device part (Clear + FilterToArrays + gather) is enqueued on the solver's stream and the copy to the host
+	// on the slab's copy stream behind it, into a second staging set - the caller goes on with the next time step and
+	// collects the result with get_layer_wait (reference: TimeLayer3D::FilterToArrays + OutputNetCDF3D_layer run between
+	// two time steps, TimeLayer3D.h:819-924, IO.h:350-388)
+	int get_layer_impl(void *vel, double *T, int ox, int oy, int oz, bool async)
 	{
 		if (!have_lines) return fail(CMC_ERR_INVALID, "get_layer: call cmc_adi3d_build_lines first");
 		CU_TRY(cudaSetDevice(device));
@@ -1152,14 +1201,22 @@ struct Engine : cmc_adi3d {
 			cudaStream_t stream = s->stream;
 			launch_clear_out<FT>(s->L, s->role[2], s->layer(CMC_LAYER_NEXT), (FT)CMC_MISSING_VALUE, stream, &launches);
 			const size_t need = (nccl && rank == 0) ? outN : (size_t)std::max(0, hi[s->index] - lo[s->index]) * rowN;
-			if (need > s->out_cap) {
-				if (s->d_outvel) cudaFree(s->d_outvel);
-				if (s->d_outT) cudaFree(s->d_outT);
-				s->d_outvel = nullptr; s->d_outT = nullptr;
-				CU_TRY(cudaMalloc((void **)&s->d_outvel, need * 3 * sizeof(FT)));
-				CU_TRY(cudaMalloc((void **)&s->d_outT, need * sizeof(double)));
-				s->out_cap = need;
+			if (async) { int rc = s->io_setup(); if (rc) return rc; }
+			const int k = async ? (s->out_idx ^= 1) : s->out_idx;
+			if (s->out_pending[k]) {          // this staging set still feeds an earlier asynchronous copy
+				if (need > s->out_cap2[k]) { CU_TRY(cudaEventSynchronize(s->ev_out_done[k])); }
+				else CU_TRY(cudaStreamWaitEvent(stream, s->ev_out_done[k], 0));
+				s->out_pending[k] = false;
 			}
+			if (need > s->out_cap2[k]) {
+				if (s->d_outvel2[k]) cudaFree(s->d_outvel2[k]);
+				if (s->d_outT2[k]) cudaFree(s->d_outT2[k]);
+				s->d_outvel2[k] = nullptr; s->d_outT2[k] = nullptr;
+				CU_TRY(cudaMalloc((void **)&s->d_outvel2[k], need * 3 * sizeof(FT)));
+				CU_TRY(cudaMalloc((void **)&s->d_outT2[k], need * sizeof(double)));
+				s->out_cap2[k] = need;
+			}
+			s->d_outvel = s->d_outvel2[k]; s->d_outT = s->d_outT2[k];
 			// slab-local output buffer starts at output row lo (rank 0 of an NCCL run: at row 0, it also receives)
 			const int oi0 = lo[s->index], oi1 = hi[s->index];
 			const size_t shift = (nccl && rank == 0) ? 0 : (size_t)std::max(oi0, 0) * rowN;
@@ -1184,8 +1241,11 @@ struct Engine : cmc_adi3d {
 			}
 			if (!ops.empty() && nccl_exchange(nccl, ops.data(), (int)ops.size(), stream)) return fail(CMC_ERR_COMM, nccl_error());
 			if (rank == 0) {
-				CU_TRY(cudaMemcpyAsync(vel, s->d_outvel, outN * 3 * sizeof(FT), cudaMemcpyDeviceToHost, stream));
-				CU_TRY(cudaMemcpyAsync(T, s->d_outT, outN * sizeof(double), cudaMemcpyDeviceToHost, stream));
+				cudaStream_t cs = stream;
+				if (async) { CU_TRY(cudaEventRecord(s->ev_filtered, stream)); CU_TRY(cudaStreamWaitEvent(s->io_out, s->ev_filtered, 0)); cs = s->io_out; }
+				CU_TRY(cudaMemcpyAsync(vel, s->d_outvel, outN * 3 * sizeof(FT), cudaMemcpyDeviceToHost, cs));
+				CU_TRY(cudaMemcpyAsync(T, s->d_outT, outN * sizeof(double), cudaMemcpyDeviceToHost, cs));
+				if (async) { CU_TRY(cudaEventRecord(s->ev_out_done[s->out_idx], cs)); s->out_pending[s->out_idx] = true; }
 			}
 		} else {
 			for (auto *s : slabs) {
@@ -1193,13 +1253,58 @@ struct Engine : cmc_adi3d {
 				if (oi1 <= oi0) continue;
 				use(s);
 				const size_t o0 = (size_t)oi0 * rowN, cnt = (size_t)(oi1 - oi0) * rowN;
-				CU_TRY(cudaMemcpyAsync((FT *)vel + 3 * o0, s->d_outvel, cnt * 3 * sizeof(FT), cudaMemcpyDeviceToHost, s->stream));
-				CU_TRY(cudaMemcpyAsync(T + o0, s->d_outT, cnt * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+				cudaStream_t cs = s->stream;
+				if (async) { CU_TRY(cudaEventRecord(s->ev_filtered, s->stream)); CU_TRY(cudaStreamWaitEvent(s->io_out, s->ev_filtered, 0)); cs = s->io_out; }
+				CU_TRY(cudaMemcpyAsync((FT *)vel + 3 * o0, s->d_outvel, cnt * 3 * sizeof(FT), cudaMemcpyDeviceToHost, cs));
+				CU_TRY(cudaMemcpyAsync(T + o0, s->d_outT, cnt * sizeof(double), cudaMemcpyDeviceToHost, cs));
+				if (async) { CU_TRY(cudaEventRecord(s->ev_out_done[s->out_idx], cs)); s->out_pending[s->out_idx] = true; }
 			}
 		}
+		if (multi_device) cudaSetDevice(device);
+		if (async) return CMC_OK;
 		{ int rc = sync_all(); if (rc) return rc; }
 		CU_TRY(cudaGetLastError());
 		return check_peers();
+	}
+
+	// Asynchronous upload of a whole layer (u, v, w, T: dense host arrays of this handle's planes): the copies run on the
+	// copy stream into a dense staging buffer while the solver's stream keeps computing; write_layer_commit makes the
+	// solver's stream wait for them and scatters the staging buffer into the (padded, y-blocked) layer - one pass at HBM
+	// speed.  (Solver3D::SetLayer-style state injection; TimeLayer3D::CopyFromGrid for the fields, TimeLayer3D.h:926-951.)
+	int write_layer_async(const void *const src[4]) override
+	{
+		for (auto *s : slabs) {
+			use(s);
+			int rc = s->io_setup();
+			if (rc) return rc;
+			const size_t n = (size_t)s->L.nx * s->L.ny * s->L.nz;
+			const size_t o = (size_t)(s->L.x0 - L.x0) * s->L.ny * s->L.nz;
+			if (s->in_pending) CU_TRY(cudaStreamWaitEvent(s->io_in, s->ev_in_free, 0));   // the previous commit has read the staging buffer
+			for (int q = 0; q < 4; q++) {
+				if (!s->d_stage_in[q]) { CU_TRY(cudaMalloc((void **)&s->d_stage_in[q], n * sizeof(FT))); s->bytes += (long long)(n * sizeof(FT)); }
+				CU_TRY(cudaMemcpyAsync(s->d_stage_in[q], (const FT *)src[q] + o, n * sizeof(FT), cudaMemcpyHostToDevice, s->io_in));
+			}
+			CU_TRY(cudaEventRecord(s->ev_in_done, s->io_in));
+			s->in_pending = true;
+		}
+		if (multi_device) cudaSetDevice(device);
+		return CMC_OK;
+	}
+
+	int write_layer_commit(int logical) override
+	{
+		if (logical < 0 || logical > 3) return fail(CMC_ERR_INVALID, "write_layer_commit: bad layer");
+		for (auto *s : slabs) {
+			if (!s->in_pending) return fail(CMC_ERR_INVALID, "write_layer_commit: no upload pending (call cmc_adi3d_write_layer_async first)");
+			use(s);
+			CU_TRY(cudaStreamWaitEvent(s->stream, s->ev_in_done, 0));
+			ConstLayerPtrs<FT> st; for (int q = 0; q < 4; q++) st.f[q] = s->d_stage_in[q];
+			launch_scatter_dense<FT>(s->L, st, s->layer(logical), s->stream, &launches);
+			CU_TRY(cudaEventRecord(s->ev_in_free, s->stream));
+		}
+		if (multi_device) cudaSetDevice(device);
+		halos_dirty = true;
+		return CMC_OK;
 	}
 
 	// dense host copy of the locally held planes (all local slabs, in x order)
@@ -1521,6 +1626,25 @@ int cmc_adi3d_get_layer(cmc_adi3d *h, void *vel, double *T, int ox, int oy, int 
 	if (h->rank == 0 && (!vel || !T)) return fail(CMC_ERR_INVALID, "get_layer: null output");
 	return h->get_layer(vel, T, ox, oy, oz);
 }
+
+int cmc_adi3d_get_layer_async(cmc_adi3d *h, void *vel, double *T, int ox, int oy, int oz)
+{
+	H_CHECK(h);
+	if (h->rank == 0 && (!vel || !T)) return fail(CMC_ERR_INVALID, "get_layer_async: null output");
+	return h->get_layer_async(vel, T, ox, oy, oz);
+}
+
+int cmc_adi3d_get_layer_wait(cmc_adi3d *h) { H_CHECK(h); return h->get_layer_wait(); }
+
+int cmc_adi3d_write_layer_async(cmc_adi3d *h, const void *u, const void *v, const void *w, const void *T)
+{
+	H_CHECK(h);
+	if (!u || !v || !w || !T) return fail(CMC_ERR_INVALID, "write_layer_async: null source");
+	const void *src[4] = {u, v, w, T};
+	return h->write_layer_async(src);
+}
+
+int cmc_adi3d_write_layer_commit(cmc_adi3d *h, int layer) { H_CHECK(h); return h->write_layer_commit(layer); }
 
 int cmc_adi3d_set_option(cmc_adi3d *h, const char *key, int64_t value)
 {

@@ -73,6 +73,9 @@ template <typename FT>
 void launch_div_error(const Layout &L, const uint8_t *role, const FT *U, const FT *V, const FT *W,
                       FT dx, FT dy, FT dz, double *block_partials, int max_blocks, double *result2,
                       cudaStream_t s, long long *launches);
+// dense [nx][ny][nz] staging arrays -> the padded / y-blocked layer
+template <typename FT>
+void launch_scatter_dense(const Layout &L, ConstLayerPtrs<FT> src, LayerPtrs<FT> dst, cudaStream_t s, long long *launches);
 // per-field sums and sums of squares over the non-OUT cells of the slab (checksums; block_partials: 8 per block)
 template <typename FT>
 void launch_field_sums(const Layout &L, const uint8_t *role, ConstLayerPtrs<FT> f, double *block_partials, int max_blocks, double *result8,

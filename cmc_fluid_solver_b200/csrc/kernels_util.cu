@@ -259,6 +259,26 @@ __global__ void k_update_boundaries(const Layout L, const uint8_t *__restrict__ 
 	}
 }
 
+// dense [nx][ny][nz] arrays -> the padded / y-blocked layer (asynchronous layer upload, cmc_adi3d_write_layer_commit)
+template <typename FT>
+__global__ void k_scatter_dense(const Layout L, ConstLayerPtrs<FT> src, LayerPtrs<FT> dst)
+{
+	const long long rows = (long long)L.nx * L.ny;
+	for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+		const long long d0 = L.idx((int)(row / L.ny), (int)(row % L.ny), 0), s0 = row * L.nz;
+		for (int k = threadIdx.x; k < L.nz; k += blockDim.x) {
+			dst.f[0][d0 + k] = src.f[0][s0 + k]; dst.f[1][d0 + k] = src.f[1][s0 + k];
+			dst.f[2][d0 + k] = src.f[2][s0 + k]; dst.f[3][d0 + k] = src.f[3][s0 + k];
+		}
+	}
+}
+template <typename FT>
+void launch_scatter_dense(const Layout &L, ConstLayerPtrs<FT> src, LayerPtrs<FT> dst, cudaStream_t s, long long *launches)
+{
+	k_scatter_dense<FT><<<grid_for((long long)L.nx * L.ny, 1), 128, 0, s>>>(L, src, dst);
+	if (launches) (*launches)++;
+}
+
 template <typename FT>
 __global__ void k_clear_out(const Layout L, const uint8_t *__restrict__ role, LayerPtrs<FT> layer, FT value)
 {
@@ -476,6 +496,7 @@ void launch_filter(const Layout &L, ConstLayerPtrs<FT> layer, int ox, int oy, in
 	template void launch_fill<FT>(FT *, long long, FT, cudaStream_t, long long *); \
 	template void launch_div_error<FT>(const Layout &, const uint8_t *, const FT *, const FT *, const FT *, FT, FT, FT, double *, int, double *, cudaStream_t, long long *); \
 	template void launch_filter<FT>(const Layout &, ConstLayerPtrs<FT>, int, int, int, int, int, FT *, double *, cudaStream_t, long long *); \
+	template void launch_scatter_dense<FT>(const Layout &, ConstLayerPtrs<FT>, LayerPtrs<FT>, cudaStream_t, long long *); \
 	template void launch_field_sums<FT>(const Layout &, const uint8_t *, ConstLayerPtrs<FT>, double *, int, double *, cudaStream_t, long long *);
 CMC_INST(float)
 CMC_INST(double)

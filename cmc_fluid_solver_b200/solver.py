@@ -114,7 +114,7 @@ class AdiSolver3D:
         arr_f = [np.ascontiguousarray(a, dtype=self.ft) for a in (case.vx, case.vy, case.vz, case.T)]
         if case.x_lo is not None:
             # slab-local case: the arrays cover this rank's planes plus `halo` planes either side (clipped to the grid)
-            halo = max(self.x0 - case.x_lo, case.x_hi - self.x0 - self.nx)
+            halo = max(NODE_HALO, self.x0 - case.x_lo, case.x_hi - self.x0 - self.nx)
             want = slab_window(case.dimx, self.x0, self.nx, halo)
             if (case.x_lo, case.x_hi) != want:
                 raise ValueError(f"slab-local case covers planes [{case.x_lo}, {case.x_hi}), the slab [{self.x0}, {self.x0 + self.nx}) needs {want}")
@@ -198,6 +198,27 @@ class AdiSolver3D:
             T = np.empty(n, dtype=np.float64)
         _check(load_library().cmc_adi3d_get_layer(self._h, _ptr(vel), _ptr(T), ox, oy, oz))
         return vel, T
+
+    def GetLayerAsync(self, vel, T, outdimx=0, outdimy=0, outdimz=0):
+        """GetLayer without the wait: `vel` ((n, 3) FTYPE) and `T` (n doubles) are filled in the background (keep them alive -
+        pinned memory keeps the copy asynchronous); collect with GetLayerWait()."""
+        c = self.case
+        ox, oy, oz = outdimx or c.dimx, outdimy or c.dimy, outdimz or c.dimz
+        _check(load_library().cmc_adi3d_get_layer_async(self._h, _ptr(vel), _ptr(T), ox, oy, oz))
+
+    def GetLayerWait(self):
+        _check(load_library().cmc_adi3d_get_layer_wait(self._h))
+
+    def write_layer_async(self, u, v, w, T):
+        """Start the upload of a whole layer (dense arrays of this handle's planes) on the copy stream."""
+        arrs = [np.ascontiguousarray(a, dtype=self.ft) for a in (u, v, w, T)]
+        for a in arrs:
+            assert a.size == self.nx * self.case.dimy * self.case.dimz
+        self._pending_upload = arrs            # keep the host arrays alive until the commit
+        _check(load_library().cmc_adi3d_write_layer_async(self._h, *[_ptr(a) for a in arrs]))
+
+    def write_layer_commit(self, layer=LAYER_CUR):
+        _check(load_library().cmc_adi3d_write_layer_commit(self._h, layer))
 
     # -- hooks -------------------------------------------------------------------------------------------------
     def read_field(self, layer, var) -> np.ndarray:

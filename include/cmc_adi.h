@@ -172,6 +172,20 @@ int cmc_adi3d_time_step(cmc_adi3d *h, double dt, int num_global, int num_local,
  * Output dims of 0 mean "grid dims".  On a distributed handle every rank must call; rank 0 receives the result. */
 int cmc_adi3d_get_layer(cmc_adi3d *h, void *vel_xyz, double *T, int outdimx, int outdimy, int outdimz);
 
+/* ---- overlapped I/O (fused readback + output staging; reference: TimeLayer3D::FilterToArrays +
+ * OutputNetCDF3D_layer between two time steps, TimeLayer3D.h:819-924, IO.h:350-388).
+ * cmc_adi3d_get_layer_async = cmc_adi3d_get_layer without the wait: Clear + FilterToArrays (+ the gather of a distributed
+ * handle) are enqueued behind the time steps already issued, the copy to vel_xyz / T runs on a separate copy stream out of
+ * one of two staging sets, and the caller goes on stepping; cmc_adi3d_get_layer_wait returns when every readback started
+ * so far has landed.  The host arrays must stay valid until then (pinned memory keeps the copy asynchronous).
+ * cmc_adi3d_write_layer_async uploads a whole layer (u, v, w, T: dense arrays of this handle's planes) on the copy stream
+ * into a staging buffer while the solver keeps computing; cmc_adi3d_write_layer_commit(layer) orders the solver's stream
+ * behind that upload and scatters the staging buffer into the layer (the asynchronous form of cmc_adi3d_write_field x 4). */
+int cmc_adi3d_get_layer_async(cmc_adi3d *h, void *vel_xyz, double *T, int outdimx, int outdimy, int outdimz);
+int cmc_adi3d_get_layer_wait(cmc_adi3d *h);
+int cmc_adi3d_write_layer_async(cmc_adi3d *h, const void *u, const void *v, const void *w, const void *T);
+int cmc_adi3d_write_layer_commit(cmc_adi3d *h, int layer);
+
 /* ---- options ----  "mode": CMC_MODE_FAST | CMC_MODE_EXACT;  "tma": bit 0 / bit 1 = run the x / y sweeps as TMA-staged
  * persistent tiles where the grid allows (kernels_tma.cu; default from the environment variable CMC_TMA);  "profile": 0|1|2 (see cmc_adi3d_get_timing);
  * read-only: "kernel_x" / "kernel_y" / "kernel_z" (which kernel a sweep along that axis runs: 0 exact Thomas kernels,

@@ -449,3 +449,44 @@ def test_slab_local_node_arrays_single_slab(oracle_mod, mode):
         s.CreateSegments()
     assert ei.value.code == -4
     s.close()
+
+
+@pytest.mark.parametrize("emulate", [0, 3])
+def test_overlapped_readback_and_upload(oracle_mod, emulate):
+    """cmc_adi3d_get_layer_async / _wait and cmc_adi3d_write_layer_async / _commit: the readback of step n lands while step
+    n + 1 runs and equals the synchronous GetLayer; an asynchronously uploaded layer equals write_field x 4."""
+    O = oracle_mod
+    case = channel_case(48, 40, 36, fp_bytes=8, depth_var=0.25)
+    case.outdims = (12, 10, 9)
+    kw = dict(emulate_slabs=emulate) if emulate else {}
+    a = AdiSolver3D().Init(case, mode="fast", **kw); a.CreateSegments()
+    b = AdiSolver3D().Init(case, mode="fast", **kw); b.CreateSegments()
+    n = 12 * 10 * 9
+    bufs = [(np.empty((n, 3)), np.empty(n)) for _ in range(3)]
+    full = (np.empty((case.ncells, 3)), np.empty(case.ncells))
+    sync_out = []
+    for i in range(3):
+        for s in (a, b):
+            s.UpdateBoundaries(); s.TimeStep(case.dt, case.num_global, case.num_local, False)
+        sync_out.append(a.GetLayer(*case.outdims))
+        b.GetLayerAsync(bufs[i][0], bufs[i][1], *case.outdims)         # three readbacks in flight over two staging sets
+    b.GetLayerAsync(full[0], full[1])
+    b.GetLayerWait()
+    for i in range(3):
+        assert np.array_equal(bufs[i][0], sync_out[i][0]) and np.array_equal(bufs[i][1], sync_out[i][1]), i
+    vf, Tf = a.GetLayer()
+    assert np.array_equal(full[0], vf) and np.array_equal(full[1], Tf)
+    # asynchronous layer upload against write_field
+    rng = np.random.default_rng(3)
+    fields = [rng.standard_normal(case.shape) for _ in range(4)]
+    for q in range(4):
+        a.write_field(LAYER_CUR, q, fields[q])
+    b.write_layer_async(*fields)
+    b.UpdateBoundaries()                       # (work on the solver's stream while the upload runs)
+    b.write_layer_commit(LAYER_CUR)
+    a.UpdateBoundaries()
+    for q in range(4):
+        got, ref = b.read_field(LAYER_CUR, q), a.read_field(LAYER_CUR, q)
+        bv = (case.type.reshape(case.shape) >= 2)
+        assert np.array_equal(got[~bv], ref[~bv]) and np.array_equal(got[~bv], fields[q][~bv])
+    a.close(); b.close()
