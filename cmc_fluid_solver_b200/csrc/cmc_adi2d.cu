@@ -44,6 +44,8 @@ struct Dev2 {
 	FT *f[L2_COUNT][3];
 	Seg2 *listX, *listY;   // listX[i]: segment of column i (direction Y); listY[j]: segment of row j (direction X)
 	FT *scratch;           // per (segment, variable): a, b, c, d, x of max(dimx, dimy) rows
+	FT *resid;             // per cell: its term of the divergence residual (0 where the reference skips the cell)
+	FT dt;                 // time step of the batched launch (cmc_adi2d_time_step_batch)
 	double *result;        // [0] err, [1] iterations, [2] status (0 ok, 1 exceeded MAX_GLOBAL_ITERS, 2 error too big)
 };
 
@@ -63,24 +65,45 @@ __device__ void copy_cells(const Dev2<FT> &P, int src, int dst, int type, bool m
 	__syncthreads();
 }
 
-// TimeLayer2D::EvalDivError (TimeLayer2D.h:88-102): FTYPE accumulation in the reference's cell order
+// TimeLayer2D::EvalDivError (TimeLayer2D.h:88-102).  The reference adds the cells' terms into one FTYPE accumulator in
+// row-major order, and floating-point addition does not commute with a tree: the terms (8 loads, 2 type tests and a dozen
+// operations per cell - the expensive part) are computed by the whole block, the additions are then done by one thread
+// in the reference's order.  Skipped cells contribute +0.0, which leaves an FTYPE sum of non-negative terms unchanged.
 template <typename FT>
 __device__ double eval_div_error(const Dev2<FT> &P, int l, double *sh)
 {
+	const FT *U = P.f[l][0], *V = P.f[l][1];
+	const int ncell = (P.dimx - 1) * (P.dimy - 1);
+	int mine = 0;
+	for (int t = threadIdx.x; t < ncell; t += blockDim.x) {
+		const int i = t / (P.dimy - 1), j = t % (P.dimy - 1);
+		FT term = 0.0;
+		if (P.type[ID2(i, j)] == CMC_NODE_IN && P.type[ID2(i + 1, j)] == CMC_NODE_IN && P.type[ID2(i, j + 1)] == CMC_NODE_IN && P.type[ID2(i + 1, j + 1)] == CMC_NODE_IN) {
+			const FT tx = P.dy * (U[ID2(i + 1, j)] - U[ID2(i, j)]) + (U[ID2(i + 1, j + 1)] - U[ID2(i, j + 1)]) / 2;
+			const FT ty = P.dx * (V[ID2(i, j + 1)] - V[ID2(i, j)]) + (V[ID2(i + 1, j + 1)] - V[ID2(i + 1, j)]) / 2;
+			const FT s = tx + ty;
+			term = s < 0 ? -s : s;
+			mine++;
+		}
+		P.resid[t] = term;
+	}
+	const int count = __syncthreads_count(0) + 0;      // (barrier: the terms are visible)
+	(void)count;
+	__shared__ int s_count;
+	if (threadIdx.x == 0) s_count = 0;
+	__syncthreads();
+	if (mine) atomicAdd(&s_count, mine);
+	__syncthreads();
 	if (threadIdx.x == 0) {
 		FT err = 0.0;
-		int count = 0;
-		const FT *U = P.f[l][0], *V = P.f[l][1];
-		for (int i = 0; i < P.dimx - 1; i++)
-			for (int j = 0; j < P.dimy - 1; j++)
-				if (P.type[ID2(i, j)] == CMC_NODE_IN && P.type[ID2(i + 1, j)] == CMC_NODE_IN && P.type[ID2(i, j + 1)] == CMC_NODE_IN && P.type[ID2(i + 1, j + 1)] == CMC_NODE_IN) {
-					const FT tx = P.dy * (U[ID2(i + 1, j)] - U[ID2(i, j)]) + (U[ID2(i + 1, j + 1)] - U[ID2(i, j + 1)]) / 2;
-					const FT ty = P.dx * (V[ID2(i, j + 1)] - V[ID2(i, j)]) + (V[ID2(i + 1, j + 1)] - V[ID2(i + 1, j)]) / 2;
-					const FT s = tx + ty;
-					err += s < 0 ? -s : s;
-					count++;
-				}
-		*sh = err / count;
+		int t = 0;
+		for (; t + 8 <= ncell; t += 8) {              // loads first, then the eight dependent additions
+			const FT a0 = P.resid[t], a1 = P.resid[t + 1], a2 = P.resid[t + 2], a3 = P.resid[t + 3];
+			const FT a4 = P.resid[t + 4], a5 = P.resid[t + 5], a6 = P.resid[t + 6], a7 = P.resid[t + 7];
+			err += a0; err += a1; err += a2; err += a3; err += a4; err += a5; err += a6; err += a7;
+		}
+		for (; t < ncell; t++) err += P.resid[t];
+		*sh = err / s_count;
 	}
 	__syncthreads();
 	const double e = *sh;
@@ -166,10 +189,16 @@ __device__ void solve_direction(const Dev2<FT> &P, FT dt, int num_local, int dir
 }
 
 // AdiSolver2D::TimeStep (:279-323)
+// One thread block per case: blockIdx.x indexes the batch (cmc_adi2d_time_step_batch: many independent 2D cases - a
+// parameter study, an ensemble - advance in ONE launch, one case per SM; a single case is a batch of one).
 template <typename FT>
-__global__ void __launch_bounds__(1024, 1) k_adi2d_time_step(const Dev2<FT> P, FT dt, int num_global, int num_local)
+__global__ void __launch_bounds__(1024, 1) k_adi2d_time_step(const Dev2<FT> *batch, int num_global, int num_local)
 {
 	__shared__ double sh_err;
+	__shared__ Dev2<FT> P;
+	if (threadIdx.x == 0) P = batch[blockIdx.x];
+	__syncthreads();
+	const FT dt = P.dt;
 	// CreateSegments (:228-277)
 	for (int t = threadIdx.x; t < P.dimx + P.dimy; t += blockDim.x) {
 		const bool col = t < P.dimx;            // listX: column i, scanned along j
@@ -224,6 +253,20 @@ __global__ void k_adi2d_update_boundaries(const Dev2<FT> P)
 		for (int q = 0; q < 3; q++) P.f[L2_NEXT][q][t] = P.f[L2_CUR][q][t];
 }
 
+template <typename FT>
+__global__ void k_adi2d_update_boundaries_batch(const Dev2<FT> *batch)
+{
+	const Dev2<FT> &P = batch[blockIdx.y];
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= P.dimx * P.dimy) return;
+	const int ty = P.type[t];
+	if (ty != CMC_NODE_BOUND && ty != CMC_NODE_VALVE) return;
+	P.f[L2_CUR][0][t] = P.gvx[t]; P.f[L2_CUR][1][t] = P.gvy[t]; P.f[L2_CUR][2][t] = P.gT[t];
+	const int i = t / P.dimy, j = t % P.dimy;
+	if (i < P.dimx - 1 && j < P.dimy - 1)
+		for (int q = 0; q < 3; q++) P.f[L2_NEXT][q][t] = P.f[L2_CUR][q][t];
+}
+
 } // namespace
 
 struct cmc_adi2d {
@@ -234,6 +277,11 @@ struct cmc_adi2d {
 	virtual int time_step(double dt, int ng, int nl, double *err, int *iters) = 0;
 	virtual int get_layer(void *vel, double *T, int ox, int oy) = 0;
 	virtual int rw_field(int layer, int var, void *dst, const void *src) = 0;
+	virtual const void *dev_params(double dt) = 0;
+	virtual size_t dev_params_size() const = 0;
+	virtual int launch_batch(const void *dev_array, int n, int ng, int nl, bool with_boundaries, void *stream) = 0;
+	virtual int collect(double *err, int *iters) = 0;
+	virtual void *stream_handle() = 0;
 	int device = 0, fp = 4, dimx = 0, dimy = 0;
 	long long launches = 0;
 };
@@ -253,6 +301,7 @@ namespace {
 template <typename FT>
 struct Engine2D : cmc_adi2d {
 	Dev2<FT> P{};
+	Dev2<FT> *d_self = nullptr;     // device copy of P: the batch of one
 	std::vector<void *> allocs;
 	cudaStream_t stream = nullptr;
 	bool have_grid = false;
@@ -289,7 +338,9 @@ struct Engine2D : cmc_adi2d {
 		for (int l = 0; l < L2_COUNT; l++) for (int q = 0; q < 3; q++) if ((rc = dalloc(P.f[l][q], N))) return rc;
 		if ((rc = dalloc(P.listX, (size_t)dimx)) || (rc = dalloc(P.listY, (size_t)dimy))) return rc;
 		if ((rc = dalloc(P.scratch, 3 * maxn * 5 * maxn))) return rc;
+		if ((rc = dalloc(P.resid, N))) return rc;
 		if ((rc = dalloc(P.result, 4))) return rc;
+		if ((rc = dalloc(d_self, 1))) return rc;
 		return CMC_OK;
 	}
 	int set_grid(const int32_t *type, const int32_t *bc, const void *vx, const void *vy, const void *T) override
@@ -332,8 +383,14 @@ struct Engine2D : cmc_adi2d {
 		if (!have_grid) return cmc_set_error(CMC_ERR_INVALID, "adi2d: call cmc_adi2d_set_grid first");
 		if (ng < 0 || nl < 0) return cmc_set_error(CMC_ERR_INVALID, "adi2d time_step: negative iteration count");
 		CU2(cudaSetDevice(device));
-		k_adi2d_time_step<FT><<<1, 1024, 0, stream>>>(P, (FT)dt, ng, nl);      // (FTYPE)dt: FluidSolver2D.cpp:131
+		P.dt = (FT)dt;                                                       // (FTYPE)dt: FluidSolver2D.cpp:131
+		CU2(cudaMemcpyAsync(d_self, &P, sizeof P, cudaMemcpyHostToDevice, stream));
+		k_adi2d_time_step<FT><<<1, 1024, 0, stream>>>(d_self, ng, nl);
 		launches++;
+		return collect(err, iters);
+	}
+	int collect(double *err, int *iters)
+	{
 		double r[4] = {};
 		CU2(cudaMemcpyAsync(r, P.result, sizeof r, cudaMemcpyDeviceToHost, stream));
 		CU2(cudaStreamSynchronize(stream));
@@ -344,6 +401,20 @@ struct Engine2D : cmc_adi2d {
 		if (r[2] == 2.0) return cmc_set_error(CMC_ERR_DIVERGED, "Error is too big!");                         // :309-313
 		return CMC_OK;
 	}
+	// batch: the Dev2 of every member on this (the first) handle's stream; update_boundaries of all members rides in the same launch sequence
+	const void *dev_params(double dt) override { P.dt = (FT)dt; return &P; }
+	size_t dev_params_size() const override { return sizeof P; }
+	int launch_batch(const void *dev_array, int n, int ng, int nl, bool with_boundaries, void *stream_) override
+	{
+		CU2(cudaSetDevice(device));
+		cudaStream_t st = (cudaStream_t)stream_;
+		if (with_boundaries) k_adi2d_update_boundaries_batch<FT><<<dim3((dimx * dimy + 255) / 256, n), 256, 0, st>>>((const Dev2<FT> *)dev_array);
+		k_adi2d_time_step<FT><<<n, 1024, 0, st>>>((const Dev2<FT> *)dev_array, ng, nl);
+		CU2(cudaGetLastError());
+		launches += with_boundaries ? 2 : 1;
+		return CMC_OK;
+	}
+	void *stream_handle() override { return (void *)stream; }
 	int get_layer(void *vel, double *T, int ox, int oy) override      // Solver2D::GetLayer (Solver2D.cpp:20-34)
 	{
 		CU2(cudaSetDevice(device));
@@ -429,6 +500,43 @@ int cmc_adi2d_write_field(cmc_adi2d *h, int layer, int var, const void *src)
 	if (!src) return cmc_set_error(CMC_ERR_INVALID, "adi2d write_field: null source");
 	return h->rw_field(layer, var, nullptr, src);
 }
+// Many independent cases in one launch (one thread block - one SM - per case).  All handles: same precision, same grid
+// dimensions, same device.  update_boundaries != 0 runs Solver2D::UpdateBoundaries of every case first.  err_out /
+// iters_out / status_out: per case (status: CMC_OK or CMC_ERR_DIVERGED); returns the first non-OK status.
+int cmc_adi2d_time_step_batch(cmc_adi2d *const *handles, int n, double dt, int num_global, int num_local, int update_boundaries,
+                              double *err_out, int *iters_out, int *status_out)
+{
+	if (!handles || n < 1) return cmc_set_error(CMC_ERR_INVALID, "adi2d batch: no handles");
+	for (int i = 0; i < n; i++) {
+		if (!handles[i]) return cmc_set_error(CMC_ERR_INVALID, "adi2d batch: null handle");
+		if (handles[i]->fp != handles[0]->fp || handles[i]->device != handles[0]->device || handles[i]->dimx != handles[0]->dimx || handles[i]->dimy != handles[0]->dimy)
+			return cmc_set_error(CMC_ERR_INVALID, "adi2d batch: every case needs the same precision, grid dimensions and device");
+	}
+	if (num_global < 0 || num_local < 0) return cmc_set_error(CMC_ERR_INVALID, "adi2d batch: negative iteration count");
+	cudaSetDevice(handles[0]->device);
+	const size_t psz = handles[0]->dev_params_size();
+	std::vector<char> host((size_t)n * psz);
+	for (int i = 0; i < n; i++) memcpy(host.data() + (size_t)i * psz, handles[i]->dev_params(dt), psz);
+	void *dev = nullptr;
+	cudaStream_t st = (cudaStream_t)handles[0]->stream_handle();
+	if (cudaMalloc(&dev, host.size()) != cudaSuccess) return cmc_set_error(CMC_ERR_CUDA, "adi2d batch: out of device memory");
+	if (cudaMemcpyAsync(dev, host.data(), host.size(), cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaFree(dev); return cmc_set_error(CMC_ERR_CUDA, "adi2d batch: upload failed"); }
+	int rc = handles[0]->launch_batch(dev, n, num_global, num_local, update_boundaries != 0, st);
+	int first = rc;
+	if (cudaStreamSynchronize(st) != cudaSuccess) first = cmc_set_error(CMC_ERR_CUDA, std::string("adi2d batch: ") + cudaGetErrorString(cudaGetLastError()));
+	cudaFree(dev);
+	if (first) return first;
+	for (int i = 0; i < n; i++) {
+		double e = 0.0; int it = 0;
+		const int r = handles[i]->collect(&e, &it);
+		if (err_out) err_out[i] = e;
+		if (iters_out) iters_out[i] = it;
+		if (status_out) status_out[i] = r;
+		if (r && !first) first = r;
+	}
+	return first;
+}
+
 int cmc_adi2d_launch_count(const cmc_adi2d *h, int64_t *n) { H2(h); if (n) *n = h->launches; return CMC_OK; }
 
 } // extern "C"

@@ -383,6 +383,19 @@ class AdiSolver2D:
     time_step = TimeStep
 
 
+def time_step_batch_2d(solvers, dt, num_global, num_local, update_boundaries=True):
+    """Advance many independent AdiSolver2D cases (same grid size, precision, device) in ONE launch; returns
+    (residuals, outer iterations) per case.  Raises for the first case that diverged."""
+    n = len(solvers)
+    hs = (C.c_void_p * n)(*[s._h for s in solvers])
+    err, it, st = (C.c_double * n)(), (C.c_int * n)(), (C.c_int * n)()
+    rc = load_library().cmc_adi2d_time_step_batch(hs, n, float(dt), int(num_global), int(num_local), int(bool(update_boundaries)), err, it, st)
+    for s, e, i in zip(solvers, err, it):
+        s.err, s.iters = e, i
+    _check(rc)
+    return list(err), list(it)
+
+
 def solve_tridiagonal_batch(a, b, c, d, mode="exact"):
     """Batched line solve on the GPU: rows of a,b,c,d are independent systems (Common::SolveTridiagonal)."""
     ft = a.dtype

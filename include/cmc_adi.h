@@ -266,6 +266,13 @@ int cmc_adi2d_update_boundaries(cmc_adi2d *h);
  * residual the reference prints, *iters_out = outer iterations done.  CMC_ERR_DIVERGED where the reference exits
  * ("Exceeded max number of iterations", "Error is too big!"). */
 int cmc_adi2d_time_step(cmc_adi2d *h, double dt, int num_global, int num_local, double *err_out, int *iters_out);
+/* many independent 2D cases in ONE launch, one thread block (one SM) per case - the throughput form of the 2D solver
+ * (a single ~16 k-cell case cannot fill a GPU).  All handles: same precision, grid dimensions and
+ * device.  update_boundaries != 0 runs Solver2D::UpdateBoundaries of every case first.  Per case: residual, outer
+ * iterations and status (CMC_OK / CMC_ERR_DIVERGED); returns the first non-OK status.  Results are bit-identical with n
+ * separate cmc_adi2d_time_step calls. */
+int cmc_adi2d_time_step_batch(cmc_adi2d *const *handles, int n, double dt, int num_global, int num_local, int update_boundaries,
+                              double *err_out, int *iters_out, int *status_out);
 /* Solver2D::GetLayer (Solver2D.cpp:20-34): nearest-lower downsample of `next`; vel_xy = Vec2D[ox*oy] (2 x FTYPE), T = double[] */
 int cmc_adi2d_get_layer(cmc_adi2d *h, void *vel_xy, double *T, int outdimx, int outdimy);
 /* dense host copy of one field of one layer (Solver2D::SetGridBoundaries, Solver2D.cpp:64-71, reads cur.u / cur.v this

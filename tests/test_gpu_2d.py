@@ -149,3 +149,42 @@ def test_moving_boundaries_2d_matches_reference_bitwise():
         s.write_field(0, q, z["layer_init"][q])
     drive_dynamic(s, z, lambda q: s.read_field(0, q))
     s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fp", [4, 8])
+def test_batched_2d_cases_equal_single_steps(oracle_mod, fp):
+    """cmc_adi2d_time_step_batch: several independent cases (different inflow speeds, so different outer-iteration counts)
+    advance in one launch - bit-identical with stepping every case on its own, and with the oracle."""
+    from cmc_fluid_solver_b200 import AdiSolver2D
+    from cmc_fluid_solver_b200.solver import time_step_batch_2d
+    O = oracle_mod
+    dimx, dimy, h = 61, 47, 0.02
+    par = (1.0, 0.05, 0.07, 0.002)
+    ft = np.float32 if fp == 4 else np.float64
+    speeds = [0.5, 1.0, 1.5, 0.8, 1.2, 0.3, 0.9]
+    batch, single, oracles = [], [], []
+    for v in speeds:
+        ty, bc, vx, vy, T = synthetic_2d(dimx, dimy)
+        vx = vx * v
+        for lst in (batch, single):
+            s = AdiSolver2D().Init(dimx, dimy, h, h, *par, 1.0, fp)
+            s.set_grid(ty, bc, vx, vy, T); s.init_layer()
+            lst.append(s)
+        o = O.Oracle2D(dimx, dimy, h, h, *par, 1.0, fp)
+        o.set_grid(ty, bc, vx, vy, T); o.init_layer()
+        oracles.append(o)
+    for step in range(4):
+        errs, iters = time_step_batch_2d(batch, 0.05, 3, 2, update_boundaries=True)
+        for k, (s, o) in enumerate(zip(single, oracles)):
+            s.UpdateBoundaries(); e = s.TimeStep(0.05, 3, 2)
+            o.update_boundaries(); e_ref = o.time_step(0.05, 3, 2)
+            assert errs[k] == e == e_ref and iters[k] == s.iters == o.iters(), (step, k)
+            for q in range(3):
+                assert np.array_equal(batch[k].read_field(0, q), s.read_field(0, q))
+                assert np.array_equal(batch[k].read_field(0, q), o.field(0, q).astype(ft))
+    assert len(set(iters)) >= 1
+    for s in batch + single:
+        s.close()
+    for o in oracles:
+        o.close()
