@@ -205,6 +205,79 @@ def bench_config(args, world):
             "l2": f"inputs larger than L2: each field {DX * DY * DZ * args.fp / 1e9:.2f} GB, 20 resident fields"}
 
 
+# --------------------------------------------------------------------------------- BASELINE config 1 (2D)
+def bench_2d(args):
+    """`bench.py --config 2d`: the reference's own 2D case data/2D/box_pipe (120 x 135, fp32, 49 steps - BASELINE config 1)
+    through cmc_adi2d_*: `--batch` independent copies of the case advance per launch (one thread block per case; the
+    2D solver is bit-identical with the reference, so every copy reproduces the golden residuals).  CPU baseline: the
+    oracle's C restatement of AdiSolver2D (pinned bit-for-bit to the reference; the reference's 2D solver is serial)."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, str(ROOT / "tests"))
+    from test_oracle2d import golden_grid, load_golden2d
+    from cmc_fluid_solver_b200 import AdiSolver2D
+    from cmc_fluid_solver_b200.solver import time_step_batch_2d
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the ADI path has no CPU fallback")
+    z = load_golden2d()
+    dimx, dimy = (int(v) for v in z["dims"])
+    steps, dt, ng, nl = int(z["steps"]), float(z["dt"]), int(z["iters"][0]), int(z["iters"][1])
+    B = args.batch
+
+    def make(n):
+        out = []
+        for _ in range(n):
+            s = AdiSolver2D().Init(dimx, dimy, *[float(v) for v in z["spacing"]], *[float(v) for v in z["params"]], float(z["startT"]), 4)
+            for q in range(3):
+                s.write_field(0, q, z["layer_init"][q])
+            s.set_grid(*golden_grid(z, 0))
+            out.append(s)
+        return out
+
+    def run(solvers):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        errs = None
+        for _ in range(steps):
+            errs, _it = time_step_batch_2d(solvers, dt, ng, nl, update_boundaries=True)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, errs
+
+    run(make(2))                                   # warm-up (module load, first launches)
+    one = make(1)
+    t1, e1 = run(one)
+    many = make(B)
+    tb, eb = run(many)
+    assert all(e == eb[0] for e in eb), "the copies of a batch diverged from each other"
+    # the case with a static grid (Prepare(0) only) for all 49 steps, against the oracle doing the same
+    from oracle import oracle as O
+    O.build()
+    o = O.Oracle2D(dimx, dimy, *[float(v) for v in z["spacing"]], *[float(v) for v in z["params"]], float(z["startT"]), 4)
+    for q in range(3):
+        o.field(0, q)[:] = z["layer_init"][q]
+    o.set_grid(*golden_grid(z, 0))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.update_boundaries(); e_ref = o.time_step(dt, ng, nl)
+    tc = time.perf_counter() - t0
+    cells = dimx * dimy
+    line = {
+        "metric": "Mcell-updates/s per 2D time step", "value": B * cells * steps / tb / 1e6, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": 1,
+        "ms_per_step": tb / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "reference case data/2D/box_pipe (static grid)",
+        "config": {"workload": f"2D ADI, data/2D/box_pipe {dimx}x{dimy}, fp32, {steps} steps, num_global {ng} num_local {nl} (BASELINE config 1), {B} independent copies per launch",
+                   "batch": B},
+        "single_case": {"value": cells * steps / t1 / 1e6, "ms_per_step": t1 / steps * 1e3},
+        "parity": {"residual_last_step": eb[0], "oracle_residual_last_step": e_ref, "bit_identical": bool(eb[0] == e_ref and e1[0] == e_ref)},
+        "cpu_baseline": {"value": cells * steps / tc / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"oracle/adi2d_oracle.c (C restatement of the reference's serial AdiSolver2D, pinned bit-for-bit), the same {steps} steps"},
+        "gpu_launches": sum(s.launch_count() for s in many[:1]),
+    }
+    print(json.dumps(line))
+    for s in one + many:
+        s.close()
+    o.close()
+
+
 # ------------------------------------------------------------------------------------------------- ours
 def main():
     ap = argparse.ArgumentParser()
@@ -220,6 +293,8 @@ def main():
     ap.add_argument("--ref-size", type=int, default=0, help="grid of the reference arm's sample (0 = the largest of 512/256/128 that fits ~2 minutes)")
     ap.add_argument("--cpu-size", type=int, default=128, help="grid of the cpu_baseline leg printed with our own arm")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="weak = BASELINE config 5: 128x512x512 cells per GPU")
+    ap.add_argument("--config", default="3d", choices=["3d", "2d"], help="2d = BASELINE config 1 (data/2D/box_pipe through cmc_adi2d_*)")
+    ap.add_argument("--batch", type=int, default=296, help="--config 2d: independent cases per launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -227,6 +302,9 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         reference_arm(args)
+        return
+    if args.config == "2d":
+        bench_2d(args)
         return
 
     import numpy as np
