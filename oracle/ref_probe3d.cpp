@@ -10,7 +10,7 @@
 // bench.py's cpu_baseline / --impl reference legs may execute the resulting binary.
 //
 // usage: ref_probe3d <data> <config> <out.bin|-> <nsteps> [align] [dump=every|last|none|list:<s0,s1,..>]
-//                    [stats=<stride>] [getlayer] [dt=<v>] [sweep=<Z|Y|X>] [threads=<n>] [solver=cpu|b200|b200exact]
+//                    [stats=<stride>] [getlayer] [dt=<v>] [sweep=<Z|Y|X>] [threads=<n>] [solver=cpu|refgpu|b200|b200exact]
 //                    [gpus=<n>]
 // stats=<stride>: the steps selected by dump= are written as compact records (kind 5: per-field sum, sum of squares,
 // sum of |.|, and the strided subsample [::stride, ::stride, ::stride]) instead of whole layers - what the golden
@@ -130,16 +130,20 @@ int main(int argc, char **argv)
 		else if (!strncmp(argv[a], "solver=", 7)) which = argv[a] + 7;
 	}
 	try {
+		// solver=refgpu: the reference's OWN CUDA backend (AdiSolver3D.cu / TimeLayer3D.cu, compiled unmodified for the GPU at
+		// hand) - timing and residual only; the second baseline SURVEY.md offers.  gpus=<n> = the reference CLI's "GPU <n>"
+		const BackendType be = (which == "refgpu") ? GPU : CPU;
 		PARAplan *pplan = PARAplan::Instance();
-		pplan->init(CPU);
+		pplan->init(be);
+		if (be == GPU) pplan->setGPUnum(ngpus);
 		Config();
 		Config::LoadFromFile(argv[2]);
 
 		Grid3D *grid = NULL;
 		if (Config::in_fmt == Shape3D)
-			grid = new Grid3D(Config::dx, Config::dy, Config::dz, Config::baseT, CPU, false, EVEN_X);
+			grid = new Grid3D(Config::dx, Config::dy, Config::dz, Config::baseT, be, false, EVEN_X);
 		else if (Config::in_fmt == Shape2D)
-			grid = new Grid3D(Config::dx, Config::dy, Config::dz, Config::depth, Config::depth_var, Config::baseT, CPU, false, EVEN_X);
+			grid = new Grid3D(Config::dx, Config::dy, Config::dz, Config::depth, Config::depth_var, Config::baseT, be, false, EVEN_X);
 		else
 			throw std::runtime_error("probe: SeaNetCDF input needs libnetcdf (not available)");
 		grid->SetFrameTime(Config::frame_time);
@@ -161,16 +165,17 @@ int main(int argc, char **argv)
 		AdiSolver3D *solver = NULL;
 #ifdef WITH_B200
 		B200AdiSolver3D *b200 = NULL;
-		if (which != "cpu") {
+		if (which != "cpu" && which != "refgpu") {
 			b200 = new B200AdiSolver3D(which == "b200exact" ? CMC_MODE_EXACT : CMC_MODE_FAST, 0, ngpus);      // gpus=<n>: the reference CLI's "GPU <n>"
 			b200->Init(GPU, false, grid, *params, false, 1);
 		}
 #else
-		if (which != "cpu") throw std::runtime_error("probe: built without the B200 adapter");
+		if (which != "cpu" && which != "refgpu") throw std::runtime_error("probe: built without the B200 adapter");
 #endif
-		if (which == "cpu") {
+		if (which == "cpu" || which == "refgpu") {
 			solver = new AdiSolver3D();
-			solver->Init(CPU, false, grid, *params, false, 1);
+			if (be == GPU) solver->SetOptionsGPU(false, false);       // the driver's defaults (FluidSolver3D.cpp:63-64,187)
+			solver->Init(be, false, grid, *params, false, 1);
 		}
 
 		int frames = grid->GetFramesNum();
@@ -252,13 +257,36 @@ int main(int argc, char **argv)
 #endif
 		// half/next/temp are allocated uninitialised by the reference (TimeLayer3D.h:353).
 		// Define their initial contents (= cur) so dumps are deterministic, OUT cells included.
-		solver->cur->CopyLayerTo(solver->next);
-		solver->cur->CopyLayerTo(solver->half);
-		solver->cur->CopyLayerTo(solver->temp);
+		if (be == CPU) {
+			solver->cur->CopyLayerTo(solver->next);
+			solver->cur->CopyLayerTo(solver->half);
+			solver->cur->CopyLayerTo(solver->temp);
+		}
 
 		solver->CreateSegments();
 		grid->Prepare(0);
 		printf("probe: segments X %d Y %d Z %d\n", solver->numSegs[X], solver->numSegs[Y], solver->numSegs[Z]);
+		if (be == GPU) {
+			// timing + residual only (the layers live on the device)
+			double t_steps = 0.0;
+			for (int i = 0; i < nsteps; i++) {
+				bool computeError = (i % 10 == 0) || (i == nsteps - 1);
+				cudaDeviceSynchronize();
+				double t0 = omp_get_wtime();
+				solver->UpdateBoundaries();
+				solver->TimeStep((FTYPE)dt, Config::num_global, Config::num_local, computeError);
+				cudaDeviceSynchronize();
+				const double t1 = omp_get_wtime();
+				t_steps += t1 - t0;
+				printf("\nprobe: refgpu step %d seconds %.6f err %.10g\n", i, t1 - t0, solver->diffError);
+			}
+			printf("\nprobe: refgpu steps %d, seconds %.6f, sec_per_step %.6f, mcells_per_s %.6f, err %.10g\n",
+				nsteps, t_steps, nsteps ? t_steps / nsteps : 0.0,
+				(nsteps && t_steps > 0) ? (double)N * nsteps / t_steps / 1e6 : 0.0, solver->diffError);
+			if (g_out) fclose(g_out);
+			fflush(stdout);
+			_Exit(0);
+		}
 
 		if (!sweep.empty()) {
 			// component vector: the TimeStep prologue (AdiSolver3D.cpp:310-320) followed by ONE

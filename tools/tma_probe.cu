@@ -77,6 +77,71 @@ __global__ void __launch_bounds__(128, 1) k_probe(const __grid_constant__ Maps T
 	(void)next_box;
 }
 
+
+// The same tiles pulled by 1-D bulk copies (cp.async.bulk, UBLKCP): every thread issues the 64-byte row segments of its
+// own rows, one instruction per row.  Does the copy engine take many small independent requests faster than the rows of
+// one tensor box?
+template <int NSLOT>
+__global__ void __launch_bounds__(128, 1) k_probe_bulk(const double *const *fields, int ntiles, int ktiles, int *counter, int slot_bytes,
+                                                      long long plane, long long bstride, int nzp, int jbm, int jbs, int nrows, int row_bytes, long long *sink)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	unsigned long long *full = reinterpret_cast<unsigned long long *>(smem + (size_t)NSLOT * slot_bytes);
+	__shared__ int next_tile;
+	const int t = threadIdx.x;
+	if (t == 0) {
+		for (int s = 0; s < NSLOT; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(full + s)));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	__syncthreads();
+	unsigned ph = 0;
+	int issued = 0;
+	int tile = blockIdx.x;
+	while (tile < ntiles) {
+		const int jj = tile / ktiles, k0 = (tile - jj * ktiles) * (row_bytes / 8);
+		const int j = jj & 511, half = jj >> 9;          // (128-byte rows: two half-height tiles per line position)
+		const long long tbase = (long long)(j >> jbs) * bstride + (1 + (long long)half * nrows) * plane + (long long)(j & jbm) * nzp + k0;
+		for (int f = 0; f < 11; f++) {
+			const int s = issued % NSLOT;
+			if (t == 0) {
+				if (issued >= NSLOT) {
+					const unsigned par = (ph >> s) & 1u;
+					unsigned ok = 0;
+					while (!ok)
+						asm volatile("{ .reg .pred P1; mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x100000; selp.u32 %0, 1, 0, P1; }"
+						             : "=r"(ok) : "r"(smem_u32(full + s)), "r"(par) : "memory");
+					ph ^= 1u << s;
+				}
+				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(full + s)), "r"(slot_bytes) : "memory");
+			}
+			__syncthreads();
+			const double *src = fields[f % 8] + tbase;
+			for (int r = t; r < nrows; r += 128)
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				             ::"r"(smem_u32(smem + (size_t)s * slot_bytes + (size_t)r * row_bytes)), "l"(src + (long long)r * plane), "r"(row_bytes),
+				             "r"(smem_u32(full + s)) : "memory");
+			issued++;
+		}
+		if (t == 0) next_tile = (int)gridDim.x + atomicAdd(counter, 1);
+		__syncthreads();
+		tile = next_tile;
+		__syncthreads();
+	}
+	if (t == 0) {
+		for (int w = issued > NSLOT ? issued - NSLOT : 0; w < issued; w++) {
+			const int s = w % NSLOT;
+			const unsigned par = (ph >> s) & 1u;
+			unsigned ok = 0;
+			while (!ok)
+				asm volatile("{ .reg .pred P1; mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x100000; selp.u32 %0, 1, 0, P1; }"
+				             : "=r"(ok) : "r"(smem_u32(full + s)), "r"(par) : "memory");
+			ph ^= 1u << s;
+		}
+		if (issued == -1) *sink = 1;
+	}
+}
+
 int main()
 {
 	const int nx = 512, ny = 512, nz = 512, nzp = 512, jb = 64, jbs = 6, jbm = 63;
@@ -135,5 +200,33 @@ int main()
 			};
 			run(k_probe<2>, 2); run(k_probe<4>, 4); run(k_probe<6>, 6);
 		}
+	// 1-D bulk copies, x tiles only: 512 rows of 64 / 128 bytes per field per tile
+	{
+		const double **dfields;
+		CK(cudaMalloc(&dfields, 8 * sizeof(double *)));
+		CK(cudaMemcpy(dfields, fields, 8 * sizeof(double *), cudaMemcpyHostToDevice));
+		for (int kw = 8; kw <= 16; kw *= 2) {
+			const int nrows = 512 * 8 / kw;                 // rows per slot so that a slot stays 32 KB
+			const int slot_bytes = nrows * kw * 8, ktiles = nz / kw, ntiles = ny * ktiles * (kw / 8);
+			auto run = [&](auto kern, int nslot) {
+				const size_t smem = (size_t)nslot * slot_bytes + 64;
+				CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				float best = 1e9f;
+				for (int rep = 0; rep < 3; rep++) {
+					CK(cudaMemset(counter, 0, 4));
+					cudaEventRecord(e0);
+					kern<<<148, 128, smem>>>(dfields, ntiles, ktiles, counter, slot_bytes, plane, bstride, nzp, jbm, jbs, nrows, kw * 8, sink);
+					cudaEventRecord(e1);
+					CK(cudaDeviceSynchronize());
+					float ms; cudaEventElapsedTime(&ms, e0, e1);
+					if (ms < best) best = ms;
+				}
+				const double bytes = (double)ntiles * 11 * slot_bytes;
+				printf("1-D bulk copies, x rows of %3d B, %d rows per slot, %d slots in flight: %.3f ms  %.0f GB/s delivered to shared memory\n",
+				       kw * 8, nrows, nslot, best, bytes / best / 1e6);
+			};
+			run(k_probe_bulk<4>, 4); run(k_probe_bulk<6>, 6);
+		}
+	}
 	return 0;
 }
