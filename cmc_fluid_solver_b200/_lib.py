@@ -19,7 +19,7 @@ SYMBOLS = [
     "cmc_adi3d_eval_div_error", "cmc_adi3d_field_sums", "cmc_adi3d_time_step_async", "cmc_adi3d_sync", "cmc_adi3d_stream",
     "cmc_adi3d_launch_count", "cmc_adi3d_get_timing", "cmc_adi3d_device_bytes", "cmc_solve_tridiagonal_batch",
     "cmc_adi2d_create", "cmc_adi2d_destroy", "cmc_adi2d_set_grid", "cmc_adi2d_init_layer", "cmc_adi2d_update_boundaries",
-    "cmc_adi2d_time_step", "cmc_adi2d_time_step_batch", "cmc_adi2d_get_layer", "cmc_adi2d_read_field", "cmc_adi2d_write_field", "cmc_adi2d_launch_count",
+    "cmc_adi2d_time_step", "cmc_adi2d_step_host", "cmc_adi2d_time_step_batch", "cmc_adi2d_get_layer", "cmc_adi2d_read_field", "cmc_adi2d_write_field", "cmc_adi2d_launch_count",
 ]
 
 
@@ -101,6 +101,7 @@ def load_library() -> C.CDLL:
         "cmc_adi2d_init_layer": [vp],
         "cmc_adi2d_update_boundaries": [vp],
         "cmc_adi2d_time_step": [vp, dbl, i32, i32, P(dbl), P(i32)],
+        "cmc_adi2d_step_host": [vp, vp, vp, vp, vp, vp, P(vp), P(vp), dbl, i32, i32, P(dbl), P(i32)],
         "cmc_adi2d_time_step_batch": [P(vp), i32, dbl, i32, i32, i32, P(dbl), P(i32), P(i32)],
         "cmc_adi2d_get_layer": [vp, vp, vp, i32, i32],
         "cmc_adi2d_read_field": [vp, i32, i32, vp],

@@ -81,6 +81,7 @@ struct cmc_adi3d {
 	long long shared_free[3] = {0, 0, 0};   // cells shared by two segments with a BC_FREE row (informational)
 	int mode = CMC_MODE_FAST;
 	int tma_mask = default_tma_mask();
+	int tma_shape = 0;               // option "tma_shape": 0 = automatic, else lines per tile + 256 * CTAs per tile (kernels_tma.cu)
 	static int default_tma_mask()
 	{
 		// default: both strided axes (measured at 512^3 fp64 on B200: x 5.14 -> 4.44 ms, y 5.07 -> 4.36 ms per launch against
@@ -797,6 +798,7 @@ struct Engine : cmc_adi3d {
 		A.xcoef = s->xcoef_send; A.xbnd = s->xbnd_recv; A.lpo = (int)s->lines_per_owner(nslabs_total);
 		A.extra_merge = 0;
 		A.tile_counter = s->d_tilectr;
+		A.tma_shape = tma_shape;
 		for (int q = 0; q < 4; q++) A.push_lo[q] = A.push_hi[q] = A.pushn_lo[q] = A.pushn_hi[q] = nullptr;
 		for (int r = 0; r < MAX_SLABS; r++) A.xcoef_to[r] = nullptr;
 		if (multi()) {
@@ -1656,6 +1658,11 @@ int cmc_adi3d_set_option(cmc_adi3d *h, const char *key, int64_t value)
 		return CMC_OK;
 	}
 	if (!strcmp(key, "tma")) { h->tma_mask = (int)value & 3; return CMC_OK; }
+	if (!strcmp(key, "tma_shape")) {
+		const int nl = (int)value & 255, cl = (int)value >> 8;
+		if (value != 0 && !((nl == 8 || nl == 16) && (cl == 1 || cl == 2))) return fail(CMC_ERR_INVALID, "set_option tma_shape: 0, or lines per tile (8 | 16) + 256 * CTAs per tile (1 | 2)");
+		h->tma_shape = (int)value; return CMC_OK;
+	}
 	if (!strcmp(key, "profile")) {
 		h->spans_collect();
 		h->profile = value != 0;
@@ -1671,6 +1678,7 @@ int cmc_adi3d_get_option(const cmc_adi3d *h, const char *key, int64_t *value)
 	if (!key || !value) return fail(CMC_ERR_INVALID, "get_option: null argument");
 	if (!strcmp(key, "mode")) { *value = h->mode; return CMC_OK; }
 	if (!strcmp(key, "tma")) { *value = h->tma_mask; return CMC_OK; }
+	if (!strcmp(key, "tma_shape")) { *value = h->tma_shape; return CMC_OK; }
 	if (!strcmp(key, "nzp")) { *value = h->L.nzp; return CMC_OK; }
 	if (!strcmp(key, "jb")) { *value = h->L.nblk == 1 ? 0 : (1 << h->L.jbs); return CMC_OK; }   // rows per y-block, 0 = one block
 	if (!strncmp(key, "kernel_", 7) && key[7] >= 'x' && key[7] <= 'z' && !key[8]) { *value = h->kernel_kind(key[7] - 'x'); return CMC_OK; }

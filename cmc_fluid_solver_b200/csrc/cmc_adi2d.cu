@@ -275,6 +275,8 @@ struct cmc_adi2d {
 	virtual int init_layer() = 0;
 	virtual int update_boundaries() = 0;
 	virtual int time_step(double dt, int ng, int nl, double *err, int *iters) = 0;
+	virtual int step_host(const int32_t *type, const int32_t *bc, const void *vx, const void *vy, const void *T, void *const cur[3], void *const next[3],
+	                      double dt, int ng, int nl, double *err, int *iters) = 0;
 	virtual int get_layer(void *vel, double *T, int ox, int oy) = 0;
 	virtual int rw_field(int layer, int var, void *dst, const void *src) = 0;
 	virtual const void *dev_params(double dt) = 0;
@@ -305,12 +307,17 @@ struct Engine2D : cmc_adi2d {
 	std::vector<void *> allocs;
 	cudaStream_t stream = nullptr;
 	bool have_grid = false;
+	// everything a host-driven step moves lives in ONE device block, mirrored by one pinned host block:
+	// [cur u v T | next u v T | grid vx vy T | type | bc] - one copy up, one copy (the first six arrays) down (step_host)
+	unsigned char *io_dev = nullptr, *io_host = nullptr;
+	size_t io_bytes = 0;
 
 	~Engine2D() override
 	{
 		cudaSetDevice(device);
 		if (stream) cudaStreamSynchronize(stream);
 		for (void *p : allocs) cudaFree(p);
+		if (io_host) cudaFreeHost(io_host);
 		if (stream) cudaStreamDestroy(stream);
 	}
 	template <typename T>
@@ -330,12 +337,17 @@ struct Engine2D : cmc_adi2d {
 		P.v_T = (FT)fp_->v_T; P.v_vis = (FT)fp_->v_vis; P.t_vis = (FT)fp_->t_vis; P.t_phi = (FT)fp_->t_phi; P.startT = (FT)startT;
 		const size_t N = (size_t)dimx * dimy, maxn = (size_t)std::max(dimx, dimy);
 		int rc;
-		int *ty = nullptr, *bc = nullptr; FT *g[3] = {};
-		if ((rc = dalloc(ty, N)) || (rc = dalloc(bc, N))) return rc;
-		for (auto &p : g) if ((rc = dalloc(p, N))) return rc;
-		P.type = ty; P.bc = bc; P.gvx = g[0]; P.gvy = g[1]; P.gT = g[2];
+		io_bytes = 9 * N * sizeof(FT) + 2 * N * sizeof(int);
+		if ((rc = dalloc(io_dev, io_bytes))) return rc;
+		CU2(cudaMallocHost((void **)&io_host, io_bytes));
+		FT *fb = reinterpret_cast<FT *>(io_dev);
+		for (int q = 0; q < 3; q++) { P.f[L2_CUR][q] = fb + q * N; P.f[L2_NEXT][q] = fb + (3 + q) * N; }
+		P.gvx = fb + 6 * N; P.gvy = fb + 7 * N; P.gT = fb + 8 * N;
+		P.type = reinterpret_cast<const int *>(fb + 9 * N); P.bc = P.type + N;
 		// the reference allocates half / next / temp / next_local uninitialised (TimeLayer2D.h:176-181): zero here
-		for (int l = 0; l < L2_COUNT; l++) for (int q = 0; q < 3; q++) if ((rc = dalloc(P.f[l][q], N))) return rc;
+		for (int l = 0; l < L2_COUNT; l++)
+			if (l != L2_CUR && l != L2_NEXT)
+				for (int q = 0; q < 3; q++) if ((rc = dalloc(P.f[l][q], N))) return rc;
 		if ((rc = dalloc(P.listX, (size_t)dimx)) || (rc = dalloc(P.listY, (size_t)dimy))) return rc;
 		if ((rc = dalloc(P.scratch, 3 * maxn * 5 * maxn))) return rc;
 		if ((rc = dalloc(P.resid, N))) return rc;
@@ -388,6 +400,30 @@ struct Engine2D : cmc_adi2d {
 		k_adi2d_time_step<FT><<<1, 1024, 0, stream>>>(d_self, ng, nl);
 		launches++;
 		return collect(err, iters);
+	}
+	// set_grid + the host's cur / next layers up, one step, both layers down: two copies and one synchronisation
+	int step_host(const int32_t *type, const int32_t *bc, const void *vx, const void *vy, const void *T, void *const cur[3], void *const next[3],
+	              double dt, int ng, int nl, double *err, int *iters) override
+	{
+		if (ng < 0 || nl < 0) return cmc_set_error(CMC_ERR_INVALID, "adi2d step_host: negative iteration count");
+		CU2(cudaSetDevice(device));
+		const size_t N = (size_t)dimx * dimy, B = N * sizeof(FT);
+		for (size_t i = 0; i < N; i++)
+			if (type[i] < 0 || type[i] > 3 || bc[i] < 0 || bc[i] > 1) return cmc_set_error(CMC_ERR_INVALID, "adi2d step_host: node type / boundary type out of range");
+		for (int q = 0; q < 3; q++) { memcpy(io_host + q * B, cur[q], B); memcpy(io_host + (3 + q) * B, next[q], B); }
+		memcpy(io_host + 6 * B, vx, B); memcpy(io_host + 7 * B, vy, B); memcpy(io_host + 8 * B, T, B);
+		memcpy(io_host + 9 * B, type, N * sizeof(int)); memcpy(io_host + 9 * B + N * sizeof(int), bc, N * sizeof(int));
+		CU2(cudaMemcpyAsync(io_dev, io_host, io_bytes, cudaMemcpyHostToDevice, stream));
+		have_grid = true;
+		P.dt = (FT)dt;
+		CU2(cudaMemcpyAsync(d_self, &P, sizeof P, cudaMemcpyHostToDevice, stream));
+		k_adi2d_time_step<FT><<<1, 1024, 0, stream>>>(d_self, ng, nl);
+		launches++;
+		CU2(cudaMemcpyAsync(io_host, io_dev, 6 * B, cudaMemcpyDeviceToHost, stream));
+		const int rc = collect(err, iters);          // synchronises
+		if (rc != CMC_OK && rc != CMC_ERR_DIVERGED) return rc;
+		for (int q = 0; q < 3; q++) { memcpy(cur[q], io_host + q * B, B); memcpy(next[q], io_host + (3 + q) * B, B); }
+		return rc;
 	}
 	int collect(double *err, int *iters)
 	{
@@ -481,6 +517,15 @@ int cmc_adi2d_time_step(cmc_adi2d *h, double dt, int num_global, int num_local, 
 {
 	H2(h);
 	return h->time_step(dt, num_global, num_local, err_out, iters_out);
+}
+int cmc_adi2d_step_host(cmc_adi2d *h, const int32_t *type, const int32_t *bc_type, const void *vx, const void *vy, const void *T, void *const cur_uvT[3],
+                        void *const next_uvT[3], double dt, int num_global, int num_local, double *err_out, int *iters_out)
+{
+	H2(h);
+	if (!type || !bc_type || !vx || !vy || !T || !cur_uvT || !next_uvT) return cmc_set_error(CMC_ERR_INVALID, "adi2d step_host: null argument");
+	for (int q = 0; q < 3; q++)
+		if (!cur_uvT[q] || !next_uvT[q]) return cmc_set_error(CMC_ERR_INVALID, "adi2d step_host: null layer array");
+	return h->step_host(type, bc_type, vx, vy, T, cur_uvT, next_uvT, dt, num_global, num_local, err_out, iters_out);
 }
 int cmc_adi2d_get_layer(cmc_adi2d *h, void *vel_xy, double *T, int outdimx, int outdimy)
 {

@@ -96,6 +96,7 @@ struct SweepArgs {
 	int lpo;                 // lines per owner rank of the interface solve
 	int extra_merge;         // fast mode: apply the relaxation twice (folds the post-X MergeLayerTo, AdiSolver3D.cpp:354)
 	int *tile_counter;       // persistent-CTA kernels (kernels_tma.cu): next tile to hand out; zeroed before every launch
+	int tma_shape;           // kernels_tma.cu: 0 = automatic tile shape, else lines per tile + 256 * CTAs per tile
 	// ---- slab-decomposed runs: exchanges fused into the sweeps as stores into the other slabs' buffers (peer memory
 	// over NVLink when the slabs live on different GPUs, see dist.h) --------------------------------------------------
 	// boundary x-planes of the sweep's outputs -> the x-neighbours' guard planes.  Each pointer addresses the target

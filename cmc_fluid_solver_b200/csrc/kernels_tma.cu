@@ -65,18 +65,18 @@ static EncodeTiledFn encode_fn()
 // One map per (field buffer, direction, layout): the layers rotate through a handful of physical buffers, so the maps
 // are built once and cached.
 struct MapKey {
-	const void *ptr; long long bstride; int dir, fp, gp, nx, ny, nz, jbs;
+	const void *ptr; long long bstride; int dir, fp, gp, nl, nx, ny, nz, jbs;
 	bool operator<(const MapKey &o) const { return memcmp(this, &o, sizeof(MapKey)) < 0; }
 };
 
 template <typename FT>
-static bool tensor_map_for(const FT *field, const Layout &L, int dir, int GP, CUtensorMap *out)
+static bool tensor_map_for(const FT *field, const Layout &L, int dir, int GP, int NL, CUtensorMap *out)
 {
 	static std::map<MapKey, CUtensorMap> cache;
 	static std::mutex mu;
 	MapKey key;
 	memset(&key, 0, sizeof key);
-	key.ptr = field; key.bstride = L.bstride; key.dir = dir; key.fp = (int)sizeof(FT); key.gp = GP; key.nx = L.nx; key.ny = L.ny; key.nz = L.nz; key.jbs = L.jbs;
+	key.ptr = field; key.bstride = L.bstride; key.dir = dir; key.fp = (int)sizeof(FT); key.gp = GP; key.nl = NL; key.nx = L.nx; key.ny = L.ny; key.nz = L.nz; key.jbs = L.jbs;
 	std::lock_guard<std::mutex> lock(mu);
 	auto it = cache.find(key);
 	if (it != cache.end()) { *out = it->second; return true; }
@@ -91,7 +91,7 @@ static bool tensor_map_for(const FT *field, const Layout &L, int dir, int GP, CU
 		// (k, chunk along x, row in chunk, j inside its y-block, y-block); plane 0 is the first real plane
 		dims[0] = (cuuint64_t)L.nzp; dims[1] = (cuuint64_t)(L.nx / M); dims[2] = M; dims[3] = (cuuint64_t)rows_per_block; dims[4] = (cuuint64_t)L.nblk;
 		strides[0] = (cuuint64_t)(M * L.plane) * es; strides[1] = (cuuint64_t)L.plane * es; strides[2] = (cuuint64_t)L.nzp * es; strides[3] = (cuuint64_t)L.bstride * es;
-		box[0] = 8; box[1] = (cuuint32_t)GP; box[2] = M; box[3] = 1; box[4] = 1;
+		box[0] = (cuuint32_t)NL; box[1] = (cuuint32_t)GP; box[2] = M; box[3] = 1; box[4] = 1;
 		base = (void *)(field + L.plane);
 	} else {
 		// (k, chunk inside a y-block, y-block, row in chunk, x-plane incl. the guard planes)
@@ -99,7 +99,7 @@ static bool tensor_map_for(const FT *field, const Layout &L, int dir, int GP, CU
 		dims[0] = (cuuint64_t)L.nzp; dims[1] = (cuuint64_t)gb; dims[2] = (cuuint64_t)L.nblk; dims[3] = M; dims[4] = (cuuint64_t)(L.nx + 2);
 		strides[0] = (cuuint64_t)(M * L.nzp) * es; strides[1] = (cuuint64_t)L.bstride * es; strides[2] = (cuuint64_t)L.nzp * es; strides[3] = (cuuint64_t)L.plane * es;
 		const int bg = L.nblk > 1 ? gb : GP;            // chunks of one y-block in the box; GP / bg blocks
-		box[0] = 8; box[1] = (cuuint32_t)bg; box[2] = (cuuint32_t)(GP / bg); box[3] = M; box[4] = 1;
+		box[0] = (cuuint32_t)NL; box[1] = (cuuint32_t)bg; box[2] = (cuuint32_t)(GP / bg); box[3] = M; box[4] = 1;
 		base = (void *)field;
 	}
 	const CUtensorMapDataType dt = sizeof(FT) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
@@ -197,50 +197,121 @@ __device__ __forceinline__ void store8_stream(FT *__restrict__ p, const int (&of
 	}
 }
 
+// ---- cluster helpers (CL == 2: two CTAs on neighbouring SMs share a tile, each takes half of every line) --------------------
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+	unsigned r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+	asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory object in the CTA `rank` of the cluster
+__device__ __forceinline__ unsigned peer_smem(const void *p, unsigned rank)
+{
+	unsigned r;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+	return r;
+}
+__device__ __forceinline__ void st_cluster(unsigned addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+__device__ __forceinline__ void st_cluster(unsigned addr, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void st_cluster(unsigned addr, int v) { asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_peer(unsigned bar_addr)
+{
+	asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long *bar, unsigned parity)
+{
+	long long t0 = 0;
+	for (int tries = 0;; tries++) {
+		unsigned ok;
+		asm volatile(
+			"{\n\t"
+			".reg .pred P1;\n\t"
+			"mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2, 0x100000;\n\t"
+			"selp.u32 %0, 1, 0, P1;\n\t"
+			"}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+		if (ok) return;
+		if ((tries & 63) == 63) {
+			const long long now = clock64();
+			if (!t0) t0 = now;
+			else if (now - t0 > 4000000000ll) __trap();
+		}
+	}
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------------------------------
-template <typename FT, int DIR, int GP>
-__global__ void __launch_bounds__(GP * 8, GP >= 64 ? 1 : 2)
+// GP chunks x NL lines per CTA (GP * NL threads).  CL = CTAs per tile:
+//   CL 1: the CTA holds whole lines (up to GP * 8 rows);
+//   CL 2: a cluster of two CTAs holds a tile of NL lines, each CTA one half of every line.  What that buys is the tile
+//         shape: 16 lines x 256 rows fit the same 32 KB slots as 8 lines x 512 rows, and a 16-line fp64 tile has 128-byte
+//         rows, which the copy engine delivers twice as fast as 64-byte rows (tools/tma_probe.cu).  The two halves of a
+//         line are coupled like two slabs of a decomposed grid (kernels_fast.cu MODE 1 / 2), except that nothing is
+//         read twice: each CTA eliminates its half, solves its reduced system with one extra right-hand side (the
+//         response to the unknown row of the other half), the CTAs swap 4 numbers per line and phase through distributed
+//         shared memory, and every thread finishes its rows from registers.
+template <typename FT, int DIR, int GP, int NL, int CL>
+__global__ void __launch_bounds__(GP * NL, GP * NL >= 512 ? 1 : 512 / (GP * NL))
 k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant__ TmaMaps TM, const int ntiles, const int hints)
 {
 	static_assert(DIR == 0 || DIR == 1, "strided axes only (z lines are contiguous: kernels_fast.cu)");
-	constexpr int NL = 8;
+	static_assert(NL == 8 || NL == 16, "8 or 16 lines per tile");
+	static_assert(CL == 1 || CL == 2, "one CTA or a CTA pair per tile");
 	constexpr int STR = GP * NL;
 	constexpr int GS = NL;                          // shared-memory distance of neighbouring chunks of a line
-	constexpr int SLOT = STR * M;                   // elements per slot: one field of one tile
+	constexpr int SLOT = STR * M;                   // elements per slot: one field of one tile (part)
 	constexpr int NW = STR / 32;                    // warps
+	constexpr int NS = 5;                           // slots
+	constexpr int XV = CL == 2 ? 1 : 0;             // extra right-hand sides of the reduced solves (CL 2: one spike column)
 	constexpr unsigned SLOT_BYTES = SLOT * (unsigned)sizeof(FT);
 	// the two temp components other than the one along the sweep, and their slots
 	constexpr int QO1 = DIR == 0 ? 1 : 0, QO2 = 2;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	FT *slots = reinterpret_cast<FT *>(smem_raw);                                   // 6 slots
-	FT *sys = slots + 6 * SLOT;                                                     // reduced-solve scratch
+	FT *slots = reinterpret_cast<FT *>(smem_raw);                                   // NS slots
+	FT *sys = slots + NS * SLOT;                                                    // reduced-solve scratch
 	FT *sol = sys;                                                                  // aliases the CR publications (see reduced_solve)
-	FT *headx = sys + reduced_scratch_elems<3, GP, NL>();                           // heads that cross a warp: 5 x (NW * 8)
-	uint8_t *roles = reinterpret_cast<uint8_t *>(headx + 5 * NW * 8);               // descriptor bytes of the tile: 8 * STR
-	unsigned long long *full = reinterpret_cast<unsigned long long *>(roles + 8 * STR);   // 6 mbarriers
-	int *next_box = reinterpret_cast<int *>(full + 6);                                    // the tile after the current one
+	FT *headx = sys + reduced_scratch_elems<3 + XV, GP, NL>();                      // heads that cross a warp: 5 x (NW * NL)
+	FT *edge = headx + 5 * NW * NL;                                                 // CL 2: the row next to this half, 4 fields x NL
+	FT *xown = edge + (CL == 2 ? 4 * NL : 0);                                       // CL 2: this half's interface coefficients [6][NL]
+	FT *xin = xown + (CL == 2 ? 6 * NL : 0);                                        // CL 2: the other half's, written by the peer CTA
+	uint8_t *roles = reinterpret_cast<uint8_t *>(xin + (CL == 2 ? 6 * NL : 0));     // descriptor bytes of the tile: NL * GP * 8
+	unsigned long long *full = reinterpret_cast<unsigned long long *>(roles + NL * GP * 8);   // NS mbarriers (+ 2 for the exchange)
+	unsigned long long *xbar = full + NS;                                                 // CL 2: [0] u,v,w phase, [1] T phase
+	int *next_box = reinterpret_cast<int *>(full + NS + 2);                               // the tile after the current one
 #define SLOTP(k) (slots + (k) * SLOT)
 
 	const Layout &L = A.L;
 	const int t = threadIdx.x;
-	const int l = t % NL, g = t / NL;               // line in tile, chunk
+	const int l = t % NL, g = t / NL;               // line in tile, chunk (of this CTA's part of the line)
 	const int e = t;                                // == g * NL + l
 	const int lane = t & 31, warp = t >> 5;
-	const int r0 = g * M;
-	const int n = DIR == 0 ? L.nx : L.ny;
-	const int GL = n / M;                           // chunks that hold real rows (n % 8 == 0)
+	const unsigned crank = CL == 2 ? cluster_ctarank() : 0u;
+	const int n = DIR == 0 ? L.nx : L.ny;           // rows of a line
+	const int nloc = n / CL;                        // rows of this CTA's part
+	const int row0 = (int)crank * nloc;             // first row of this CTA's part
+	const int GL = nloc / M;                        // chunks that hold real rows (nloc % 8 == 0)
+	const int r0 = row0 + g * M;                    // first row of this chunk in the line
 	const int ktiles = (L.nz + NL - 1) / NL;
 	const int stride = DIR == 0 ? (int)L.plane : (int)L.nzp;        // between the rows of a chunk
+	const int cid = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // tile-processing unit: CTA or CTA pair
+	const int nunits = (int)gridDim.x / CL;
+	// open ends of this part (CL 2): the other half continues the line there
+	const bool open_lo = CL == 2 && crank == 1, open_hi = CL == 2 && crank == 0;
 
 	if (t == 0) {
 #pragma unroll
-		for (int s = 0; s < 6; s++) mbar_init(full + s, 1);
+		for (int s = 0; s < NS; s++) mbar_init(full + s, 1);
+		if (CL == 2) { mbar_init(xbar + 0, NL + (crank == 1 ? 1 : 0)); mbar_init(xbar + 1, NL); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
 	__syncthreads();
-	unsigned ph = 0;                                // phase parity of every slot's mbarrier
+	if (CL == 2) cluster_sync_all();                // the peer's barriers exist before anything arrives on them
+	unsigned ph = 0;                                // phase parity of every slot's mbarrier (bits NS, NS + 1: the exchange barriers)
 #define WAIT_SLOT(s) do { mbar_wait(full + (s), (ph >> (s)) & 1u); ph ^= 1u << (s); } while (0)
+#define WAIT_XCHG(w) do { mbar_wait_cluster(xbar + (w), (ph >> (NS + (w))) & 1u); ph ^= 1u << (NS + (w)); } while (0)
 
 	// L2 policies (hints bit 0): the `cur` fields are read exactly once per sweep -> evict-first; the temp fields are
 	// read again within a tile time (the cross-line neighbours of the adjacent tiles, the second copy of temp.T) -> evict-last
@@ -250,64 +321,85 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 	auto issue = [&](int s, const CUtensorMap *map, int tile, int shift, int keep) {
 		const int a = tile / ktiles, k0 = (tile - a * ktiles) * NL;       // a = j (x lines) or i (y lines)
 		mbar_expect_tx(full + s, SLOT_BYTES);
-		int c3, c4;
+		int c1 = 0, c2 = 0, c3, c4;
 		if (DIR == 0) {
 			const int j = min(max(a + shift, 0), L.ny - 1);
-			c3 = j & L.jbm; c4 = j >> L.jbs;
-		} else { c3 = 0; c4 = a + 1 + shift; }
-		if (hints & 1) tma_load_5d_hint(SLOTP(s), map, full + s, k0, 0, 0, c3, c4, keep ? pol_keep : pol_once);
-		else tma_load_5d(SLOTP(s), map, full + s, k0, 0, 0, c3, c4);
+			c1 = (int)crank * GL; c3 = j & L.jbm; c4 = j >> L.jbs;
+		} else {
+			// (chunk inside a y-block, y-block): the upper half starts GL chunks further along the line
+			if (L.nblk > 1) c2 = ((int)crank * nloc) >> L.jbs; else c1 = (int)crank * GL;
+			c3 = 0; c4 = a + 1 + shift;
+		}
+		if (hints & 1) tma_load_5d_hint(SLOTP(s), map, full + s, k0, c1, c2, c3, c4, keep ? pol_keep : pol_once);
+		else tma_load_5d(SLOTP(s), map, full + s, k0, c1, c2, c3, c4);
 	};
-	auto issue_A = [&](int tile) {                 // u,v,w phase inputs
+	// Slot plan (five slots, eleven copies per tile, each issued a solve phase or more before its use):
+	//   slot 0: temp[DIR]            (resident from the u,v,w phase to the dissipation function)
+	//   slot 1: temp.T -> the first other temp component
+	//   slot 2: cur.u  -> the second other temp component
+	//   slot 3: cur.v  -> temp[DIR] of the cross-line neighbour below -> cur.T
+	//   slot 4: cur.w  -> temp[DIR] of the cross-line neighbour above -> temp.T (relaxation of T at the end)
+	auto issue_A = [&](int tile) {                 // u,v,w phase inputs but cur.w (its slot is busy until the tile ends)
 		issue(0, &TM.temp[DIR], tile, 0, 1);
 		issue(1, &TM.temp[3], tile, 0, 1);
 		issue(2, &TM.cur[0], tile, 0, 0);
 		issue(3, &TM.cur[1], tile, 0, 0);
-		issue(4, &TM.cur[2], tile, 0, 0);
 	};
-	// descriptor bytes: 8 per tile row, thread <-> tile row
+	// descriptor bytes: NL per tile row, thread <-> tile row; CL 2: plus the row of the linearisation layer next to this half
 	auto issue_roles = [&](int tile) {
 		const int a = tile / ktiles, k0 = (tile - a * ktiles) * NL;
-		const int r = min(t, n - 1);
-		const long long o = DIR == 0 ? L.idx(r, a, k0) : L.idx(a, r, k0);
-		cp_async8(roles + (size_t)t * 8, A.role + o);
+		if (t < GP * M) {
+			const int r = min(row0 + t, n - 1);
+			const long long o = DIR == 0 ? L.idx(r, a, k0) : L.idx(a, r, k0);
+#pragma unroll
+			for (int c = 0; c < NL / 8; c++) cp_async8(roles + (size_t)t * NL + c * 8, A.role + o + c * 8);
+		}
+		if (CL == 2 && t < 4 * NL) {
+			const int q = t / NL, ll = t - q * NL;
+			const int r = crank == 0 ? nloc : row0 - 1, kk = min(k0 + ll, L.nz - 1);
+			const long long o = DIR == 0 ? L.idx(r, a, kk) : L.idx(a, r, kk);
+			cp_async_elem<FT>(edge + t, A.temp[q] + o);
+		}
 		cp_async_commit();
 	};
 
-	// Tiles are handed out dynamically (the first gridDim.x statically, then in index order through an atomic counter):
+	// Tiles are handed out dynamically (the first ones statically, then in index order through an atomic counter):
 	// SMs that run a little faster take more tiles, and - what matters for HBM traffic - tiles that are neighbours in
 	// memory (adjacent k-tiles share their 128-byte lines, adjacent rows are each other's cross-line neighbours) are in
 	// flight at about the same time on different SMs, so the second request for a line finds it in L2.  With a static
 	// stride the CTAs drift apart and every line is fetched from HBM twice (ncu: 15.5 GB read against 8.7 algorithmic).
-	int tile = blockIdx.x;
+	int tile = cid;
 	if (tile < ntiles) {
-		if (t == 0) { issue_A(tile); issue(5, &TM.cur[3], tile, 0, 0); }
+		if (t == 0) { issue_A(tile); issue(4, &TM.cur[2], tile, 0, 0); }
 		issue_roles(tile);
 	}
 
 	// (thread 0 asks for the next tile at the top of an iteration and first looks at the answer when it issues that tile's
 	// copies, half a tile later: the latency of the atomic is never waited for; the other threads learn the index behind
-	// the next barrier)
+	// a later barrier.  CL 2: the first CTA of the pair asks and passes the answer on with the first exchange.)
 	while (tile < ntiles) {
 		int fetched = 0;
-		if (t == 0) fetched = (int)gridDim.x + atomicAdd(A.tile_counter, 1);
+		if (t == 0 && crank == 0) fetched = nunits + atomicAdd(A.tile_counter, 1);
 		int next_tile = ntiles;
 		const int a = tile / ktiles, k0 = (tile - a * ktiles) * NL;
 		const int k = k0 + l;
 		const bool line_ok = k < L.nz;
 		// global offsets of the chunk's rows (stores, boundary-row node values, edge-line k +- 1 loads)
 		const int rc = min(r0, n - 1);              // (padding chunks: clamped, never stored)
+		const bool chunk_ok = g < GL;
 		const int off0 = (int)(DIR == 0 ? L.idx(rc, a, line_ok ? k : 0) : L.idx(a, rc, line_ok ? k : 0));
 		int off[M];
 #pragma unroll
-		for (int i = 0; i < M; i++) off[i] = off0 + (r0 < n ? i : 0) * stride;
+		for (int i = 0; i < M; i++) off[i] = off0 + (chunk_ok ? i : 0) * stride;
 		// distance from the chunk's last row to the next row of the line (y lines: may cross into the next y-block)
 		const int rn = min(r0 + M, n - 1);
 		const int step_last = (int)(DIR == 0 ? L.idx(rn, a, line_ok ? k : 0) : L.idx(a, rn, line_ok ? k : 0)) - off[M - 1];
-		unsigned rowmask = (line_ok && r0 < n) ? 0xffu : 0u;
-		// rows r0 - 1 and r0 + 8 of the line inside a slot (clamped into the line like the direct-load kernel)
+		unsigned rowmask = (line_ok && chunk_ok) ? 0xffu : 0u;
+		// rows r0 - 1 and r0 + 8 of the line inside a slot (clamped into the line like the direct-load kernel; at an open end
+		// of a half the value comes from `edge` instead)
 		const int e_lo = g > 0 ? (M - 1) * STR + e - GS : e;               // row r0 - 1 = last row of chunk g - 1
 		const int e_hi = g + 1 < GL ? e + GS : (M - 1) * STR + e;          // row r0 + 8 = first row of chunk g + 1
+		const bool edge_lo = open_lo && g == 0, edge_hi = open_hi && g == GL - 1;
 
 		cp_async_wait_all();
 		WAIT_SLOT(0); WAIT_SLOT(1); WAIT_SLOT(2); WAIT_SLOT(3); WAIT_SLOT(4);
@@ -316,8 +408,8 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 		unsigned rw0 = 0, rw1 = 0;
 #pragma unroll
 		for (int i = 0; i < 4; i++) {
-			rw0 |= (unsigned)roles[(min(r0, n - M) + i) * 8 + l] << (8 * i);
-			rw1 |= (unsigned)roles[(min(r0, n - M) + 4 + i) * 8 + l] << (8 * i);
+			rw0 |= (unsigned)roles[(min(g * M, nloc - M) + i) * NL + l] << (8 * i);
+			rw1 |= (unsigned)roles[(min(g * M, nloc - M) + 4 + i) * NL + l] << (8 * i);
 		}
 		if (!rowmask) { rw0 = 0; rw1 = 0; }
 #define ROLE(i) (((i) < 4 ? rw0 >> (8 * (i)) : rw1 >> (8 * ((i) - 4))) & 0xffu)
@@ -345,36 +437,7 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 				dp[1][i] = SLOTP(3)[i * STR + e];
 				dp[2][i] = SLOTP(4)[i * STR + e];
 			}
-			const FT Tlo = SLOTP(1)[e_lo], Thi = SLOTP(1)[e_hi];
-#ifdef CMC_TMA_DEBUG
-			// debug build: what the copies delivered against plain global loads of the same cells
-			if (rowmask) {
-				int bad = 0, badslot = -1, badrow = -1;
-#pragma unroll
-				for (int i = 0; i < M; i++) {
-					if (V[i] != A.temp[DIR][off[i]]) { bad++; badslot = 0; badrow = r0 + i; }
-					if (Tl[i] != A.temp[3][off[i]]) { bad++; badslot = 1; badrow = r0 + i; }
-					if (dp[0][i] != A.cur[0][off[i]]) { bad++; badslot = 2; badrow = r0 + i; }
-					if (dp[1][i] != A.cur[1][off[i]]) { bad++; badslot = 3; badrow = r0 + i; }
-					if (dp[2][i] != A.cur[2][off[i]]) { bad++; badslot = 4; badrow = r0 + i; }
-				}
-				if (bad) {
-					const int old = atomicAdd(A.tile_counter + 1, bad);
-					// look again a little later: has the data arrived meanwhile?
-					const long long t0 = clock64();
-					while (clock64() - t0 < 20000) { }
-					int still = 0;
-#pragma unroll
-					for (int i = 0; i < M; i++) {
-						const FT *sq = badslot == 0 ? SLOTP(0) : badslot == 1 ? SLOTP(1) : badslot == 2 ? SLOTP(2) : badslot == 3 ? SLOTP(3) : SLOTP(4);
-						const FT *gq = badslot == 0 ? A.temp[DIR] : badslot == 1 ? A.temp[3] : A.cur[badslot - 2];
-						if (sq[i * STR + e] != gq[off[i]]) still++;
-					}
-					if (old == 0) printf("[tma debug] tile %d (a %d k0 %d) thread %d (g %d l %d): %d mismatches, last in slot %d row %d; %d still differ 20k cycles later; ph %x\n",
-					                     tile, a, k0, t, g, l, bad, badslot, badrow, still, ph);
-				}
-			}
-#endif
+			const FT Tlo = edge_lo ? edge[3 * NL + l] : SLOTP(1)[e_lo], Thi = edge_hi ? edge[3 * NL + l] : SLOTP(1)[e_hi];
 			slot_reads_done();
 			__syncthreads();        // every thread has its inputs in registers: slots 1-4 are free (slot 0 stays)
 			if (t == 0) {
@@ -421,14 +484,15 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 				}
 			}
 		}
-		// head of the NEXT chunk of the line (thread t + 8): lanes 0-23 by shuffle, lanes 24-31 from the next warp's
-		// lanes 0-7 through headx
+		// head of the NEXT chunk of the line (thread t + NL): the lower lanes by shuffle, the last NL lanes of a warp from the
+		// next warp's first NL lanes through headx
 #define NEXT_HEAD(dst, val, slot_)                                                     \
 		do {                                                                           \
-			const FT sh__ = __shfl_down_sync(0xffffffffu, (val), 8);                   \
-			(dst) = lane < 24 ? sh__ : (warp + 1 < NW ? headx[(slot_) * (NW * 8) + (warp + 1) * 8 + (lane - 24)] : FT(0)); \
+			const FT sh__ = __shfl_down_sync(0xffffffffu, (val), NL);                  \
+			(dst) = lane < 32 - NL ? sh__ : (warp + 1 < NW ? headx[(slot_) * (NW * NL) + (warp + 1) * NL + (lane - (32 - NL))] : FT(0)); \
 		} while (0)
 		FT E[3];
+		FT xl[3] = {FT(0), FT(0), FT(0)}, xr[3] = {FT(0), FT(0), FT(0)}, Es = FT(0);      // CL 2: the other half's adjacent row, this separator's spike
 		{
 			// coupling of the first interior row to the two separators: x_0 = y0 - v0*E(g-1) - w0*E(g)
 			FT y0[3] = {dp[0][M - 2], dp[1][M - 2], dp[2][M - 2]}, v0 = lp[M - 2], w0 = cp[M - 2];
@@ -437,10 +501,10 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 				y0[0] = dp[0][i] - cp[i] * y0[0]; y0[1] = dp[1][i] - cp[i] * y0[1]; y0[2] = dp[2][i] - cp[i] * y0[2];
 				v0 = lp[i] - cp[i] * v0; w0 = -cp[i] * w0;
 			}
-			if (lane < 8) {
-				headx[0 * (NW * 8) + warp * 8 + lane] = y0[0]; headx[1 * (NW * 8) + warp * 8 + lane] = y0[1];
-				headx[2 * (NW * 8) + warp * 8 + lane] = y0[2]; headx[3 * (NW * 8) + warp * 8 + lane] = v0;
-				headx[4 * (NW * 8) + warp * 8 + lane] = w0;
+			if (lane < NL) {
+				headx[0 * (NW * NL) + warp * NL + lane] = y0[0]; headx[1 * (NW * NL) + warp * NL + lane] = y0[1];
+				headx[2 * (NW * NL) + warp * NL + lane] = y0[2]; headx[3 * (NW * NL) + warp * NL + lane] = v0;
+				headx[4 * (NW * NL) + warp * NL + lane] = w0;
 			}
 			__syncthreads();
 			FT ny0, ny1, ny2, nv, nw;
@@ -451,15 +515,63 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 			Rd[0] = (dp[0][M - 1] - a7 * dp[0][M - 2] - c7 * ny0) * rr;
 			Rd[1] = (dp[1][M - 1] - a7 * dp[1][M - 2] - c7 * ny1) * rr;
 			Rd[2] = (dp[2][M - 1] - a7 * dp[2][M - 2] - c7 * ny2) * rr;
-			reduced_solve<FT, 3, GP, GS, NL>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, E);    // every row's solution -> sol[]
+			if (CL == 2) {
+				// open-ended half: E = Y - S * x_other, S = one more right-hand side: the left spike of chunk 0 (upper half,
+				// x_other = last row of the lower half) or the last separator's coupling c7 (lower half, x_other = first row
+				// of the upper half).  Same algebra as the slab-coupled x-sweep (kernels_fast.cu MODE 1).
+				FT Re[4] = {Rd[0], Rd[1], Rd[2], FT(0)}, Xe[4];
+				FT Ra = -a7 * lp[M - 2] * rr;
+				if (open_lo && g == 0) { Re[3] = Ra; Ra = FT(0); }
+				if (open_hi && g == GL - 1) Re[3] = c7 * rr;         // (the chunk after it is an identity chunk or absent: nv == nw == 0)
+				reduced_solve<FT, 4, GP, GS, NL>(sys, sol, g, e, Ra, -c7 * nw * rr, Re, Xe);
+				// interface coefficients of this half: lower: last row x = c[q] - s * x_first(upper); upper: first row
+				// x = c[q] - s * x_last(lower)
+				if ((open_hi && g == GL - 1) || (open_lo && g == 0)) {
+					FT cq[3], sp;
+					if (open_hi) { cq[0] = Xe[0]; cq[1] = Xe[1]; cq[2] = Xe[2]; sp = Xe[3]; }
+					else { cq[0] = y0[0] - w0 * Xe[0]; cq[1] = y0[1] - w0 * Xe[1]; cq[2] = y0[2] - w0 * Xe[2]; sp = v0 - w0 * Xe[3]; }
+					const unsigned pa = peer_smem(xin, crank ^ 1u);
+#pragma unroll
+					for (int q = 0; q < 3; q++) { xown[q * NL + l] = cq[q]; st_cluster(pa + (unsigned)((q * NL + l) * sizeof(FT)), cq[q]); }
+					xown[3 * NL + l] = sp; st_cluster(pa + (unsigned)((3 * NL + l) * sizeof(FT)), sp);
+					mbar_arrive_peer(peer_smem(xbar + 0, crank ^ 1u));
+				}
+				if (t == 0 && crank == 0) {          // the next tile's index travels with the exchange
+					st_cluster(peer_smem(next_box, 1u), fetched);
+					mbar_arrive_peer(peer_smem(xbar + 0, 1u));
+				}
+				__syncthreads();                     // xown is written
+				WAIT_XCHG(0);                        // xin is written (and, upper half, next_box)
+				if (crank == 1 && t == 0) fetched = *next_box;
+				{
+					// x_last(lower) = (cl - sl * cu) / (1 - sl * su),  x_first(upper) = cu - su * x_last(lower)
+					const FT *lo_ = open_hi ? xown : xin, *up_ = open_hi ? xin : xown;
+					const FT sl = lo_[3 * NL + l], su = up_[3 * NL + l];
+					const FT den = rcp<FT>(FT(1) - sl * su);
+#pragma unroll
+					for (int q = 0; q < 3; q++) {
+						const FT xlast = (lo_[q * NL + l] - sl * up_[q * NL + l]) * den;
+						const FT xfirst = up_[q * NL + l] - su * xlast;
+						if (open_hi) xr[q] = xfirst; else xl[q] = xlast;
+					}
+				}
+				Es = Xe[3];
+#pragma unroll
+				for (int q = 0; q < 3; q++) E[q] = Xe[q] - Es * (open_hi ? xr[q] : xl[q]);
+			} else
+				reduced_solve<FT, 3, GP, GS, NL>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, E);    // every row's solution -> sol[]
 		}
 		// back substitution in place (dp[q] <- x: retires cp / lp), then store u, v, w and the relaxed linearisation layer
+		{
+			const FT Sl = (CL == 2 && g > 0) ? sol[3 * STR + e - GS] : FT(0);
 #pragma unroll
-		for (int q = 0; q < 3; q++) {
-			const FT El = g > 0 ? sol[q * STR + e - GS] : FT(0);
-			dp[q][M - 1] = E[q];
+			for (int q = 0; q < 3; q++) {
+				FT El = g > 0 ? sol[q * STR + e - GS] : FT(0);
+				if (CL == 2) El = g > 0 ? El - Sl * (open_hi ? xr[q] : xl[q]) : xl[q];      // chunk 0 of the upper half: row -1 is x_last(lower)
+				dp[q][M - 1] = E[q];
 #pragma unroll
-			for (int i = M - 2; i >= 0; i--) dp[q][i] = dp[q][i] - lp[i] * El - cp[i] * dp[q][i + 1];
+				for (int i = M - 2; i >= 0; i--) dp[q][i] = dp[q][i] - lp[i] * El - cp[i] * dp[q][i + 1];
+			}
 		}
 		WAIT_SLOT(1); WAIT_SLOT(2);
 #pragma unroll
@@ -490,9 +602,19 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 				// c1, c2: the two cross-line derivatives of temp[DIR]; c1 pairs with component QA, c2 with QB
 				constexpr int QA = DIR == 0 ? 1 : 0, QB = 2;
 				FT c1[M], c2[M];
+				WAIT_SLOT(3); WAIT_SLOT(4);
+#pragma unroll
+				for (int i = 0; i < M; i++) c1[i] = (SLOTP(4)[i * STR + e] - SLOTP(3)[i * STR + e]) * K.inv2h1;
+				slot_reads_done();
+				__syncthreads();        // the cross-line neighbours are consumed: slots 3 / 4 take cur.T and temp.T
+				if (t == 0) {
+					issue(3, &TM.cur[3], tile, 0, 0);
+					issue(4, &TM.temp[3], tile, 0, 0);       // last use of this tile's temp.T
+				}
 				{
 					// second cross direction (k +- 1): the neighbouring lines of the tile, the two edge lines from L2 / HBM
-					// (issuing those loads earlier costs more in spills than it hides in latency: measured)
+					// (issuing those loads earlier - in registers, or as cp.async into shared memory together with the
+					// descriptor bytes - costs more than it hides: measured, profiles/r02_variants.md)
 					FT p2[M], m2[M];
 					if (l == NL - 1) {
 #pragma unroll
@@ -511,9 +633,6 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 #pragma unroll
 					for (int i = 0; i < M; i++) c2[i] = (p2[i] - m2[i]) * K.inv2h2;
 				}
-				WAIT_SLOT(3); WAIT_SLOT(4);
-#pragma unroll
-				for (int i = 0; i < M; i++) c1[i] = (SLOTP(4)[i * STR + e] - SLOTP(3)[i * STR + e]) * K.inv2h1;
 #pragma unroll
 				for (int i = 0; i < M; i++) diss[i] = FT(0);
 #pragma unroll
@@ -522,7 +641,7 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 					FT f[M];
 #pragma unroll
 					for (int i = 0; i < M; i++) f[i] = sq[i * STR + e];
-					const FT lo = sq[e_lo], hi = sq[e_hi];
+					const FT lo = edge_lo ? edge[q * NL + l] : sq[e_lo], hi = edge_hi ? edge[q * NL + l] : sq[e_hi];
 #pragma unroll
 					for (int i = 0; i < M; i++) {
 						const FT d = cdiff<FT>(f, lo, hi, i, K.inv2h);
@@ -542,15 +661,14 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 				}
 			}
 			FT cT[M];
-			WAIT_SLOT(5);
+			WAIT_SLOT(3);
 #pragma unroll
-			for (int i = 0; i < M; i++) cT[i] = SLOTP(5)[i * STR + e];
+			for (int i = 0; i < M; i++) cT[i] = SLOTP(3)[i * STR + e];
 			slot_reads_done();
-			__syncthreads();        // every slot has been consumed
+			__syncthreads();        // slots 0 - 3 have been consumed (slot 4 keeps temp.T for the end of the tile)
 			if (t == 0) {
-				issue(5, &TM.temp[3], tile, 0, 0);       // last use of this tile's temp.T
 				if (fetched < ntiles) issue_A(fetched);
-				*next_box = fetched;                     // read by everybody after the next barrier
+				if (CL == 1 || crank == 0) *next_box = fetched;      // read by everybody after the next barrier (upper half: already there)
 			}
 #pragma unroll
 			for (int i = 0; i < M; i++) {
@@ -581,8 +699,8 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 			FT y0 = dT[M - 2], v0 = lp[M - 2], w0 = cp[M - 2];
 #pragma unroll
 			for (int i = M - 3; i >= 0; i--) { y0 = dT[i] - cp[i] * y0; v0 = lp[i] - cp[i] * v0; w0 = -cp[i] * w0; }
-			if (lane < 8) {
-				headx[0 * (NW * 8) + warp * 8 + lane] = y0; headx[3 * (NW * 8) + warp * 8 + lane] = v0; headx[4 * (NW * 8) + warp * 8 + lane] = w0;
+			if (lane < NL) {
+				headx[0 * (NW * NL) + warp * NL + lane] = y0; headx[3 * (NW * NL) + warp * NL + lane] = v0; headx[4 * (NW * NL) + warp * NL + lane] = w0;
 			}
 			__syncthreads();
 			next_tile = *next_box;
@@ -592,18 +710,42 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 			const FT a7 = lp[M - 1], c7 = cp[M - 1];
 			rr = rcp<FT>(b7 - a7 * cp[M - 2] - c7 * nv);
 			FT Rd[1] = {(dT[M - 1] - a7 * dT[M - 2] - c7 * ny0) * rr}, ET[1];
-			reduced_solve<FT, 1, GP, GS, NL>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, ET);
-			const FT El = g > 0 ? sol[e - GS] : FT(0);
+			FT El;
+			if (CL == 2) {
+				FT Re[2] = {Rd[0], FT(0)}, Xe[2];
+				FT Ra = -a7 * lp[M - 2] * rr;
+				if (open_lo && g == 0) { Re[1] = Ra; Ra = FT(0); }
+				if (open_hi && g == GL - 1) Re[1] = c7 * rr;
+				reduced_solve<FT, 2, GP, GS, NL>(sys, sol, g, e, Ra, -c7 * nw * rr, Re, Xe);
+				if ((open_hi && g == GL - 1) || (open_lo && g == 0)) {
+					const FT cq = open_hi ? Xe[0] : y0 - w0 * Xe[0], sp = open_hi ? Xe[1] : v0 - w0 * Xe[1];
+					const unsigned pa = peer_smem(xin, crank ^ 1u);
+					xown[4 * NL + l] = cq; st_cluster(pa + (unsigned)((4 * NL + l) * sizeof(FT)), cq);
+					xown[5 * NL + l] = sp; st_cluster(pa + (unsigned)((5 * NL + l) * sizeof(FT)), sp);
+					mbar_arrive_peer(peer_smem(xbar + 1, crank ^ 1u));
+				}
+				__syncthreads();
+				WAIT_XCHG(1);
+				const FT *lo_ = open_hi ? xown : xin, *up_ = open_hi ? xin : xown;
+				const FT sl = lo_[5 * NL + l], su = up_[5 * NL + l];
+				const FT xlast = (lo_[4 * NL + l] - sl * up_[4 * NL + l]) * rcp<FT>(FT(1) - sl * su);
+				const FT xo = open_hi ? up_[4 * NL + l] - su * xlast : xlast;          // the other half's adjacent row
+				ET[0] = Xe[0] - Xe[1] * xo;
+				El = g > 0 ? sol[e - GS] - sol[STR + e - GS] * xo : (open_lo ? xo : FT(0));
+			} else {
+				reduced_solve<FT, 1, GP, GS, NL>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, ET);
+				El = g > 0 ? sol[e - GS] : FT(0);
+			}
 			FT x[M], tq[M];
 			x[M - 1] = ET[0];
 #pragma unroll
 			for (int i = M - 2; i >= 0; i--) x[i] = dT[i] - lp[i] * El - cp[i] * x[i + 1];
-			WAIT_SLOT(5);
+			WAIT_SLOT(4);
 #pragma unroll
-			for (int i = 0; i < M; i++) tq[i] = SLOTP(5)[i * STR + e];
+			for (int i = 0; i < M; i++) tq[i] = SLOTP(4)[i * STR + e];
 			slot_reads_done();
-			__syncthreads();        // slot 5 consumed (and sol / headx are free for the next tile)
-			if (t == 0 && next_tile < ntiles) issue(5, &TM.cur[3], next_tile, 0, 0);
+			__syncthreads();        // slot 4 consumed (and sol / headx are free for the next tile)
+			if (t == 0 && next_tile < ntiles) issue(4, &TM.cur[2], next_tile, 0, 0);
 			if (holes) {
 #pragma unroll
 				for (int i = 0; i < M; i++)
@@ -617,17 +759,45 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 		tile = next_tile;
 	}
 	cp_async_wait_all();
+	if (CL == 2) cluster_sync_all();                // the peer may still be storing into this CTA's shared memory
 #undef ROLE
 #undef SLOTP
 #undef WAIT_SLOT
+#undef WAIT_XCHG
 #undef NEXT_HEAD
 }
 
-template <typename FT, int GP>
+template <typename FT, int GP, int NL, int CL>
 static size_t tma_smem_bytes()
 {
-	const size_t STR = (size_t)GP * 8;
-	return sizeof(FT) * (6 * STR * M + reduced_scratch_elems<3, GP, 8>() + 5 * (STR / 32) * 8) + 8 * STR + 6 * sizeof(unsigned long long) + 16;
+	const size_t STR = (size_t)GP * NL;
+	return sizeof(FT) * (5 * STR * M + reduced_scratch_elems<3 + (CL == 2 ? 1 : 0), GP, NL>() + 5 * (STR / 32) * NL + (CL == 2 ? 16 * NL : 0)) + (size_t)NL * GP * 8 +
+	       7 * sizeof(unsigned long long) + 16;
+}
+
+// shape of the tile a sweep uses: lines per tile, chunks per CTA, CTAs per tile (0 chunks: not supported).  Measured on B200
+// (profiles/r02_variants.md, fp64): 512-row lines - 8 lines x 1 CTA (512 threads) wins over the 16-line CTA pair although the
+// pair's copies run twice as fast: the tile time is set by the solve, not by the copy engine; 256-row lines - 16 lines x 1
+// CTA along x (0.51 against 0.66 ms at 256^3), 8 lines and two independent CTAs per SM along y (0.48 against 0.52 ms).
+struct TmaShape { int gp, nl, cl; };
+static TmaShape tma_shape(const Layout &L, int dir, int forced)
+{
+	TmaShape S = {0, 8, 1};
+	const int n = dir == 0 ? L.nx : L.ny;
+	if (n % M != 0 || n / M > 64 || n / M <= 16) return S;               // 136 .. 512 rows
+	int nl = (n / M <= 32 && dir == 0) ? 16 : 8, cl = 1;
+	static const char *env = getenv("CMC_TMA_SHAPE");                    // (experiments) "8x1" / "16x1" / "16x2": lines x CTAs per tile
+	if (env && !forced) {
+		int fnl = 0, fcl = 0;
+		if (sscanf(env, "%dx%d", &fnl, &fcl) == 2 && (fnl == 8 || fnl == 16) && (fcl == 1 || fcl == 2)) forced = fnl + 256 * fcl;
+	}
+	if (forced) { nl = forced & 255; cl = forced >> 8; }
+	// a CTA pair takes halves of whole chunks and, along y in blocked storage, of whole y-blocks
+	if (cl == 2 && (n % (2 * M) != 0 || (dir == 1 && L.nblk > 1 && (n / 2) % (1 << L.jbs) != 0))) cl = 1;
+	const int chunks = n / M / cl;
+	if (chunks > 32 && nl == 16) nl = 8;                                 // 1024 threads do not fit
+	S.gp = chunks > 32 ? 64 : 32; S.nl = nl; S.cl = cl;
+	return S;
 }
 
 bool tma_sweep_supported(const Layout &L, int dir)
@@ -640,48 +810,65 @@ bool tma_sweep_supported(const Layout &L, int dir)
 	return encode_fn() != nullptr;
 }
 
-template <typename FT, int DIR, int GP>
+template <typename FT, int DIR, int GP, int NL, int CL>
 static bool launch_tma_one(const SweepArgs<FT> &A, cudaStream_t s)
 {
 	const Layout &L = A.L;
 	if (DIR == 1 && L.nblk > 1 && (GP % ((1 << L.jbs) / M) != 0)) return false;
 	TmaMaps TM;
 	for (int q = 0; q < 4; q++) {
-		if (!tensor_map_for<FT>(A.temp[q], L, DIR, GP, &TM.temp[q])) return false;
-		if (!tensor_map_for<FT>(A.cur[q], L, DIR, GP, &TM.cur[q])) return false;
+		if (!tensor_map_for<FT>(A.temp[q], L, DIR, GP, NL, &TM.temp[q])) return false;
+		if (!tensor_map_for<FT>(A.cur[q], L, DIR, GP, NL, &TM.cur[q])) return false;
 	}
-	const int ntiles = (DIR == 0 ? L.ny : L.nx) * ((L.nz + 7) / 8);
-	const size_t smem = tma_smem_bytes<FT, GP>();
+	const int ntiles = (DIR == 0 ? L.ny : L.nx) * ((L.nz + NL - 1) / NL);
+	const size_t smem = tma_smem_bytes<FT, GP, NL, CL>();
 	static int ctas_of[64] = {};
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (dev < 0 || dev >= 64) return false;
+	auto kern = k_tma_sweep<FT, DIR, GP, NL, CL>;
 	if (!ctas_of[dev]) {
-		if (cudaFuncSetAttribute((const void *)k_tma_sweep<FT, DIR, GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
+		if (cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
 		int per_sm = 0, sms = 0;
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tma_sweep<FT, DIR, GP>, GP * 8, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return false; }
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GP * NL, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return false; }
 		if (getenv("CMC_TMA_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("CMC_TMA_CTAS"))));    // (experiments)
-		ctas_of[dev] = per_sm * sms;
+		ctas_of[dev] = (per_sm * sms) / CL * CL;
 	}
 	FastConst<FT> K; K.init(A, DIR);
 	// CMC_TMA_HINTS: bit 0 = L2 eviction hints on the bulk copies, bit 1 = streaming result stores (measured: neither helps)
 	static const int hints = getenv("CMC_TMA_HINTS") ? atoi(getenv("CMC_TMA_HINTS")) : 0;
 	if (!A.tile_counter || cudaMemsetAsync(A.tile_counter, 0, sizeof(int), s) != cudaSuccess) return false;
-	k_tma_sweep<FT, DIR, GP><<<std::min(ctas_of[dev], ntiles), GP * 8, smem, s>>>(A, K, TM, ntiles, hints);
+	const int grid = std::min(ctas_of[dev], ntiles * CL);
+	if (CL == 1) {
+		kern<<<grid, GP * NL, smem, s>>>(A, K, TM, ntiles, hints);
+		return true;
+	}
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(GP * NL); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	if (cudaLaunchKernelEx(&cfg, kern, A, K, TM, ntiles, hints) != cudaSuccess) { cudaGetLastError(); return false; }
 	return true;
+}
+
+template <typename FT, int DIR>
+static bool launch_tma_dir(const SweepArgs<FT> &A, cudaStream_t s)
+{
+	const TmaShape S = tma_shape(A.L, DIR, A.tma_shape);
+	if (S.gp == 64) return launch_tma_one<FT, DIR, 64, 8, 1>(A, s);
+	if (S.gp != 32) return false;
+	if (S.nl == 16) return S.cl == 2 ? launch_tma_one<FT, DIR, 32, 16, 2>(A, s) : launch_tma_one<FT, DIR, 32, 16, 1>(A, s);
+	return S.cl == 2 ? launch_tma_one<FT, DIR, 32, 8, 2>(A, s) : launch_tma_one<FT, DIR, 32, 8, 1>(A, s);
 }
 
 template <typename FT>
 bool launch_tma_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches)
 {
-	const Layout &L = A.L;
-	if (!tma_sweep_supported(L, dir)) return false;
-	const int n = dir == 0 ? L.nx : L.ny;
-	const int GP = n / M > 32 ? 64 : 32;
-	bool ok;
-	if (dir == 0) ok = GP == 64 ? launch_tma_one<FT, 0, 64>(A, s) : launch_tma_one<FT, 0, 32>(A, s);
-	else ok = GP == 64 ? launch_tma_one<FT, 1, 64>(A, s) : launch_tma_one<FT, 1, 32>(A, s);
+	if (!tma_sweep_supported(A.L, dir)) return false;
+	const bool ok = dir == 0 ? launch_tma_dir<FT, 0>(A, s) : launch_tma_dir<FT, 1>(A, s);
 	if (ok && launches) (*launches)++;
 	return ok;
 }

@@ -9,7 +9,7 @@
 
 namespace FluidSolver2D
 {
-	B200AdiSolver2D::B200AdiSolver2D(int _device) : h(NULL), device(_device), iters(0), err(0.0), type(NULL), bc(NULL), gvx(NULL), gvy(NULL), gT(NULL), buf(NULL)
+	B200AdiSolver2D::B200AdiSolver2D(int _device) : h(NULL), device(_device), iters(0), err(0.0), type(NULL), bc(NULL), gvx(NULL), gvy(NULL), gT(NULL)
 	{
 		grid = NULL;
 		cur = NULL;
@@ -20,7 +20,7 @@ namespace FluidSolver2D
 	{
 		if (h) cmc_adi2d_destroy(h);
 		delete cur; delete next;
-		delete [] type; delete [] bc; delete [] gvx; delete [] gvy; delete [] gT; delete [] buf;
+		delete [] type; delete [] bc; delete [] gvx; delete [] gvy; delete [] gT;
 	}
 
 	void B200AdiSolver2D::check(int rc, const char *what)
@@ -40,7 +40,7 @@ namespace FluidSolver2D
 		params = _params;
 		const int N = dimx * dimy;
 		type = new int[N]; bc = new int[N];
-		gvx = new FTYPE[N]; gvy = new FTYPE[N]; gT = new FTYPE[N]; buf = new FTYPE[N];
+		gvx = new FTYPE[N]; gvy = new FTYPE[N]; gT = new FTYPE[N];
 		// host mirrors of the two layers the non-virtual Solver2D members work on (AdiSolver2D.cpp:30-50)
 		cur = new TimeLayer2D(dimx, dimy, (FTYPE)grid->dx, (FTYPE)grid->dy);
 		next = new TimeLayer2D(dimx, dimy, (FTYPE)grid->dx, (FTYPE)grid->dy);
@@ -53,21 +53,6 @@ namespace FluidSolver2D
 		check(cmc_adi2d_create(dimx, dimy, grid->dx, grid->dy, &p, grid->startT, (int)sizeof(FTYPE), device, &h), "cmc_adi2d_create");
 	}
 
-	void B200AdiSolver2D::transfer(TimeLayer2D *layer, int which, bool upload)
-	{
-		for (int q = 0; q < 3; q++) {
-			if (upload) {
-				for (int i = 0; i < dimx; i++)
-					for (int j = 0; j < dimy; j++) buf[i * dimy + j] = q == 0 ? layer->U(i, j) : q == 1 ? layer->V(i, j) : layer->T(i, j);
-				check(cmc_adi2d_write_field(h, which, q, buf), "cmc_adi2d_write_field");
-			} else {
-				check(cmc_adi2d_read_field(h, which, q, buf), "cmc_adi2d_read_field");
-				for (int i = 0; i < dimx; i++)
-					for (int j = 0; j < dimy; j++) (q == 0 ? layer->U(i, j) : q == 1 ? layer->V(i, j) : layer->T(i, j)) = buf[i * dimy + j];
-			}
-		}
-	}
-
 	void B200AdiSolver2D::TimeStep(FTYPE dt, int num_global, int num_local)
 	{
 		// what the solver may read of the grid (the driver refreshed it: grid.Prepare(t), FluidSolver2D.cpp:129)
@@ -78,12 +63,10 @@ namespace FluidSolver2D
 				type[id] = (int)grid->GetType(i, j); bc[id] = (int)d.type;
 				gvx[id] = d.vel.x; gvy[id] = d.vel.y; gT[id] = d.T;
 			}
-		check(cmc_adi2d_set_grid(h, type, bc, gvx, gvy, gT), "cmc_adi2d_set_grid");
-		transfer(cur, CMC_LAYER_CUR, true);        // Solver2D::UpdateBoundaries has just edited both on the host
-		transfer(next, CMC_LAYER_NEXT, true);
-		check(cmc_adi2d_time_step(h, (double)dt, num_global, num_local, &err, &iters), "cmc_adi2d_time_step");
-		transfer(cur, CMC_LAYER_CUR, false);
-		transfer(next, CMC_LAYER_NEXT, false);
+		// one round trip: grid arrays + both host layers up (Solver2D::UpdateBoundaries has just edited them on the host), the
+		// step on the device (half / temp / next_local stay resident), both layers down
+		void *c[3] = { &cur->U(0, 0), &cur->V(0, 0), &cur->T(0, 0) }, *n[3] = { &next->U(0, 0), &next->V(0, 0), &next->T(0, 0) };
+		check(cmc_adi2d_step_host(h, type, bc, gvx, gvy, gT, c, n, (double)dt, num_global, num_local, &err, &iters), "cmc_adi2d_step_host");
 		printf("\rerr = %.4f,", err);              // AdiSolver2D.cpp:318
 	}
 }

@@ -34,8 +34,7 @@ namespace FluidSolver2D
 		int device, iters;
 		double err;
 		int *type, *bc;
-		FTYPE *gvx, *gvy, *gT, *buf;
+		FTYPE *gvx, *gvy, *gT;
 		void check(int rc, const char *what);
-		void transfer(TimeLayer2D *layer, int which, bool upload);
 	};
 }

@@ -356,6 +356,21 @@ class AdiSolver2D:
         _check(rc)
         return self.err
 
+    def StepHost(self, type_, bc, vx, vy, T, cur, nxt, dt, num_global, num_local):
+        """cmc_adi2d_step_host: grid arrays + the host's cur / next layers (3 arrays each, updated in place) up in one copy, one
+        TimeStep, both layers down in one copy - what the Solver2D adapter does every step."""
+        ai = [np.ascontiguousarray(a, dtype=np.int32) for a in (type_, bc)]
+        af = [np.ascontiguousarray(a, dtype=self.ft) for a in (vx, vy, T)]
+        for a in list(cur) + list(nxt):
+            assert a.dtype == self.ft and a.flags.c_contiguous and a.size == self.dimx * self.dimy
+        pc = (C.c_void_p * 3)(*[a.ctypes.data for a in cur]); pn = (C.c_void_p * 3)(*[a.ctypes.data for a in nxt])
+        e, it = C.c_double(0.0), C.c_int(0)
+        rc = load_library().cmc_adi2d_step_host(self._h, *[_ptr(a) for a in ai], *[_ptr(a) for a in af], pc, pn, float(dt), int(num_global),
+                                                int(num_local), C.byref(e), C.byref(it))
+        self.err, self.iters = e.value, it.value
+        _check(rc)
+        return self.err
+
     def GetLayer(self, outdimx=0, outdimy=0):
         ox, oy = outdimx or self.dimx, outdimy or self.dimy
         vel = np.empty((ox * oy, 2), dtype=self.ft)

@@ -266,6 +266,14 @@ int cmc_adi2d_update_boundaries(cmc_adi2d *h);
  * residual the reference prints, *iters_out = outer iterations done.  CMC_ERR_DIVERGED where the reference exits
  * ("Exceeded max number of iterations", "Error is too big!"). */
 int cmc_adi2d_time_step(cmc_adi2d *h, double dt, int num_global, int num_local, double *err_out, int *iters_out);
+/* One TimeStep of a host-driven loop in one round trip - what B200AdiSolver2D::TimeStep needs, because Solver2D's non-virtual
+ * UpdateBoundaries / SetGridBoundaries edit the layers on the host between steps (Solver2D.cpp:48-71): the grid arrays (as in
+ * cmc_adi2d_set_grid) and the host's cur / next layers (3 dense arrays each: u, v, T) go up in ONE copy from a pinned staging
+ * block, the step runs, both layers come back in ONE copy and are updated in place.  Same result as cmc_adi2d_set_grid +
+ * 6 x write_field + cmc_adi2d_time_step + 6 x read_field (17 synchronised copies). */
+int cmc_adi2d_step_host(cmc_adi2d *h, const int32_t *type, const int32_t *bc_type, const void *vx, const void *vy, const void *T,
+                        void *const cur_uvT[3], void *const next_uvT[3], double dt, int num_global, int num_local,
+                        double *err_out, int *iters_out);
 /* many independent 2D cases in ONE launch, one thread block (one SM) per case - the throughput form of the 2D solver
  * (a single ~16 k-cell case cannot fill a GPU).  All handles: same precision, grid dimensions and
  * device.  update_boundaries != 0 runs Solver2D::UpdateBoundaries of every case first.  Per case: residual, outer

@@ -188,3 +188,33 @@ def test_batched_2d_cases_equal_single_steps(oracle_mod, fp):
         s.close()
     for o in oracles:
         o.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fp", [4, 8])
+def test_step_host_round_trip_equals_separate_calls(fp):
+    """cmc_adi2d_step_host (what the Solver2D adapter calls every step): grid + both host layers up in one copy, TimeStep, both
+    layers down in one copy - bit-identical with set_grid + write_field x6 + TimeStep + read_field x6."""
+    from cmc_fluid_solver_b200 import AdiSolver2D
+    dimx, dimy, h = 61, 47, 0.02
+    par = (1.0, 0.05, 0.07, 0.002)
+    ft = np.float32 if fp == 4 else np.float64
+    g = synthetic_2d(dimx, dimy)
+    a = AdiSolver2D().Init(dimx, dimy, h, h, *par, 1.0, fp)
+    b = AdiSolver2D().Init(dimx, dimy, h, h, *par, 1.0, fp)
+    a.set_grid(*g); a.init_layer()
+    cur = [np.ascontiguousarray(np.asarray(g[2 + q], dtype=ft).reshape(-1)) for q in range(3)]
+    nxt = [np.zeros(dimx * dimy, dtype=ft) for _ in range(3)]
+    for step in range(4):
+        vx = np.asarray(g[2], dtype=ft) * (1.0 + 0.1 * step)          # the driver changes the grid between steps
+        a.set_grid(g[0], g[1], vx, g[3], g[4])
+        for q in range(3):                                            # a host-side edit of both layers, as Solver2D::UpdateBoundaries does
+            cur[q][7 * dimy + 5] += ft(0.01); nxt[q][9 * dimy + 3] -= ft(0.02)
+            a.write_field(0, q, cur[q]); a.write_field(2, q, nxt[q])
+        e_a = a.TimeStep(0.05, 3, 2)
+        e_b = b.StepHost(g[0], g[1], vx, g[3], g[4], cur, nxt, 0.05, 3, 2)
+        assert e_a == e_b and a.iters == b.iters
+        for q in range(3):
+            assert np.array_equal(a.read_field(0, q).reshape(-1), cur[q]), (step, q)
+            assert np.array_equal(a.read_field(2, q).reshape(-1), nxt[q]), (step, q)
+    a.close(); b.close()

@@ -12,9 +12,11 @@ from cmc_fluid_solver_b200.solver import DIR_X, DIR_Y, LAYER_CUR, LAYER_HALF, LA
 pytestmark = pytest.mark.gpu
 
 
-def _tma(case, mask=3):
+def _tma(case, mask=3, shape=0):
     s = AdiSolver3D().Init(case, mode="fast")
     s.set_option("tma", mask)
+    if shape:
+        s.set_option("tma_shape", shape)
     s.CreateSegments()
     return s
 
@@ -78,3 +80,27 @@ def test_tma_against_direct_kernel_256(fp):
             s.UpdateBoundaries(); s.TimeStep(case.dt, case.num_global, case.num_local, True)
     assert_fields_close([a.read_field(LAYER_CUR, q) for q in range(4)], [b.read_field(LAYER_CUR, q) for q in range(4)], fp, "256^3 TMA vs direct")
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("fp", [8, 4])
+@pytest.mark.parametrize("shape", ["8x1", "16x1", "8x2", "16x2"])
+@pytest.mark.parametrize("dims", [(512, 40, 44), (40, 512, 60), (256, 48, 20), (48, 256, 37), (400, 144, 24)])
+def test_tma_tile_shapes_against_oracle(oracle_mod, dims, shape, fp):
+    """Every tile shape of the kernel (option "tma_shape" = lines per tile + 256 * CTAs per tile): 8 or 16 lines, whole lines
+    in one CTA or a cluster of two CTAs that split every line in halves and couple them through distributed shared memory
+    (spike column + 2x2 interface per line) - all against the oracle, ragged k-tiles included."""
+    O = oracle_mod
+    nl, cl = (int(v) for v in shape.split("x"))
+    if max(dims[0], dims[1]) // 8 // cl > 32 and nl == 16:
+        pytest.skip("16 lines x 64 chunks would need 1024 threads")
+    case = channel_case(*dims, fp_bytes=fp, depth_var=0.25)
+    ora = O.Oracle3D(case); ora.create_segments()
+    s = _tma(case, shape=nl + 256 * cl)
+    assert 3 in [s.get_option("kernel_x"), s.get_option("kernel_y")]
+    for i in range(2):
+        ora.update_boundaries(); s.UpdateBoundaries()
+        e_ref = ora.time_step(case.dt, case.num_global, case.num_local, True)
+        e = s.TimeStep(case.dt, case.num_global, case.num_local, True)
+        assert abs(e - e_ref) <= (1e-5 if fp == 4 else 1e-9) * abs(e_ref)
+        assert_fields_close([ora.field(O.LAYER_CUR, q) for q in range(4)], [s.read_field(LAYER_CUR, q) for q in range(4)], fp, f"{dims} {shape} step {i}")
+    s.close()

@@ -142,6 +142,71 @@ __global__ void __launch_bounds__(128, 1) k_probe_bulk(const double *const *fiel
 	}
 }
 
+// Copy-through probe: the sweep's memory traffic without its arithmetic.  Per tile 11 box loads (8 distinct fields + 3
+// repeats, like the sweep kernel) and 8 box stores (cp.async.bulk.tensor shared -> global) into 8 other fields, tiles
+// handed out by the same atomic counter.  What the memory system delivers for THIS access pattern (64- or 128-byte row
+// segments a plane apart, reads and writes mixed) is the practical ceiling of the x / y sweep kernels.
+struct Maps16 { CUtensorMap in[8], out[8]; };
+template <int NSLOT>
+__global__ void __launch_bounds__(128, 1) k_probe_copy(const __grid_constant__ Maps16 TM, int ntiles, int ktiles, int dir, int kw, int *counter, int slot_bytes,
+                                                      int jbm, int jbs)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	unsigned long long *full = reinterpret_cast<unsigned long long *>(smem + (size_t)NSLOT * slot_bytes);
+	const int t = threadIdx.x;
+	if (t == 0) {
+		for (int s = 0; s < NSLOT; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(full + s)));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	__syncthreads();
+	if (t != 0) return;
+	unsigned ph = 0;
+	int tile = blockIdx.x;
+	// software pipeline over (tile, field): loads run NSLOT - 1 ahead of the stores
+	struct Item { int c0, c3, c4, f; };
+	Item ring[NSLOT];
+	int head = 0, count = 0;     // items in flight (loaded, not yet stored)
+	auto drain_one = [&]() {
+		const int s = head % NSLOT;
+		const unsigned par = (ph >> s) & 1u;
+		unsigned ok = 0;
+		while (!ok)
+			asm volatile("{ .reg .pred P1; mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x100000; selp.u32 %0, 1, 0, P1; }"
+			             : "=r"(ok) : "r"(smem_u32(full + s)), "r"(par) : "memory");
+		ph ^= 1u << s;
+		const Item it = ring[s];
+		if (it.f < 8) {           // the 3 repeats are read-only
+			asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+			             ::"l"(reinterpret_cast<unsigned long long>(&TM.out[it.f])), "r"(smem_u32(smem + (size_t)s * slot_bytes)),
+			             "r"(it.c0), "r"(0), "r"(0), "r"(it.c3), "r"(it.c4) : "memory");
+			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+		}
+		head++; count--;
+	};
+	int issued = 0;
+	while (tile < ntiles) {
+		const int a = tile / ktiles, k0 = (tile - a * ktiles) * kw;
+		int c3, c4;
+		if (dir == 0) { c3 = a & jbm; c4 = a >> jbs; } else { c3 = 0; c4 = a + 1; }
+		for (int f = 0; f < 11; f++) {
+			if (count == NSLOT - 1) drain_one();
+			const int s = issued % NSLOT;
+			// the slot's previous store must have finished reading shared memory
+			asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NSLOT - 2) : "memory");
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(full + s)), "r"(slot_bytes) : "memory");
+			asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+			             ::"r"(smem_u32(smem + (size_t)s * slot_bytes)), "l"(reinterpret_cast<unsigned long long>(&TM.in[f % 8])), "r"(smem_u32(full + s)),
+			             "r"(k0), "r"(0), "r"(0), "r"(c3), "r"(c4) : "memory");
+			ring[s] = Item{k0, c3, c4, f};
+			issued++; count++;
+		}
+		tile = (int)gridDim.x + atomicAdd(counter, 1);
+	}
+	while (count > 0) drain_one();
+	asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 int main()
 {
 	const int nx = 512, ny = 512, nz = 512, nzp = 512, jb = 64, jbs = 6, jbm = 63;
@@ -227,6 +292,52 @@ int main()
 			};
 			run(k_probe_bulk<4>, 4); run(k_probe_bulk<6>, 6);
 		}
+	}
+	// copy-through: loads + stores
+	{
+		double *outs[8];
+		for (int f = 0; f < 8; f++) { CK(cudaMalloc(&outs[f], sizeof(double) * total)); CK(cudaMemset(outs[f], 0, sizeof(double) * total)); }
+		for (int dir = 0; dir < 2; dir++)
+			for (int kw = 8; kw <= 16; kw *= 2) {
+				const int GP = 64 * 8 / kw;
+				Maps16 TM;
+				for (int f = 0; f < 16; f++) {
+					double *fld = f < 8 ? fields[f] : outs[f - 8];
+					cuuint64_t dims[5], strides[4]; cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+					void *base;
+					if (dir == 0) {
+						dims[0] = nzp; dims[1] = nx / 8; dims[2] = 8; dims[3] = jb; dims[4] = ny / jb;
+						strides[0] = 8 * plane * 8; strides[1] = plane * 8; strides[2] = nzp * 8; strides[3] = bstride * 8;
+						box[0] = kw; box[1] = GP; box[2] = 8; box[3] = 1; box[4] = 1;
+						base = fld + plane;
+					} else {
+						dims[0] = nzp; dims[1] = jb / 8; dims[2] = ny / jb; dims[3] = 8; dims[4] = nx + 2;
+						strides[0] = 8 * nzp * 8; strides[1] = bstride * 8; strides[2] = nzp * 8; strides[3] = plane * 8;
+						box[0] = kw; box[1] = jb / 8; box[2] = GP / (jb / 8); box[3] = 8; box[4] = 1;
+						base = fld;
+					}
+					CUresult r = enc(f < 8 ? &TM.in[f] : &TM.out[f - 8], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+					                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+					if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 1; }
+				}
+				const int ktiles = nz / kw, ntiles = (dir == 0 ? ny : nx) * ktiles, slot_bytes = kw * GP * 8 * 8;
+				const size_t smem = (size_t)6 * slot_bytes + 64;
+				CK(cudaFuncSetAttribute(k_probe_copy<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				float best = 1e9f;
+				for (int rep = 0; rep < 3; rep++) {
+					CK(cudaMemset(counter, 0, 4));
+					cudaEventRecord(e0);
+					k_probe_copy<6><<<148, 128, smem>>>(TM, ntiles, ktiles, dir, kw, counter, slot_bytes, jbm, jbs);
+					cudaEventRecord(e1);
+					CK(cudaDeviceSynchronize());
+					float ms; cudaEventElapsedTime(&ms, e0, e1);
+					if (ms < best) best = ms;
+				}
+				// algorithmic bytes of a sweep: 8 fields read once + 8 fields written (here every cell, the sweep skips masked ones)
+				const double alg = 16.0 * nx * ny * nz * 8;
+				printf("copy-through dir %c  row %3d B: %.3f ms per sweep-equivalent  %.0f GB/s algorithmic (8 fields in, 8 out; 11 loads + 8 stores per tile)\n",
+				       "xy"[dir], kw * 8, best, alg / best / 1e6);
+			}
 	}
 	return 0;
 }
