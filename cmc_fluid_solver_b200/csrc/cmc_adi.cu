@@ -826,7 +826,13 @@ struct Engine : cmc_adi3d {
 		return A;
 	}
 
-	bool fast_ok(int dir) const { return mode == CMC_MODE_FAST && fast_sweep_supported(slabs[0]->L, dir); }
+	// fast mode covers lines of up to 512 rows in every kernel, and x / y lines of up to 1024 rows on one slab through the
+	// CTA-pair form of the TMA kernel; longer lines run the exact kernels + a separate merge
+	bool fast_ok(int dir) const
+	{
+		if (mode != CMC_MODE_FAST) return false;
+		return fast_sweep_supported(slabs[0]->L, dir) || (!multi() && want_tma(dir) && tma_sweep_supported(slabs[0]->L, dir));
+	}
 
 	// which kernel a sweep along `dir` runs (get_option "kernel_x|y|z"): 0 exact Thomas kernels + merge, 1 direct-load
 	// partition kernel (kernels_fast.cu), 2 cp.async ring kernel (kernels_ring.cu), 4 slab-coupled x-sweep (spike pass +
@@ -916,6 +922,7 @@ struct Engine : cmc_adi3d {
 					if (want_tma(dir)) done = launch_tma_sweep<FT>(dir, A, stream, &launches);
 					if (!done && want_ring(dir)) done = launch_ring_sweep<FT>(dir, A, stream, &launches);
 					if (!done) done = launch_fast_sweep<FT>(dir, A, stream, &launches);
+					if (!done) return fail(CMC_ERR_UNSUPPORTED, "fast sweep: no kernel for this line length (lines above 512 rows need the TMA kernel)");
 				}
 				if (done) swapped[si] = 1;                               // merged temp went to the other buffer
 				else {

@@ -22,7 +22,8 @@
 //     the result stores;
 //   * no global load in the common path except the k +- 1 neighbours of the two edge lines of a tile.
 // Requirements (launch_tma_sweep returns false otherwise and the caller uses k_fast_sweep): x or y sweep of a slab whose
-// lines stay inside the slab (MODE 0), line length a multiple of 8 and at most 512.
+// lines stay inside the slab (MODE 0), line length a multiple of 8 and at most 512 - or a multiple of 16 and at most 1024,
+// which a pair of CTAs handles (CL 2 below; the direct-load kernel stops at 512 rows).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -784,16 +785,20 @@ static TmaShape tma_shape(const Layout &L, int dir, int forced)
 {
 	TmaShape S = {0, 8, 1};
 	const int n = dir == 0 ? L.nx : L.ny;
-	if (n % M != 0 || n / M > 64 || n / M <= 16) return S;               // 136 .. 512 rows
+	if (n % M != 0 || n / M > 128 || n / M <= 16) return S;              // 136 .. 1024 rows
 	int nl = (n / M <= 32 && dir == 0) ? 16 : 8, cl = 1;
+	if (n / M > 64) { forced = 0; nl = 8; cl = 2; }                      // 520 .. 1024 rows: only a CTA pair holds the line
 	static const char *env = getenv("CMC_TMA_SHAPE");                    // (experiments) "8x1" / "16x1" / "16x2": lines x CTAs per tile
-	if (env && !forced) {
+	if (env && !forced && n / M <= 64) {
 		int fnl = 0, fcl = 0;
 		if (sscanf(env, "%dx%d", &fnl, &fcl) == 2 && (fnl == 8 || fnl == 16) && (fcl == 1 || fcl == 2)) forced = fnl + 256 * fcl;
 	}
 	if (forced) { nl = forced & 255; cl = forced >> 8; }
 	// a CTA pair takes halves of whole chunks and, along y in blocked storage, of whole y-blocks
-	if (cl == 2 && (n % (2 * M) != 0 || (dir == 1 && L.nblk > 1 && (n / 2) % (1 << L.jbs) != 0))) cl = 1;
+	if (cl == 2 && (n % (2 * M) != 0 || (dir == 1 && L.nblk > 1 && (n / 2) % (1 << L.jbs) != 0))) {
+		if (n / M > 64) return S;                                        // (no single-CTA alternative)
+		cl = 1;
+	}
 	const int chunks = n / M / cl;
 	if (chunks > 32 && nl == 16) nl = 8;                                 // 1024 threads do not fit
 	S.gp = chunks > 32 ? 64 : 32; S.nl = nl; S.cl = cl;
@@ -803,10 +808,9 @@ static TmaShape tma_shape(const Layout &L, int dir, int forced)
 bool tma_sweep_supported(const Layout &L, int dir)
 {
 	if (dir != 0 && dir != 1) return false;
-	if (!fast_sweep_supported(L, dir)) return false;
-	const int n = dir == 0 ? L.nx : L.ny;
-	if (n % M != 0 || n / M > 64 || n / M <= 16) return false;           // 136 .. 512 rows: 256- and 512-thread CTAs
+	if (L.total >= (1ll << 31)) return false;                            // 32-bit element offsets
 	if (L.nblk > 1 && ((1 << L.jbs) % M != 0)) return false;
+	if (tma_shape(L, dir, 0).gp == 0) return false;                      // 136 .. 1024 rows, a multiple of 8 (16 above 512)
 	return encode_fn() != nullptr;
 }
 
@@ -858,7 +862,7 @@ template <typename FT, int DIR>
 static bool launch_tma_dir(const SweepArgs<FT> &A, cudaStream_t s)
 {
 	const TmaShape S = tma_shape(A.L, DIR, A.tma_shape);
-	if (S.gp == 64) return launch_tma_one<FT, DIR, 64, 8, 1>(A, s);
+	if (S.gp == 64) return S.cl == 2 ? launch_tma_one<FT, DIR, 64, 8, 2>(A, s) : launch_tma_one<FT, DIR, 64, 8, 1>(A, s);
 	if (S.gp != 32) return false;
 	if (S.nl == 16) return S.cl == 2 ? launch_tma_one<FT, DIR, 32, 16, 2>(A, s) : launch_tma_one<FT, DIR, 32, 16, 1>(A, s);
 	return S.cl == 2 ? launch_tma_one<FT, DIR, 32, 8, 2>(A, s) : launch_tma_one<FT, DIR, 32, 8, 1>(A, s);

@@ -104,3 +104,23 @@ def test_tma_tile_shapes_against_oracle(oracle_mod, dims, shape, fp):
         assert abs(e - e_ref) <= (1e-5 if fp == 4 else 1e-9) * abs(e_ref)
         assert_fields_close([ora.field(O.LAYER_CUR, q) for q in range(4)], [s.read_field(LAYER_CUR, q) for q in range(4)], fp, f"{dims} {shape} step {i}")
     s.close()
+
+
+@pytest.mark.parametrize("fp", [8, 4])
+@pytest.mark.parametrize("dims", [(1024, 24, 24), (24, 1024, 24), (1008, 40, 28), (40, 1024, 60), (528, 144, 20)])
+def test_lines_up_to_1024_rows_in_fast_mode(oracle_mod, dims, fp):
+    """x / y lines of 520 .. 1024 rows (a multiple of 16): a CTA pair holds the line (64 chunks each, the halves coupled through
+    distributed shared memory), so fast mode no longer stops at 512 rows along the strided axes.  Against the oracle."""
+    O = oracle_mod
+    case = channel_case(*dims, fp_bytes=fp, depth_var=0.25)
+    ora = O.Oracle3D(case); ora.create_segments()
+    s = _tma(case)
+    long_dir = 0 if dims[0] > 512 else 1
+    assert s.get_option(("kernel_x", "kernel_y")[long_dir]) == 3
+    for i in range(2):
+        ora.update_boundaries(); s.UpdateBoundaries()
+        e_ref = ora.time_step(case.dt, case.num_global, case.num_local, True)
+        e = s.TimeStep(case.dt, case.num_global, case.num_local, True)
+        assert abs(e - e_ref) <= (1e-5 if fp == 4 else 1e-9) * abs(e_ref)
+        assert_fields_close([ora.field(O.LAYER_CUR, q) for q in range(4)], [s.read_field(LAYER_CUR, q) for q in range(4)], fp, f"{dims} step {i}")
+    s.close()

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(128, 1) k_probe_bulk(const double *const *fiel
 struct Maps16 { CUtensorMap in[8], out[8]; };
 template <int NSLOT>
 __global__ void __launch_bounds__(128, 1) k_probe_copy(const __grid_constant__ Maps16 TM, int ntiles, int ktiles, int dir, int kw, int *counter, int slot_bytes,
-                                                      int jbm, int jbs)
+                                                      int jbm, int jbs, int halves, int c1h, int c2h)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	unsigned long long *full = reinterpret_cast<unsigned long long *>(smem + (size_t)NSLOT * slot_bytes);
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128, 1) k_probe_copy(const __grid_constant__ M
 	unsigned ph = 0;
 	int tile = blockIdx.x;
 	// software pipeline over (tile, field): loads run NSLOT - 1 ahead of the stores
-	struct Item { int c0, c3, c4, f; };
+	struct Item { int c0, c1, c2, c3, c4, f; };
 	Item ring[NSLOT];
 	int head = 0, count = 0;     // items in flight (loaded, not yet stored)
 	auto drain_one = [&]() {
@@ -179,14 +179,17 @@ __global__ void __launch_bounds__(128, 1) k_probe_copy(const __grid_constant__ M
 		if (it.f < 8) {           // the 3 repeats are read-only
 			asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
 			             ::"l"(reinterpret_cast<unsigned long long>(&TM.out[it.f])), "r"(smem_u32(smem + (size_t)s * slot_bytes)),
-			             "r"(it.c0), "r"(0), "r"(0), "r"(it.c3), "r"(it.c4) : "memory");
+			             "r"(it.c0), "r"(it.c1), "r"(it.c2), "r"(it.c3), "r"(it.c4) : "memory");
 			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 		}
 		head++; count--;
 	};
 	int issued = 0;
 	while (tile < ntiles) {
-		const int a = tile / ktiles, k0 = (tile - a * ktiles) * kw;
+		// (128-byte rows: a box holds half of every line; two boxes - `halves` - per line position)
+		const int pos = tile / halves, half = tile - pos * halves;
+		const int a = pos / ktiles, k0 = (pos - a * ktiles) * kw;
+		const int c1 = half * c1h, c2 = half * c2h;
 		int c3, c4;
 		if (dir == 0) { c3 = a & jbm; c4 = a >> jbs; } else { c3 = 0; c4 = a + 1; }
 		for (int f = 0; f < 11; f++) {
@@ -197,8 +200,8 @@ __global__ void __launch_bounds__(128, 1) k_probe_copy(const __grid_constant__ M
 			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(full + s)), "r"(slot_bytes) : "memory");
 			asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
 			             ::"r"(smem_u32(smem + (size_t)s * slot_bytes)), "l"(reinterpret_cast<unsigned long long>(&TM.in[f % 8])), "r"(smem_u32(full + s)),
-			             "r"(k0), "r"(0), "r"(0), "r"(c3), "r"(c4) : "memory");
-			ring[s] = Item{k0, c3, c4, f};
+			             "r"(k0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+			ring[s] = Item{k0, c1, c2, c3, c4, f};
 			issued++; count++;
 		}
 		tile = (int)gridDim.x + atomicAdd(counter, 1);
@@ -320,14 +323,16 @@ int main()
 					                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 					if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 1; }
 				}
-				const int ktiles = nz / kw, ntiles = (dir == 0 ? ny : nx) * ktiles, slot_bytes = kw * GP * 8 * 8;
+				const int halves = 64 / GP;                      // boxes per line position
+				const int ktiles = nz / kw, ntiles = (dir == 0 ? ny : nx) * ktiles * halves, slot_bytes = kw * GP * 8 * 8;
+				const int c1h = dir == 0 ? GP : 0, c2h = dir == 0 ? 0 : GP / (jb / 8);
 				const size_t smem = (size_t)6 * slot_bytes + 64;
 				CK(cudaFuncSetAttribute(k_probe_copy<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 				float best = 1e9f;
 				for (int rep = 0; rep < 3; rep++) {
 					CK(cudaMemset(counter, 0, 4));
 					cudaEventRecord(e0);
-					k_probe_copy<6><<<148, 128, smem>>>(TM, ntiles, ktiles, dir, kw, counter, slot_bytes, jbm, jbs);
+					k_probe_copy<6><<<148, 128, smem>>>(TM, ntiles, ktiles, dir, kw, counter, slot_bytes, jbm, jbs, halves, c1h, c2h);
 					cudaEventRecord(e1);
 					CK(cudaDeviceSynchronize());
 					float ms; cudaEventElapsedTime(&ms, e0, e1);
