@@ -390,6 +390,18 @@ def main():
         ms = float(t.item())
     value = ncells * args.steps / (ms * 1e-3) / 1e6
 
+    if os.environ.get("CMC_XS_TRACE") and rank == 0:      # (instrumented kernel builds only)
+        ph = [sol.get_option(f"tilectr{i}") for i in range(12, 23)]
+        nt = sol.get_option("tilectr8")
+        if nt:
+            names = ["-", "load+eliminate uvw", "reduced solve uvw", "send uvw", "wait uvw", "interface uvw", "back-subst + stores uvw", "diss + eliminate T", "reduced solve T", "send+wait+interface T", "back-subst + stores T"]
+            print("[phase trace x] cycles per tile: " + ", ".join(f"{n} {64 * v / nt:.0f}" for n, v in zip(names[1:], ph[1:])), file=sys.stderr)
+        c = [sol.get_option(f"tilectr{i}") for i in range(2, 12)]
+        for d, o in (("x", 4), ("y", 7)):
+            if c[o + 2]:
+                print(f"[tile trace] {d}: per tile, cycles: whole tile {64 * c[o] / c[o + 2]:.0f}, of which waiting for the tile's copies {64 * c[o + 1] / c[o + 2]:.0f} (tiles {c[o + 2]})", file=sys.stderr)
+        if c[2]:
+            print(f"[xs trace] per tile, cycles: wait u,v,w {64 * c[0] / c[2]:.0f}, interface u,v,w {64 * c[1] / c[2]:.0f}, wait T {64 * c[3] / c[2]:.0f} (tiles {c[2]})", file=sys.stderr)
     # ---- per-field checksums of the final layer (all-reduced): the same numbers at every N ----------------------------
     sums = sol.field_sums(0)
     checksums = {n: {"sum": v[0], "l2": v[1] ** 0.5} for n, v in sums.items()}

@@ -70,6 +70,7 @@ struct cmc_adi3d {
 	virtual int field_sums(int layer, double *sums8) = 0;
 	virtual int exchange_kind() const = 0;
 	virtual int kernel_kind(int dir) const = 0;
+	virtual int debug_counter(int i, int64_t *value) = 0;
 
 	int device = 0, fp = 8;
 	int rank = 0, nranks = 1;       // position of this handle's (first) slab among all slabs of the grid
@@ -82,6 +83,9 @@ struct cmc_adi3d {
 	int mode = CMC_MODE_FAST;
 	int tma_mask = default_tma_mask();
 	int tma_shape = 0;               // option "tma_shape": 0 = automatic, else lines per tile + 256 * CTAs per tile (kernels_tma.cu)
+	// option "xs" / CMC_XS=1: one-pass slab-coupled x-sweep (kernels_tma.cu XS).  Off by default: measured on 2 and 4 B200s it
+	// loses to the two-pass form (4.81 against 4.07 ms and 3.28 against 1.92 ms per x-sweep at 512^3, profiles/r02_variants.md)
+	int xs_enabled = getenv("CMC_XS") ? atoi(getenv("CMC_XS")) : 0;
 	static int default_tma_mask()
 	{
 		// default: both strided axes (measured at 512^3 fp64 on B200: x 5.14 -> 4.44 ms, y 5.07 -> 4.36 ms per launch against
@@ -202,6 +206,9 @@ struct Slab {
 	// partitioned x-sweep exchange buffers: [peer][16 | 8][lpo].  The *_recv tables are filled by the other slabs'
 	// kernels directly (they live in the arena); the *_send staging buffers exist only for the NCCL transport.
 	FT *xcoef_send = nullptr, *xcoef_recv = nullptr, *xbnd_send = nullptr, *xbnd_recv = nullptr;
+	// fused one-pass x-sweep (kernels_tma.cu XS): [slab][tile][16][lines per tile] coefficients of every slab's first / last
+	// row and [slab][tile][4][lines per tile] flag words, written by all slabs' kernels (arena)
+	unsigned long long *xs_tab = nullptr;
 	// exchange arena: everything another slab stores into - the 20 field buffers (guard planes), the two interface
 	// tables and the flag words - in ONE allocation with the same layout on every rank, so that one CUDA IPC mapping
 	// per peer makes all of it addressable over NVLink
@@ -245,7 +252,10 @@ struct Slab {
 			auto up = [](size_t v) { return (v + 255) / 256 * 256; };
 			const size_t fb = up(sizeof(FT) * (size_t)L.total), lpo = lines_per_owner(nslabs);
 			const size_t cb = nslabs > 1 ? up(sizeof(FT) * lpo * 16 * nslabs) : 0, bb = nslabs > 1 ? up(sizeof(FT) * lpo * 8 * nslabs) : 0;
-			flag_off = 20 * fb + cb + bb;
+			// (lines padded to whole 16-line tiles)
+			const size_t xlines = (size_t)G.ny * (size_t)((G.nz + 15) / 16 * 16);
+			const size_t xtb = nslabs > 1 ? up(sizeof(unsigned long long) * xlines * 16 * (sizeof(FT) / 4) * nslabs) : 0;
+			flag_off = 20 * fb + cb + bb + xtb;
 			arena_bytes = flag_off + 256;
 			CU_TRY(cudaMalloc((void **)&arena, arena_bytes));
 			CU_TRY(cudaMemsetAsync(arena, 0, arena_bytes, stream));
@@ -255,6 +265,7 @@ struct Slab {
 			if (nslabs > 1) {
 				xcoef_recv = reinterpret_cast<FT *>(arena + 20 * fb);
 				xbnd_recv = reinterpret_cast<FT *>(arena + 20 * fb + cb);
+				xs_tab = reinterpret_cast<unsigned long long *>(arena + 20 * fb + cb + bb);
 			}
 		}
 		for (int q = 0; q < 4; q++) if ((rc = dalloc(nodev[q], (size_t)L.total))) return rc;
@@ -422,11 +433,31 @@ struct Engine : cmc_adi3d {
 	bool push_mode() const { return multi() && (!nccl || p2p); }
 
 	// the address, in the slab that holds slab index `r`, of the buffer that is `mine` in slab `s`
-	FT *in_slab(Slab<FT> *s, int r, FT *mine) const
+	template <typename T>
+	T *in_slab(Slab<FT> *s, int r, T *mine) const
 	{
 		const size_t o = (size_t)((char *)mine - s->arena);
-		if (nccl) return reinterpret_cast<FT *>((char *)pm.base[r] + o);
-		return reinterpret_cast<FT *>(slabs[r]->arena + o);
+		if (nccl) return reinterpret_cast<T *>((char *)pm.base[r] + o);
+		return reinterpret_cast<T *>(slabs[r]->arena + o);
+	}
+	// One-pass slab-coupled x-sweep (kernels_tma.cu XS) instead of spike pass + interface kernel + coupled pass: needs the
+	// slabs' kernels to run at the same time (one process per GPU with mapped peer memory, or one process driving several
+	// devices - not the emulation of several slabs on one stream), whole 8-row chunks in every slab and the same tile
+	// shape for all slabs.  Every rank evaluates this from the same global split, so all take the same path.
+	// Option "xs" / CMC_XS=1 switches it on (see xs_enabled).
+	int xs_epoch = 0;
+	bool fused_x() const
+	{
+		if (!multi() || !xs_enabled || mode != CMC_MODE_FAST || !want_tma(CMC_DIR_X)) return false;
+		if (!((nccl && p2p) || multi_device)) return false;
+		int nl = -1;
+		for (int r = 0; r < nslabs_total; r++) {
+			Layout Lr = G; Lr.shape(split_nx[r], G.ny, G.nz, G.nzp, G.jbs, slabs[0]->L.bstride / slabs[0]->L.plane - 2);
+			const int v = tma_xs_lines(Lr);
+			if (!v || (nl >= 0 && v != nl)) return false;
+			nl = v;
+		}
+		return true;
 	}
 
 	// peer ordering (processes): publish `epoch` after this rank's kernel / wait for the ranks in `mask`
@@ -800,7 +831,16 @@ struct Engine : cmc_adi3d {
 		A.tile_counter = s->d_tilectr;
 		A.tma_shape = tma_shape;
 		for (int q = 0; q < 4; q++) A.push_lo[q] = A.push_hi[q] = A.pushn_lo[q] = A.pushn_hi[q] = nullptr;
-		for (int r = 0; r < MAX_SLABS; r++) A.xcoef_to[r] = nullptr;
+		for (int r = 0; r < MAX_SLABS; r++) { A.xcoef_to[r] = nullptr; A.xs_tab_to[r] = nullptr; }
+		A.xs_P = nslabs_total; A.xs_me = s->index; A.xs_epoch = xs_epoch; A.xs_share = 1; A.xs_tab = s->xs_tab;
+		if (multi() && push_mode() && dir == CMC_DIR_X) {
+			for (int r = 0; r < nslabs_total; r++) A.xs_tab_to[r] = in_slab(s, r, s->xs_tab);
+			if (multi_device) {
+				int share = 0;
+				for (auto *o : slabs) share += o->device == s->device;
+				A.xs_share = share;
+			}
+		}
 		if (multi()) {
 			const size_t lpo = (size_t)A.lpo;
 			const int me = s->index;
@@ -837,9 +877,18 @@ struct Engine : cmc_adi3d {
 	// which kernel a sweep along `dir` runs (get_option "kernel_x|y|z"): 0 exact Thomas kernels + merge, 1 direct-load
 	// partition kernel (kernels_fast.cu), 2 cp.async ring kernel (kernels_ring.cu), 4 slab-coupled x-sweep (spike pass +
 	// interface solve + coupled pass)
+	int debug_counter(int i, int64_t *value) override       // (kernel instrumentation builds: words of the tile-counter block)
+	{
+		int v = 0;
+		if (i < 0 || i >= 32) return fail(CMC_ERR_INVALID, "debug counter index");
+		use(slabs[0]);
+		CU_TRY(cudaMemcpy(&v, slabs[0]->d_tilectr + i, sizeof(int), cudaMemcpyDeviceToHost));
+		*value = v;
+		return CMC_OK;
+	}
 	int kernel_kind(int dir) const override
 	{
-		if (multi() && dir == CMC_DIR_X) return 4;
+		if (multi() && dir == CMC_DIR_X) return fused_x() ? 5 : 4;
 		if (!fast_ok(dir)) return 0;
 		if (want_tma(dir) && tma_sweep_supported(slabs[0]->L, dir)) return 3;
 		return want_ring(dir) && ring_sweep_supported(slabs[0]->L, dir) ? 2 : 1;
@@ -871,10 +920,12 @@ struct Engine : cmc_adi3d {
 			if (!(push_mode() && halos_ready))
 				if ((rc = halo_exchange(t_is_c ? CMC_LAYER_CUR : CMC_LAYER_TEMP))) return rc;   // x-stencils of the sweep read the neighbours' planes
 			const bool coupled = multi() && dir == CMC_DIR_X;
+			const bool fused = coupled && fused_x();
+			if (fused) xs_epoch++;
 			// the neighbours have finished their previous sweep: their stores into this slab's guard planes are complete,
 			// and they no longer read the guard planes this sweep is about to overwrite on their side
 			await(neighbour_mask());
-			if (coupled) {
+			if (coupled && !fused) {
 				// partitioned solve along the decomposed axis: spike pass -> coefficients to the line owners -> interface
 				// solve -> neighbour values back -> coupled sweep.  (replaces LaunchSolveSegments_X, AdiSolver3D.cu:524-640)
 				span_begin(CMC_TIMING_X_SPIKE);
@@ -915,7 +966,10 @@ struct Engine : cmc_adi3d {
 					for (int q = 0; q < 4; q++) A.temp[q] = s->field[s->slot[CMC_LAYER_CUR]][q];
 				A.extra_merge = (fold_post_merge && it == nl - 1) ? 1 : 0;
 				bool done = false;
-				if (coupled) {
+				if (fused) {
+					if (!launch_tma_xs<FT>(A, stream, &launches)) return fail(CMC_ERR_UNSUPPORTED, "one-pass slab-coupled x-sweep: launch failed");
+					done = true;
+				} else if (coupled) {
 					if (!launch_x_coupled<FT>(A, stream, &launches)) return fail(CMC_ERR_UNSUPPORTED, "coupled x-sweep: unsupported slab shape");
 					done = true;
 				} else if (fast_ok(dir)) {
@@ -1377,7 +1431,9 @@ static int create_impl(const cmc_grid_desc *grid, const cmc_fluid_params *params
 	if (devices) {
 		for (int i = 0; i < nlocal; i++) {
 			if ((rc = check_device(devices[i]))) return rc;
-			for (int j = 0; j < i; j++) if (devices[j] == devices[i]) return fail(CMC_ERR_INVALID, "create_multi: a device is listed twice");
+			// (CMC_SHARE_DEVICE=1: a test configuration - several slabs, each with its own stream, on one GPU)
+			static const bool share_ok = getenv("CMC_SHARE_DEVICE") && atoi(getenv("CMC_SHARE_DEVICE")) != 0;
+			for (int j = 0; j < i && !share_ok; j++) if (devices[j] == devices[i]) return fail(CMC_ERR_INVALID, "create_multi: a device is listed twice");
 			devs.push_back(devices[i]);
 		}
 	}
@@ -1665,6 +1721,7 @@ int cmc_adi3d_set_option(cmc_adi3d *h, const char *key, int64_t value)
 		return CMC_OK;
 	}
 	if (!strcmp(key, "tma")) { h->tma_mask = (int)value & 3; return CMC_OK; }
+	if (!strcmp(key, "xs")) { h->xs_enabled = value != 0; return CMC_OK; }
 	if (!strcmp(key, "tma_shape")) {
 		const int nl = (int)value & 255, cl = (int)value >> 8;
 		if (value != 0 && !((nl == 8 || nl == 16) && (cl == 1 || cl == 2))) return fail(CMC_ERR_INVALID, "set_option tma_shape: 0, or lines per tile (8 | 16) + 256 * CTAs per tile (1 | 2)");
@@ -1686,6 +1743,8 @@ int cmc_adi3d_get_option(const cmc_adi3d *h, const char *key, int64_t *value)
 	if (!strcmp(key, "mode")) { *value = h->mode; return CMC_OK; }
 	if (!strcmp(key, "tma")) { *value = h->tma_mask; return CMC_OK; }
 	if (!strcmp(key, "tma_shape")) { *value = h->tma_shape; return CMC_OK; }
+	if (!strcmp(key, "xs")) { *value = h->xs_enabled; return CMC_OK; }
+	if (!strncmp(key, "tilectr", 7) && key[7] >= '0' && key[7] <= '9') { return const_cast<cmc_adi3d *>(h)->debug_counter(atoi(key + 7), value); }
 	if (!strcmp(key, "nzp")) { *value = h->L.nzp; return CMC_OK; }
 	if (!strcmp(key, "jb")) { *value = h->L.nblk == 1 ? 0 : (1 << h->L.jbs); return CMC_OK; }   // rows per y-block, 0 = one block
 	if (!strncmp(key, "kernel_", 7) && key[7] >= 'x' && key[7] <= 'z' && !key[8]) { *value = h->kernel_kind(key[7] - 'x'); return CMC_OK; }

@@ -97,6 +97,13 @@ struct SweepArgs {
 	int extra_merge;         // fast mode: apply the relaxation twice (folds the post-X MergeLayerTo, AdiSolver3D.cpp:354)
 	int *tile_counter;       // persistent-CTA kernels (kernels_tma.cu): next tile to hand out; zeroed before every launch
 	int tma_shape;           // kernels_tma.cu: 0 = automatic tile shape, else lines per tile + 256 * CTAs per tile
+	// fused slab-coupled x-sweep (kernels_tma.cu XS): every slab holds a table [slab][tile][16 coefficients][words][lines per
+	// tile] of self-validating 8-byte words (payload + epoch); a slab's kernel stores its part into all other slabs' tables
+	int xs_P, xs_me;         // number of slabs, this slab's index
+	int xs_epoch;            // the epoch of this sweep (grows from sweep to sweep; the tables are never reset)
+	int xs_share;            // slabs that share this slab's device (1 unless a test runs several slabs on one GPU)
+	unsigned long long *xs_tab;               // this slab's table
+	unsigned long long *xs_tab_to[MAX_SLABS]; // every slab's table (peer memory)
 	// ---- slab-decomposed runs: exchanges fused into the sweeps as stores into the other slabs' buffers (peer memory
 	// over NVLink when the slabs live on different GPUs, see dist.h) --------------------------------------------------
 	// boundary x-planes of the sweep's outputs -> the x-neighbours' guard planes.  Each pointer addresses the target

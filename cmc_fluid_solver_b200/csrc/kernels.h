@@ -23,6 +23,10 @@ bool ring_sweep_supported(const Layout &L, int dir);
 // kernels_tma.cu: x / y sweeps as persistent CTAs fed by bulk-tensor copies (TMA); false = not applicable, use the above
 template <typename FT>
 bool launch_tma_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
+// fused slab-coupled x-sweep (one pass): lines per tile of the slab shape, 0 = not supported; the launch
+int tma_xs_lines(const Layout &L);
+template <typename FT>
+bool launch_tma_xs(const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
 bool tma_sweep_supported(const Layout &L, int dir);
 // partitioned x-sweep (slab-decomposed grid): spike pass, interface solve, coupled sweep
 template <typename FT>

@@ -243,6 +243,92 @@ __device__ __forceinline__ void mbar_wait_cluster(unsigned long long *bar, unsig
 	}
 }
 
+// ---- helpers of the fused slab-coupled x-sweep (XS): coefficient tables in the other slabs' memory ----------------------------
+// A value crosses to another GPU as self-validating 8-byte words - 32 bits of payload + the sweep's 32-bit epoch, one aligned
+// store each (the low-latency protocol of collective libraries): the reader polls the word until it carries the epoch, no
+// flag word, no fence on either side.  (A release store at system scope has to wait until every earlier store of the thread -
+// the sweep's result stores - is acknowledged: measured 20 us per exchange under load, against ~3 us this way.)
+template <typename FT> struct LLWords;
+template <> struct LLWords<double> { static constexpr int W = 2; };
+template <> struct LLWords<float> { static constexpr int W = 1; };
+__device__ __forceinline__ void ll_store(unsigned long long *p, size_t wstride, double v, unsigned epoch)
+{
+	const unsigned long long b = (unsigned long long)__double_as_longlong(v), ep = (unsigned long long)epoch << 32;
+	*reinterpret_cast<volatile unsigned long long *>(p) = (b & 0xffffffffull) | ep;
+	*reinterpret_cast<volatile unsigned long long *>(p + wstride) = (b >> 32) | ep;
+}
+__device__ __forceinline__ void ll_store(unsigned long long *p, size_t, float v, unsigned epoch)
+{
+	*reinterpret_cast<volatile unsigned long long *>(p) = (unsigned long long)__float_as_uint(v) | ((unsigned long long)epoch << 32);
+}
+// word w of a value with the epoch on top
+__device__ __forceinline__ unsigned long long ll_word(double v, int w, unsigned epoch)
+{
+	const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+	return (w ? b >> 32 : b & 0xffffffffull) | ((unsigned long long)epoch << 32);
+}
+__device__ __forceinline__ unsigned long long ll_word(float v, int, unsigned epoch) { return (unsigned long long)__float_as_uint(v) | ((unsigned long long)epoch << 32); }
+// poll one word until it carries `epoch`; a peer that never arrives must not hang the device: trap after about two seconds
+__device__ __forceinline__ unsigned ll_poll(const unsigned long long *p, unsigned epoch)
+{
+	long long t0 = 0;
+	for (int tries = 0;; tries++) {
+		const unsigned long long w = *reinterpret_cast<const volatile unsigned long long *>(p);
+		if ((unsigned)(w >> 32) == epoch) return (unsigned)w;
+		if ((tries & 255) == 255) {
+			const long long now = clock64();
+			if (!t0) t0 = now;
+			else if (now - t0 > 4000000000ll) __trap();
+		}
+	}
+}
+// a value from its polled payload words (shared memory)
+template <typename FT> __device__ __forceinline__ FT ll_value(const unsigned *p, int wstride);
+template <> __device__ __forceinline__ double ll_value<double>(const unsigned *p, int wstride)
+{
+	return __longlong_as_double((long long)(((unsigned long long)p[wstride] << 32) | p[0]));
+}
+template <> __device__ __forceinline__ float ll_value<float>(const unsigned *p, int) { return __uint_as_float(p[0]); }
+
+// Interface system of one line across P slabs (same algebra as k_x_interface, kernels_fast.cu): unknowns per slab r the first
+// row F_r and the last row L_r,   F_r + pf_r L_{r-1} + qf_r F_{r+1} = f_r ,   L_r + pl_r L_{r-1} + ql_r F_{r+1} = l_r ,
+// block-tridiagonal in Z_r = (L_r, F_{r+1}), block Thomas.  Every slab solves it for itself (all slabs' coefficients are in
+// its table) and keeps the two values it needs: xl = L_{me-1}, xr = F_{me+1}.  C(r, v) = coefficient v of slab r for this line.
+template <typename FT, int NR, typename Coef>
+__device__ __noinline__ void xs_interface(Coef C, int P, int me, int vf, int vl, int vp, FT (&xl)[NR], FT (&xr)[NR])
+{
+	constexpr int MP = MAX_SLABS;
+	FT m01[MP], i00[MP], i01[MP], i10[MP], i11[MP], r0[NR][MP], r1[NR][MP];
+	FT p_i01 = 0, p_s[NR];
+#pragma unroll
+	for (int q = 0; q < NR; q++) { p_s[q] = 0; xl[q] = 0; xr[q] = 0; }
+	for (int r = 0; r + 1 < P; r++) {
+		const FT pl = C(r, vp + 2), ql = C(r, vp + 3), pf1 = C(r + 1, vp + 0), qf_r = C(r, vp + 1);
+		m01[r] = ql - pl * p_i01 * qf_r;             // (r == 0: pl == 0)
+		const FT id = rcp<FT>(FT(1) - m01[r] * pf1);
+		i00[r] = id; i01[r] = -m01[r] * id; i10[r] = -pf1 * id; i11[r] = id;
+#pragma unroll
+		for (int q = 0; q < NR; q++) {
+			r0[q][r] = C(r, vl + q) - pl * p_s[q];
+			r1[q][r] = C(r + 1, vf + q);
+			p_s[q] = i00[r] * r0[q][r] + i01[r] * r1[q][r];
+		}
+		p_i01 = i01[r];
+	}
+#pragma unroll
+	for (int q = 0; q < NR; q++) {
+		FT nextF = FT(0);                            // F_{r+2} of the block above
+		for (int r = P - 2; r >= 0; r--) {
+			const FT qf1 = C(r + 1, vp + 1);
+			const FT b0 = r0[q][r], b1 = r1[q][r] - qf1 * nextF;
+			const FT Lr = i00[r] * b0 + i01[r] * b1, Fr1 = i10[r] * b0 + i11[r] * b1;
+			if (r == me - 1) xl[q] = Lr;
+			if (r == me) xr[q] = Fr1;
+			nextF = Fr1;
+		}
+	}
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------------------------------
 // GP chunks x NL lines per CTA (GP * NL threads).  CL = CTAs per tile:
 //   CL 1: the CTA holds whole lines (up to GP * 8 rows);
@@ -253,19 +339,26 @@ __device__ __forceinline__ void mbar_wait_cluster(unsigned long long *bar, unsig
 //         read twice: each CTA eliminates its half, solves its reduced system with one extra right-hand side (the
 //         response to the unknown row of the other half), the CTAs swap 4 numbers per line and phase through distributed
 //         shared memory, and every thread finishes its rows from registers.
-template <typename FT, int DIR, int GP, int NL, int CL>
+//   XS 1: the slab-coupled x-sweep of a decomposed grid in ONE pass (replaces spike pass + interface kernel + coupled pass,
+//         kernels_fast.cu MODE 1 / 2): the same open-ended elimination with two spike columns; the first / last row's
+//         coefficients of every line go straight into every other slab's table (peer memory over NVLink, 128-byte stores)
+//         followed by a release flag per line; the tile's first NL threads wait for the flags of all slabs, solve the
+//         interface system of their line, and every thread finishes its rows from registers.  No slab waits before it has
+//         sent, tiles are handed out in index order on every GPU, so the smallest unfinished tile can always complete.
+template <typename FT, int DIR, int GP, int NL, int CL, int XS>
 __global__ void __launch_bounds__(GP * NL, GP * NL >= 512 ? 1 : 512 / (GP * NL))
 k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant__ TmaMaps TM, const int ntiles, const int hints)
 {
 	static_assert(DIR == 0 || DIR == 1, "strided axes only (z lines are contiguous: kernels_fast.cu)");
 	static_assert(NL == 8 || NL == 16, "8 or 16 lines per tile");
 	static_assert(CL == 1 || CL == 2, "one CTA or a CTA pair per tile");
+	static_assert(XS == 0 || (DIR == 0 && CL == 1), "slabs couple along x; one CTA per tile");
 	constexpr int STR = GP * NL;
 	constexpr int GS = NL;                          // shared-memory distance of neighbouring chunks of a line
 	constexpr int SLOT = STR * M;                   // elements per slot: one field of one tile (part)
 	constexpr int NW = STR / 32;                    // warps
 	constexpr int NS = 5;                           // slots
-	constexpr int XV = CL == 2 ? 1 : 0;             // extra right-hand sides of the reduced solves (CL 2: one spike column)
+	constexpr int XV = CL == 2 ? 1 : XS ? 2 : 0;    // extra right-hand sides of the reduced solves (spike columns)
 	constexpr unsigned SLOT_BYTES = SLOT * (unsigned)sizeof(FT);
 	// the two temp components other than the one along the sweep, and their slots
 	constexpr int QO1 = DIR == 0 ? 1 : 0, QO2 = 2;
@@ -275,12 +368,13 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 	FT *sol = sys;                                                                  // aliases the CR publications (see reduced_solve)
 	FT *headx = sys + reduced_scratch_elems<3 + XV, GP, NL>();                      // heads that cross a warp: 5 x (NW * NL)
 	FT *edge = headx + 5 * NW * NL;                                                 // CL 2: the row next to this half, 4 fields x NL
-	FT *xown = edge + (CL == 2 ? 4 * NL : 0);                                       // CL 2: this half's interface coefficients [6][NL]
-	FT *xin = xown + (CL == 2 ? 6 * NL : 0);                                        // CL 2: the other half's, written by the peer CTA
-	uint8_t *roles = reinterpret_cast<uint8_t *>(xin + (CL == 2 ? 6 * NL : 0));     // descriptor bytes of the tile: NL * GP * 8
+	FT *xown = edge + (CL == 2 ? 4 * NL : XS ? 8 * NL : 0);                         // CL 2: this half's interface coefficients [6][NL]; XS: xl / xr [8][NL]
+	FT *xin = xown + (CL == 2 ? 6 * NL : XS ? 8 * NL : 0);                          // CL 2: the other half's, written by the peer CTA; XS: this slab's own 16 coefficients
+	uint8_t *roles = reinterpret_cast<uint8_t *>(xin + (CL == 2 ? 6 * NL : XS ? 16 * NL : 0));     // descriptor bytes of the tile: NL * GP * 8
 	unsigned long long *full = reinterpret_cast<unsigned long long *>(roles + NL * GP * 8);   // NS mbarriers (+ 2 for the exchange)
 	unsigned long long *xbar = full + NS;                                                 // CL 2: [0] u,v,w phase, [1] T phase
 	int *next_box = reinterpret_cast<int *>(full + NS + 2);                               // the tile after the current one
+	unsigned *xw = reinterpret_cast<unsigned *>(next_box + 4);                            // XS: the other slabs' words of this tile, [slab][value][word][line]
 #define SLOTP(k) (slots + (k) * SLOT)
 
 	const Layout &L = A.L;
@@ -299,7 +393,7 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 	const int cid = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // tile-processing unit: CTA or CTA pair
 	const int nunits = (int)gridDim.x / CL;
 	// open ends of this part (CL 2): the other half continues the line there
-	const bool open_lo = CL == 2 && crank == 1, open_hi = CL == 2 && crank == 0;
+	const bool open_lo = XS ? A.xs_me > 0 : (CL == 2 && crank == 1), open_hi = XS ? A.xs_me + 1 < A.xs_P : (CL == 2 && crank == 0);
 
 	if (t == 0) {
 #pragma unroll
@@ -361,6 +455,10 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 			const long long o = DIR == 0 ? L.idx(r, a, kk) : L.idx(a, r, kk);
 			cp_async_elem<FT>(edge + t, A.temp[q] + o);
 		}
+		if (XS && t < 8 * NL) {              // the guard planes: rows -1 and n of the slab (kept current by the neighbours' sweeps)
+			const int side = t / (4 * NL), q = (t / NL) & 3, ll = t % NL;
+			cp_async_elem<FT>(edge + t, A.temp[q] + L.idx(side ? n : -1, a, min(k0 + ll, L.nz - 1)));
+		}
 		cp_async_commit();
 	};
 
@@ -402,9 +500,19 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 		const int e_hi = g + 1 < GL ? e + GS : (M - 1) * STR + e;          // row r0 + 8 = first row of chunk g + 1
 		const bool edge_lo = open_lo && g == 0, edge_hi = open_hi && g == GL - 1;
 
+#ifdef CMC_XS_TRACE
+		const long long tt0 = clock64();
+#endif
 		cp_async_wait_all();
 		WAIT_SLOT(0); WAIT_SLOT(1); WAIT_SLOT(2); WAIT_SLOT(3); WAIT_SLOT(4);
 		__syncthreads();            // roles (cp.async of every thread) have landed
+#ifdef CMC_XS_TRACE
+		const long long tt1 = clock64();
+		long long tlast = tt1;
+#define TRACE(k) do { if (t == 0) { const long long now__ = clock64(); atomicAdd(A.tile_counter + 12 + (k), (int)((now__ - tlast) >> 6)); tlast = now__; } } while (0)
+#else
+#define TRACE(k) do { } while (0)
+#endif
 
 		unsigned rw0 = 0, rw1 = 0;
 #pragma unroll
@@ -438,7 +546,7 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 				dp[1][i] = SLOTP(3)[i * STR + e];
 				dp[2][i] = SLOTP(4)[i * STR + e];
 			}
-			const FT Tlo = edge_lo ? edge[3 * NL + l] : SLOTP(1)[e_lo], Thi = edge_hi ? edge[3 * NL + l] : SLOTP(1)[e_hi];
+			const FT Tlo = edge_lo ? edge[3 * NL + l] : SLOTP(1)[e_lo], Thi = edge_hi ? edge[(XS ? 7 : 3) * NL + l] : SLOTP(1)[e_hi];
 			slot_reads_done();
 			__syncthreads();        // every thread has its inputs in registers: slots 1-4 are free (slot 0 stays)
 			if (t == 0) {
@@ -493,7 +601,7 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 			(dst) = lane < 32 - NL ? sh__ : (warp + 1 < NW ? headx[(slot_) * (NW * NL) + (warp + 1) * NL + (lane - (32 - NL))] : FT(0)); \
 		} while (0)
 		FT E[3];
-		FT xl[3] = {FT(0), FT(0), FT(0)}, xr[3] = {FT(0), FT(0), FT(0)}, Es = FT(0);      // CL 2: the other half's adjacent row, this separator's spike
+		FT xl[3] = {FT(0), FT(0), FT(0)}, xr[3] = {FT(0), FT(0), FT(0)}, Es = FT(0), Es2 = FT(0);      // CL 2 / XS: the adjacent rows of the other half / slabs, this separator's spikes
 		{
 			// coupling of the first interior row to the two separators: x_0 = y0 - v0*E(g-1) - w0*E(g)
 			FT y0[3] = {dp[0][M - 2], dp[1][M - 2], dp[2][M - 2]}, v0 = lp[M - 2], w0 = cp[M - 2];
@@ -516,7 +624,85 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 			Rd[0] = (dp[0][M - 1] - a7 * dp[0][M - 2] - c7 * ny0) * rr;
 			Rd[1] = (dp[1][M - 1] - a7 * dp[1][M - 2] - c7 * ny1) * rr;
 			Rd[2] = (dp[2][M - 1] - a7 * dp[2][M - 2] - c7 * ny2) * rr;
-			if (CL == 2) {
+			if (DIR == 0) TRACE(1);
+			if (XS) {
+				// open-ended slab: E = Y - P * x_left - Q * x_right (kernels_fast.cu MODE 1), P / Q two more right-hand sides
+				FT Re[5] = {Rd[0], Rd[1], Rd[2], FT(0), FT(0)}, Xe[5];
+				FT Ra = -a7 * lp[M - 2] * rr;
+				if (g == 0) { Re[3] = Ra; Ra = FT(0); }
+				if (g == GL - 1) Re[4] = c7 * rr;            // (the chunk after it is an identity chunk or absent: nv == nw == 0)
+				reduced_solve<FT, 5, GP, GS, NL>(sys, sol, g, e, Ra, -c7 * nw * rr, Re, Xe);
+				TRACE(2);
+				constexpr int W = LLWords<FT>::W;
+				if (g == 0 || g == GL - 1) {
+					// first row: x = f - pf x_left - qf x_right (table entries 0-2, 6, 7); last row: x = l - pl x_left - ql x_right (3-5, 8, 9)
+					const bool first = g == 0;
+					FT c5[5];
+					if (first) {
+#pragma unroll
+						for (int q = 0; q < 3; q++) c5[q] = y0[q] - w0 * Xe[q];
+						c5[3] = v0 - w0 * Xe[3]; c5[4] = -w0 * Xe[4];
+					} else {
+#pragma unroll
+						for (int q = 0; q < 5; q++) c5[q] = Xe[q];
+					}
+					const int vi[5] = {first ? 0 : 3, first ? 1 : 4, first ? 2 : 5, first ? 6 : 8, first ? 7 : 9};
+#pragma unroll
+					for (int q = 0; q < 5; q++) xin[vi[q] * NL + l] = c5[q];
+				}
+				__syncthreads();                             // this slab's coefficients are in xin
+				// ... and go to every other slab's table, one word per thread and turn (128-byte stores, all warps share the work)
+				for (int idx = t; idx < (A.xs_P - 1) * 10 * W * NL; idx += STR) {
+					const int ll = idx % NL, r1 = idx / NL, w = r1 % W, r2 = r1 / W, v = r2 % 10, ro = r2 / 10, r = ro < A.xs_me ? ro : ro + 1;
+					*reinterpret_cast<volatile unsigned long long *>(A.xs_tab_to[r] + ((((size_t)A.xs_me * ntiles + tile) * 16 + v) * W + w) * NL + ll) =
+						ll_word(xin[v * NL + ll], w, (unsigned)A.xs_epoch);
+				}
+				// all threads fetch the other slabs' words of this tile side by side (one poll each, instead of a chain of dependent
+				// polls in the thread that solves the interface)
+				TRACE(3);
+#ifdef CMC_XS_TRACE
+				const long long tw0 = clock64();
+#endif
+				for (int idx = t; idx < (A.xs_P - 1) * 10 * W * NL; idx += STR) {
+					const int ll = idx % NL, r1 = idx / NL, w = r1 % W, r2 = r1 / W, v = r2 % 10, ro = r2 / 10, r = ro < A.xs_me ? ro : ro + 1;
+					xw[idx] = ll_poll(A.xs_tab + ((((size_t)r * ntiles + tile) * 16 + v) * W + w) * NL + ll, (unsigned)A.xs_epoch);
+				}
+				__syncthreads();                             // this slab's coefficients are in xin, the others' in xw
+				TRACE(4);
+#ifdef CMC_XS_TRACE
+				const long long tw1 = clock64();
+#endif
+				if (g == 0) {                                // this line's interface system
+					auto C = [&](int r, int v) -> FT {
+						if (r == A.xs_me) return xin[v * NL + l];
+						const int ro = r < A.xs_me ? r : r - 1;
+						return ll_value<FT>(xw + ((ro * 10 + v) * W) * NL + l, NL);
+					};
+					FT il[3] = {FT(0), FT(0), FT(0)}, ir[3] = {FT(0), FT(0), FT(0)};
+					if (A.xs_P == 2) {
+						// two slabs: L_0 + ql_0 F_1 = l_0, F_1 + pf_1 L_0 = f_1
+						const FT ql0 = C(0, 9), pf1 = C(1, 6), den = rcp<FT>(FT(1) - ql0 * pf1);
+#pragma unroll
+						for (int q = 0; q < 3; q++) {
+							const FT l0 = C(0, 3 + q), f1 = C(1, q), L0 = (l0 - ql0 * f1) * den;
+							if (A.xs_me == 0) ir[q] = f1 - pf1 * L0; else il[q] = L0;
+						}
+					} else
+						xs_interface<FT, 3>(C, A.xs_P, A.xs_me, 0, 3, 6, il, ir);
+#pragma unroll
+					for (int q = 0; q < 3; q++) { xown[q * NL + l] = il[q]; xown[(4 + q) * NL + l] = ir[q]; }
+				}
+#ifdef CMC_XS_TRACE
+				if (t == 0) { atomicAdd(A.tile_counter + 2, (int)((tw1 - tw0) >> 6)); atomicAdd(A.tile_counter + 3, (int)((clock64() - tw1) >> 6)); atomicAdd(A.tile_counter + 4, 1); }
+#endif
+				__syncthreads();
+#pragma unroll
+				for (int q = 0; q < 3; q++) { xl[q] = xown[q * NL + l]; xr[q] = xown[(4 + q) * NL + l]; }
+				TRACE(5);
+				Es = Xe[3]; Es2 = Xe[4];
+#pragma unroll
+				for (int q = 0; q < 3; q++) E[q] = Xe[q] - Es * xl[q] - Es2 * xr[q];
+			} else if (CL == 2) {
 				// open-ended half: E = Y - S * x_other, S = one more right-hand side: the left spike of chunk 0 (upper half,
 				// x_other = last row of the lower half) or the last separator's coupling c7 (lower half, x_other = first row
 				// of the upper half).  Same algebra as the slab-coupled x-sweep (kernels_fast.cu MODE 1).
@@ -559,16 +745,21 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 				Es = Xe[3];
 #pragma unroll
 				for (int q = 0; q < 3; q++) E[q] = Xe[q] - Es * (open_hi ? xr[q] : xl[q]);
-			} else
+			} else {
 				reduced_solve<FT, 3, GP, GS, NL>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, E);    // every row's solution -> sol[]
+				if (DIR == 0) TRACE(2);
+			}
 		}
 		// back substitution in place (dp[q] <- x: retires cp / lp), then store u, v, w and the relaxed linearisation layer
 		{
-			const FT Sl = (CL == 2 && g > 0) ? sol[3 * STR + e - GS] : FT(0);
+			const FT Sl = ((CL == 2 || XS) && g > 0) ? sol[3 * STR + e - GS] : FT(0);
+			const FT Sl2 = (XS && g > 0) ? sol[4 * STR + e - GS] : FT(0);
+			(void)Es; (void)Es2;
 #pragma unroll
 			for (int q = 0; q < 3; q++) {
 				FT El = g > 0 ? sol[q * STR + e - GS] : FT(0);
 				if (CL == 2) El = g > 0 ? El - Sl * (open_hi ? xr[q] : xl[q]) : xl[q];      // chunk 0 of the upper half: row -1 is x_last(lower)
+				if (XS) El = g > 0 ? El - Sl * xl[q] - Sl2 * xr[q] : xl[q];                 // chunk 0: row -1 is the lower slab's last row
 				dp[q][M - 1] = E[q];
 #pragma unroll
 				for (int i = M - 2; i >= 0; i--) dp[q][i] = dp[q][i] - lp[i] * El - cp[i] * dp[q][i + 1];
@@ -590,9 +781,10 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 			relax8<FT, DIR>(tq, x, inmask, A.extra_merge);
 			store8_stream<FT>(A.temp_out[q], off, full_m, tq, streaming);
 			store8_stream<FT>(A.next[q], off, segfull, x, streaming);
-			push_planes<FT, DIR, 0>(A, q, a, g, GP, off, full_m, segfull, tq, x);
+			push_planes<FT, DIR, XS ? 2 : 0>(A, q, a, g, XS ? GL : GP, off, full_m, segfull, tq, x);
 		}
 
+		if (DIR == 0) TRACE(6);
 		// ======================================= phase T ======================================================
 		FT (&dT)[M] = dp[0];
 		{
@@ -642,7 +834,7 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 					FT f[M];
 #pragma unroll
 					for (int i = 0; i < M; i++) f[i] = sq[i * STR + e];
-					const FT lo = edge_lo ? edge[q * NL + l] : sq[e_lo], hi = edge_hi ? edge[q * NL + l] : sq[e_hi];
+					const FT lo = edge_lo ? edge[q * NL + l] : sq[e_lo], hi = edge_hi ? edge[((XS ? 4 : 0) + q) * NL + l] : sq[e_hi];
 #pragma unroll
 					for (int i = 0; i < M; i++) {
 						const FT d = cdiff<FT>(f, lo, hi, i, K.inv2h);
@@ -712,7 +904,61 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 			rr = rcp<FT>(b7 - a7 * cp[M - 2] - c7 * nv);
 			FT Rd[1] = {(dT[M - 1] - a7 * dT[M - 2] - c7 * ny0) * rr}, ET[1];
 			FT El;
-			if (CL == 2) {
+			if (DIR == 0) TRACE(7);
+			if (XS) {
+				FT Re[3] = {Rd[0], FT(0), FT(0)}, Xe[3];
+				FT Ra = -a7 * lp[M - 2] * rr;
+				if (g == 0) { Re[1] = Ra; Ra = FT(0); }
+				if (g == GL - 1) Re[2] = c7 * rr;
+				reduced_solve<FT, 3, GP, GS, NL>(sys, sol, g, e, Ra, -c7 * nw * rr, Re, Xe);
+				TRACE(8);
+				constexpr int W = LLWords<FT>::W;
+				if (g == 0 || g == GL - 1) {
+					// table entries: 10 f, 12 pf, 13 qf (first row); 11 l, 14 pl, 15 ql (last row)
+					const bool first = g == 0;
+					const FT c3[3] = {first ? y0 - w0 * Xe[0] : Xe[0], first ? v0 - w0 * Xe[1] : Xe[1], first ? -w0 * Xe[2] : Xe[2]};
+					const int vi[3] = {first ? 10 : 11, first ? 12 : 14, first ? 13 : 15};
+#pragma unroll
+					for (int q = 0; q < 3; q++) xin[vi[q] * NL + l] = c3[q];
+				}
+				__syncthreads();
+				for (int idx = t; idx < (A.xs_P - 1) * 6 * W * NL; idx += STR) {
+					const int ll = idx % NL, r1 = idx / NL, w = r1 % W, r2 = r1 / W, v = 10 + r2 % 6, ro = r2 / 6, r = ro < A.xs_me ? ro : ro + 1;
+					*reinterpret_cast<volatile unsigned long long *>(A.xs_tab_to[r] + ((((size_t)A.xs_me * ntiles + tile) * 16 + v) * W + w) * NL + ll) =
+						ll_word(xin[v * NL + ll], w, (unsigned)A.xs_epoch);
+				}
+#ifdef CMC_XS_TRACE
+				const long long tw0 = clock64();
+#endif
+				for (int idx = t; idx < (A.xs_P - 1) * 6 * W * NL; idx += STR) {
+					const int ll = idx % NL, r1 = idx / NL, w = r1 % W, r2 = r1 / W, v = r2 % 6, ro = r2 / 6, r = ro < A.xs_me ? ro : ro + 1;
+					xw[idx] = ll_poll(A.xs_tab + ((((size_t)r * ntiles + tile) * 16 + 10 + v) * W + w) * NL + ll, (unsigned)A.xs_epoch);
+				}
+				__syncthreads();
+#ifdef CMC_XS_TRACE
+				if (t == 0) atomicAdd(A.tile_counter + 5, (int)((clock64() - tw0) >> 6));
+#endif
+				if (g == 0) {
+					auto C = [&](int r, int v) -> FT {
+						if (r == A.xs_me) return xin[v * NL + l];
+						const int ro = r < A.xs_me ? r : r - 1;
+						return ll_value<FT>(xw + ((ro * 6 + (v - 10)) * W) * NL + l, NL);
+					};
+					FT il[1] = {FT(0)}, ir[1] = {FT(0)};
+					if (A.xs_P == 2) {
+						const FT ql0 = C(0, 15), pf1 = C(1, 12), l0 = C(0, 11), f1 = C(1, 10);
+						const FT L0 = (l0 - ql0 * f1) * rcp<FT>(FT(1) - ql0 * pf1);
+						if (A.xs_me == 0) ir[0] = f1 - pf1 * L0; else il[0] = L0;
+					} else
+						xs_interface<FT, 1>(C, A.xs_P, A.xs_me, 10, 11, 12, il, ir);
+					xown[3 * NL + l] = il[0]; xown[7 * NL + l] = ir[0];
+				}
+				__syncthreads();
+				const FT xlT = xown[3 * NL + l], xrT = xown[7 * NL + l];
+				TRACE(9);
+				ET[0] = Xe[0] - Xe[1] * xlT - Xe[2] * xrT;
+				El = g > 0 ? sol[e - GS] - sol[STR + e - GS] * xlT - sol[2 * STR + e - GS] * xrT : xlT;
+			} else if (CL == 2) {
 				FT Re[2] = {Rd[0], FT(0)}, Xe[2];
 				FT Ra = -a7 * lp[M - 2] * rr;
 				if (open_lo && g == 0) { Re[1] = Ra; Ra = FT(0); }
@@ -736,6 +982,7 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 			} else {
 				reduced_solve<FT, 1, GP, GS, NL>(sys, sol, g, e, -a7 * lp[M - 2] * rr, -c7 * nw * rr, Rd, ET);
 				El = g > 0 ? sol[e - GS] : FT(0);
+				if (DIR == 0) TRACE(8);
 			}
 			FT x[M], tq[M];
 			x[M - 1] = ET[0];
@@ -755,8 +1002,12 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 			relax8<FT, DIR>(tq, x, inmask, A.extra_merge);
 			store8_stream<FT>(A.temp_out[3], off, full_m, tq, streaming);
 			store8_stream<FT>(A.next[3], off, segfull, x, streaming);
-			push_planes<FT, DIR, 0>(A, 3, a, g, GP, off, full_m, segfull, tq, x);
+			push_planes<FT, DIR, XS ? 2 : 0>(A, 3, a, g, XS ? GL : GP, off, full_m, segfull, tq, x);
 		}
+		if (DIR == 0) TRACE(10);
+#ifdef CMC_XS_TRACE
+		if (t == 0) { atomicAdd(A.tile_counter + 6 + 3 * DIR, (int)((clock64() - tt0) >> 6)); atomicAdd(A.tile_counter + 7 + 3 * DIR, (int)((tt1 - tt0) >> 6)); atomicAdd(A.tile_counter + 8 + 3 * DIR, 1); }
+#endif
 		tile = next_tile;
 	}
 	cp_async_wait_all();
@@ -766,13 +1017,14 @@ k_tma_sweep(const SweepArgs<FT> A, const FastConst<FT> K, const __grid_constant_
 #undef WAIT_SLOT
 #undef WAIT_XCHG
 #undef NEXT_HEAD
+#undef TRACE
 }
 
-template <typename FT, int GP, int NL, int CL>
+template <typename FT, int GP, int NL, int CL, int XS>
 static size_t tma_smem_bytes()
 {
 	const size_t STR = (size_t)GP * NL;
-	return sizeof(FT) * (5 * STR * M + reduced_scratch_elems<3 + (CL == 2 ? 1 : 0), GP, NL>() + 5 * (STR / 32) * NL + (CL == 2 ? 16 * NL : 0)) + (size_t)NL * GP * 8 +
+	return sizeof(FT) * (5 * STR * M + reduced_scratch_elems<3 + (CL == 2 ? 1 : XS ? 2 : 0), GP, NL>() + 5 * (STR / 32) * NL + (CL == 2 ? 16 * NL : XS ? 32 * NL : 0)) + (size_t)NL * GP * 8 +
 	       7 * sizeof(unsigned long long) + 16;
 }
 
@@ -814,7 +1066,7 @@ bool tma_sweep_supported(const Layout &L, int dir)
 	return encode_fn() != nullptr;
 }
 
-template <typename FT, int DIR, int GP, int NL, int CL>
+template <typename FT, int DIR, int GP, int NL, int CL, int XS = 0>
 static bool launch_tma_one(const SweepArgs<FT> &A, cudaStream_t s)
 {
 	const Layout &L = A.L;
@@ -825,13 +1077,15 @@ static bool launch_tma_one(const SweepArgs<FT> &A, cudaStream_t s)
 		if (!tensor_map_for<FT>(A.cur[q], L, DIR, GP, NL, &TM.cur[q])) return false;
 	}
 	const int ntiles = (DIR == 0 ? L.ny : L.nx) * ((L.nz + NL - 1) / NL);
-	const size_t smem = tma_smem_bytes<FT, GP, NL, CL>();
+	const size_t smem = tma_smem_bytes<FT, GP, NL, CL, XS>() + (XS ? (size_t)(A.xs_P - 1) * 10 * (sizeof(FT) / 4) * NL * sizeof(unsigned) : 0);
 	static int ctas_of[64] = {};
+	static size_t smem_of[64] = {};          // (XS: the shared-memory size grows with the number of slabs)
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (dev < 0 || dev >= 64) return false;
-	auto kern = k_tma_sweep<FT, DIR, GP, NL, CL>;
-	if (!ctas_of[dev]) {
+	auto kern = k_tma_sweep<FT, DIR, GP, NL, CL, XS>;
+	if (!ctas_of[dev] || smem != smem_of[dev]) {
+		smem_of[dev] = smem;
 		if (cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
 		int per_sm = 0, sms = 0;
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -843,7 +1097,9 @@ static bool launch_tma_one(const SweepArgs<FT> &A, cudaStream_t s)
 	// CMC_TMA_HINTS: bit 0 = L2 eviction hints on the bulk copies, bit 1 = streaming result stores (measured: neither helps)
 	static const int hints = getenv("CMC_TMA_HINTS") ? atoi(getenv("CMC_TMA_HINTS")) : 0;
 	if (!A.tile_counter || cudaMemsetAsync(A.tile_counter, 0, sizeof(int), s) != cudaSuccess) return false;
-	const int grid = std::min(ctas_of[dev], ntiles * CL);
+	int grid = std::min(ctas_of[dev], ntiles * CL);
+	// XS: the kernels of all slabs wait for each other; slabs that share a device (a test configuration) must be resident together
+	if (XS && A.xs_share > 1) grid = std::max(1, std::min(grid, ctas_of[dev] / A.xs_share));
 	if (CL == 1) {
 		kern<<<grid, GP * NL, smem, s>>>(A, K, TM, ntiles, hints);
 		return true;
@@ -867,6 +1123,34 @@ static bool launch_tma_dir(const SweepArgs<FT> &A, cudaStream_t s)
 	if (S.nl == 16) return S.cl == 2 ? launch_tma_one<FT, DIR, 32, 16, 2>(A, s) : launch_tma_one<FT, DIR, 32, 16, 1>(A, s);
 	return S.cl == 2 ? launch_tma_one<FT, DIR, 32, 8, 2>(A, s) : launch_tma_one<FT, DIR, 32, 8, 1>(A, s);
 }
+
+// fused slab-coupled x-sweep: chunks per slab line -> lines per tile (the same for all slabs of a grid: tiles index the
+// coefficient tables).  CMC_XS_NL=8|16 overrides (experiments).
+int tma_xs_lines(const Layout &L)
+{
+	const int n = L.nx;
+	if (n % M != 0 || n < 64 || n > 512 || L.total >= (1ll << 31) || (L.nblk > 1 && ((1 << L.jbs) % M != 0)) || !encode_fn()) return 0;
+	if (n / M > 32) return 8;
+	static const int force = getenv("CMC_XS_NL") ? atoi(getenv("CMC_XS_NL")) : 0;
+	if (force == 8 && n / M > 8) return 8;
+	if (force == 16) return 16;
+	return 16;
+}
+template <typename FT>
+bool launch_tma_xs(const SweepArgs<FT> &A, cudaStream_t s, long long *launches)
+{
+	const int nl = tma_xs_lines(A.L), chunks = A.L.nx / M;
+	if (!nl) return false;
+	bool ok;
+	if (chunks > 32) ok = launch_tma_one<FT, 0, 64, 8, 1, 1>(A, s);
+	else if (chunks > 16) ok = nl == 16 ? launch_tma_one<FT, 0, 32, 16, 1, 1>(A, s) : launch_tma_one<FT, 0, 32, 8, 1, 1>(A, s);
+	else if (chunks > 8) ok = nl == 16 ? launch_tma_one<FT, 0, 16, 16, 1, 1>(A, s) : launch_tma_one<FT, 0, 16, 8, 1, 1>(A, s);
+	else ok = launch_tma_one<FT, 0, 8, 16, 1, 1>(A, s);
+	if (ok && launches) (*launches)++;
+	return ok;
+}
+template bool launch_tma_xs<float>(const SweepArgs<float> &, cudaStream_t, long long *);
+template bool launch_tma_xs<double>(const SweepArgs<double> &, cudaStream_t, long long *);
 
 template <typename FT>
 bool launch_tma_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches)

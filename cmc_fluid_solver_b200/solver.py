@@ -283,7 +283,8 @@ class AdiSolver3D:
         _check(load_library().cmc_adi3d_get_option(self._h, f"kernel_{kind[-1]}".encode(), C.byref(v)))
         ft = "double" if self.fp == 8 else "float"
         return {0: f"k_exact_forward/backward<{ft}> + k_merge", 1: f"k_fast_sweep<{ft},{d}>", 2: f"k_ring_sweep<{ft},{d}>",
-                3: f"k_tma_sweep<{ft},{d}>", 4: f"k_fast_sweep<{ft},0,MODE 1> + k_x_interface + k_fast_sweep<{ft},0,MODE 2>"}[v.value]
+                3: f"k_tma_sweep<{ft},{d}>", 4: f"k_fast_sweep<{ft},0,MODE 1> + k_x_interface + k_fast_sweep<{ft},0,MODE 2>",
+                5: f"k_tma_sweep<{ft},0,XS> (one-pass slab-coupled)"}[v.value]
 
     def storage_block_rows(self) -> int:
         v = C.c_int64(0)

@@ -95,3 +95,25 @@ def test_reference_driver_on_two_devices(oracle_mod, tmp_path):
     a, b = outs["cpu"].snapshots[-1], outs["gpu2"].snapshots[-1]
     assert outs["cpu"].shape[0] % 16 == 0, outs["cpu"].shape
     assert_fields_close([a[n] for n in "uvwT"], [b[n] for n in "uvwT"], 8, "reference CPU vs adapter on 2 devices")
+
+
+@pytest.mark.parametrize("fp", ["8", "4"])
+def test_one_pass_coupled_x_sweep_slabs_sharing_one_gpu(fp):
+    """The one-pass slab-coupled x-sweep (kernels_tma.cu XS, option "xs" / CMC_XS=1, off by default): 2, 3, 4 and 8 slabs with
+    their own streams on ONE device (CMC_SHARE_DEVICE=1: the slabs' kernels wait for each other's words, so each gets a share
+    of the SMs) against the oracle.  In its own process: a peer that never arrives ends in a trap, not in a hang."""
+    env = dict(os.environ, CMC_SHARE_DEVICE="1", CMC_XS="1")
+    r = subprocess.run([sys.executable, str(ROOT / "tools" / "xs_check.py"), fp], capture_output=True, text=True, timeout=600, env=env, cwd=str(ROOT))
+    assert r.returncode == 0 and "XS CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_one_pass_coupled_x_sweep_two_ranks():
+    """The same kernel between two real GPUs (one process per GPU, words stored into the peer's table over NVLink)."""
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    env = dict(os.environ, CMC_P2P="1", CMC_XS="1", DIST_CHECK_PLANES="64")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29536", str(ROOT / "tools" / "dist_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=str(ROOT))
+    assert r.returncode == 0 and "DIST CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "kernel_x 5" in r.stdout, r.stdout[-2000:]

@@ -35,13 +35,13 @@ def main():
     ok = True
     for fp, tol in ((8, 1e-10), (4, 1e-5)):
         nid = fresh_id()
-        case = channel_case(16 * world * 2, 40, 48, fp_bytes=fp, depth_var=0.25)
+        case = channel_case(int(os.environ.get("DIST_CHECK_PLANES", "32")) * world, 40, 48, fp_bytes=fp, depth_var=0.25)
         case.outdims = (9, 7, 5)
         one = AdiSolver3D().Init(case, device=lr, mode="fast"); one.CreateSegments()
         many = AdiSolver3D().Init(case, device=lr, mode="fast", rank=rank, nranks=world, nccl_id=nid); many.CreateSegments()
         assert [many.numSegs(d) for d in range(3)] == [one.numSegs(d) for d in range(3)], "segment counts differ"
         if rank == 0:
-            print(f"exchange {many.exchange_kind()}", flush=True)
+            print(f"exchange {many.exchange_kind()} kernel_x {many.get_option('kernel_x')}", flush=True)
         for i in range(4):
             one.UpdateBoundaries(); many.UpdateBoundaries()
             e1 = one.TimeStep(case.dt, 4, 2, True)
