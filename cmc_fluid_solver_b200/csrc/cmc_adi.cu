@@ -101,6 +101,7 @@ struct cmc_adi3d {
 	int profile = 0;
 	struct Span { int kind; cudaEvent_t a, b; };
 	std::vector<Span> spans;
+	std::vector<size_t> open_spans;          // indices of the spans begun and not yet ended (innermost last)
 	double kind_ms[CMC_TIMING_KINDS] = {};
 	long long kind_calls[CMC_TIMING_KINDS] = {};
 	void span_begin(int kind)
@@ -110,21 +111,25 @@ struct cmc_adi3d {
 		cudaSetDevice(device);                  // (a handle with slabs on several devices may have left another one current)
 		cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
 		cudaEventRecord(sp.a, stream);          // (slabs on several devices: the first slab's stream)
+		open_spans.push_back(spans.size());     // (spans nest: the residual span contains a halo exchange on the NCCL transport)
 		spans.push_back(sp);
 	}
 	void span_end()
 	{
-		if (!profile || spans.empty()) return;
+		if (!profile || open_spans.empty()) return;
 		cudaSetDevice(device);
-		cudaEventRecord(spans.back().b, stream);
+		cudaEventRecord(spans[open_spans.back()].b, stream);
+		open_spans.pop_back();
 	}
 	void spans_collect()
 	{
+		open_spans.clear();
 		if (spans.empty()) return;
 		cudaStreamSynchronize(stream);
 		for (auto &sp : spans) {
 			float ms = 0.f;
 			if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { kind_ms[sp.kind] += ms; kind_calls[sp.kind]++; }
+			else cudaGetLastError();            // (a span that an error return left open: not an error of a later call)
 			cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
 		}
 		spans.clear();
