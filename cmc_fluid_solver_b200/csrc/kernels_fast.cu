@@ -480,6 +480,7 @@ static unsigned launch_dir(int GP, const SweepArgs<FT> &A, cudaStream_t s, long 
 	case 8: return launch_one<FT, DIR, 8>(A, s, trace, dry);
 	case 16: return launch_one<FT, DIR, 16>(A, s, trace, dry);
 	case 32: return launch_one<FT, DIR, 32>(A, s, trace, dry);
+	case 128: return launch_one<FT, 2, 128, 0, 2>(A, s, trace, dry);       // (z only: fast_sweep_supported)
 	default: {
 		// z lines of 512 rows: fewer lines per CTA, more independent CTAs per SM (CMC_NLZ = 2, 4 or 8 lines per CTA)
 		static const int nlz = getenv("CMC_NLZ") ? atoi(getenv("CMC_NLZ")) : 2;     // measured, 512^3 fp64: 4.00 / 4.17 / 4.65 ms for 2 / 4 / 8 lines
@@ -496,7 +497,9 @@ bool fast_sweep_supported(const Layout &L, int dir)
 	const int n = dir == 0 ? L.nx : dir == 1 ? L.ny : L.nz;
 	if (n < M) return false;                              // clamped row offsets need at least one full chunk
 	if (L.total >= (1ll << 31)) return false;             // 32-bit element offsets
-	return (n + M - 1) / M <= 64;                         // lines longer than 512 rows: caller falls back
+	// lines of up to 512 rows; along z (contiguous lines, 2 lines x 128 chunks per CTA) up to 1024.  Longer x / y lines: the
+	// CTA-pair form of the TMA kernel (kernels_tma.cu) or the caller's fallback
+	return (n + M - 1) / M <= (dir == 2 ? 128 : 64);
 }
 
 template <typename FT>

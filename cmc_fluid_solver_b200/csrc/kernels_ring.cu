@@ -430,6 +430,8 @@ static bool launch_ring_dir(int GP, const SweepArgs<FT> &A, cudaStream_t s)
 bool ring_sweep_supported(const Layout &L, int dir)
 {
 	if (!fast_sweep_supported(L, dir)) return false;
+	const int n = dir == 0 ? L.nx : dir == 1 ? L.ny : L.nz;
+	if ((n + M - 1) / M > 64) return false;              // (512 rows at most; longer z lines: k_fast_sweep with 128 chunks)
 	return !(L.nblk > 1 && dir != 2);                    // the x / y tiles of this kernel assume the one-block layout
 }
 

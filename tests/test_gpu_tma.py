@@ -116,11 +116,34 @@ def test_lines_up_to_1024_rows_in_fast_mode(oracle_mod, dims, fp):
     ora = O.Oracle3D(case); ora.create_segments()
     s = _tma(case)
     long_dir = 0 if dims[0] > 512 else 1
-    assert s.get_option(("kernel_x", "kernel_y")[long_dir]) == 3
+    # (fp32 keeps the exact kernels above 512 rows: the partition solve's rounding can exceed 1e-5 of the field there)
+    assert s.get_option(("kernel_x", "kernel_y")[long_dir]) == (3 if fp == 8 else 0)
     for i in range(2):
         ora.update_boundaries(); s.UpdateBoundaries()
         e_ref = ora.time_step(case.dt, case.num_global, case.num_local, True)
         e = s.TimeStep(case.dt, case.num_global, case.num_local, True)
         assert abs(e - e_ref) <= (1e-5 if fp == 4 else 1e-9) * abs(e_ref)
         assert_fields_close([ora.field(O.LAYER_CUR, q) for q in range(4)], [s.read_field(LAYER_CUR, q) for q in range(4)], fp, f"{dims} step {i}")
+    s.close()
+
+
+@pytest.mark.parametrize("fp", [8, 4])
+@pytest.mark.parametrize("dims", [(24, 24, 1024), (40, 28, 1000), (1024, 24, 1024)])
+def test_z_lines_up_to_1024_rows_in_fast_mode(oracle_mod, dims, fp):
+    """z lines of 520 .. 1024 rows: the direct-load kernel with 128 chunks per line (one more reduction level); together with the
+    CTA-pair kernel along x / y, fast mode covers 1024^3-shaped grids.  Against the oracle."""
+    O = oracle_mod
+    case = channel_case(*dims, fp_bytes=fp, depth_var=0.25)
+    ora = O.Oracle3D(case); ora.create_segments()
+    s = AdiSolver3D().Init(case, mode="fast"); s.CreateSegments()
+    # (fp32 keeps the exact kernels along z above 512 rows: the partition solve's rounding would exceed 1e-5 there)
+    assert s.get_option("kernel_z") == (1 if fp == 8 else 0)
+    for i in range(2):
+        ora.update_boundaries(); s.UpdateBoundaries()
+        e_ref = ora.time_step(case.dt, case.num_global, case.num_local, True)
+        e = s.TimeStep(case.dt, case.num_global, case.num_local, True)
+        assert_fields_close([ora.field(O.LAYER_CUR, q) for q in range(4)], [s.read_field(LAYER_CUR, q) for q in range(4)], fp, f"{dims} step {i}")
+        # (the residual is a sum of differences of neighbouring values: in fp32, with 1024 cells per line, it carries the fields'
+        # 1e-6 relative rounding amplified by the cancellation)
+        assert abs(e - e_ref) <= (5e-3 if fp == 4 else 1e-9) * abs(e_ref)
     s.close()
