@@ -466,8 +466,12 @@ def main():
         host_in = [torch.empty(local_cells, dtype=ft).pin_memory() for _ in range(4)]
         for q in range(4):
             host_in[q].numpy()[:] = sol.read_field(0, q).ravel()
-        host_vel = [torch.empty(ncells * 3 if rank == 0 else 3, dtype=ft).pin_memory() for _ in range(2)]
-        host_T = [torch.empty(ncells if rank == 0 else 1, dtype=torch.float64).pin_memory() for _ in range(2)]
+        # N > 1: every rank receives the output rows of its own slab (option "local_output": N host links carry the result);
+        # `gathered` below is the same loop with everything collected on rank 0 (one host link)
+        lo_, hi_ = sol.output_rows(0)
+        own = (hi_ - lo_) * DY * DZ
+        host_vel = [torch.empty(max((ncells if rank == 0 else own) * 3, 3), dtype=ft).pin_memory() for _ in range(2)]
+        host_T = [torch.empty(max(ncells if rank == 0 else own, 1), dtype=torch.float64).pin_memory() for _ in range(2)]
         h2d = 4 * ncells * fpb                                   # all ranks together
         d2h = ncells * (3 * fpb + 8) + 16
         ins = [h.numpy() for h in host_in]
@@ -518,15 +522,27 @@ def main():
             sol.write_layer_commit(0)                                # (consume the last upload)
             sol.Sync()
 
+        gathered = None
+        if world > 1:
+            timed(piped_step, 2, piped_start, piped_end)
+            g_ms = timed(piped_step, 3, piped_start, piped_end)
+            gathered = {"value": ncells * 3 / (g_ms * 1e-3) / 1e6, "ms_per_step": g_ms / 3, "steps": 3,
+                        "what": "the same loop with the whole output gathered on rank 0 (one host link carries the 4.29 GB result)"}
+            sol.set_option("local_output", 1)
         timed(piped_step, 2, piped_start, piped_end)                 # warm-up: staging buffers, copy streams
         e2e_ms = timed(piped_step, args.e2e_steps, piped_start, piped_end)
+        if world > 1:
+            sol.set_option("local_output", 0)
         e2e = {"value": ncells * args.e2e_steps / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": e2e_ms / args.e2e_steps, "steps": args.e2e_steps,
                "serial": {"value": ncells * 2 / (serial_ms * 1e-3) / 1e6, "ms_per_step": serial_ms / 2, "steps": 2,
                           "what": "the same step with blocking calls: write_field x4, UpdateBoundaries, TimeStep(computeError), GetLayer"},
                "what": "per step: inputs of the step from pinned host memory (write_layer_async during the previous step, write_layer_commit), "
                        "UpdateBoundaries, TimeStep(computeError) with the residual read back, GetLayer at full resolution into pinned host memory "
-                       "(get_layer_async, landing during the next step; rank 0 receives); host wall clock between barriers, max over ranks"}
+                       "(get_layer_async, landing during the next step; " + ("every rank receives the output rows of its own slab" if world > 1 else "one GPU, one host buffer") +
+                       "); host wall clock between barriers, max over ranks"}
+        if gathered:
+            e2e["gathered"] = gathered
 
     # the reported CPU baseline: rank 0 runs the reference solver on the host cores while the other ranks wait at a barrier
     cpu = None

@@ -12,7 +12,7 @@ SYMBOLS = [
     "cmc_last_error", "cmc_abi_version", "cmc_device_count",
     "cmc_adi3d_create", "cmc_nccl_unique_id", "cmc_adi3d_create_dist", "cmc_adi3d_create_emulated", "cmc_adi3d_create_multi", "cmc_adi3d_create_ex", "cmc_split_planes", "cmc_adi3d_destroy", "cmc_adi3d_slab",
     "cmc_adi3d_set_nodes", "cmc_adi3d_set_nodes_aos", "cmc_adi3d_set_nodes_slab", "cmc_adi3d_update_nodes", "cmc_adi3d_update_nodes_aos", "cmc_adi3d_build_lines", "cmc_adi3d_num_segments",
-    "cmc_adi3d_update_boundaries", "cmc_adi3d_time_step", "cmc_adi3d_get_layer", "cmc_adi3d_get_layer_async", "cmc_adi3d_get_layer_wait",
+    "cmc_adi3d_update_boundaries", "cmc_adi3d_time_step", "cmc_adi3d_get_layer", "cmc_adi3d_get_layer_async", "cmc_adi3d_get_layer_wait", "cmc_adi3d_output_rows",
     "cmc_adi3d_write_layer_async", "cmc_adi3d_write_layer_commit",
     "cmc_adi3d_set_option", "cmc_adi3d_get_option",
     "cmc_adi3d_read_field", "cmc_adi3d_write_field", "cmc_adi3d_step_prologue", "cmc_adi3d_solve_direction",
@@ -94,6 +94,7 @@ def load_library() -> C.CDLL:
         "cmc_adi3d_launch_count": [vp, P(i64), i32],
         "cmc_adi3d_get_timing": [vp, i32, P(dbl), P(i64)],
         "cmc_adi3d_device_bytes": [vp, P(i64)],
+        "cmc_adi3d_output_rows": [vp, i32, P(i32), P(i32)],
         "cmc_solve_tridiagonal_batch": [i32, i32, i32, i32, vp, vp, vp, vp, vp],
         "cmc_adi2d_create": [i32, i32, dbl, dbl, P(FluidParams), dbl, i32, i32, P(vp)],
         "cmc_adi2d_destroy": [vp],

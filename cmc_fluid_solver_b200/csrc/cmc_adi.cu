@@ -82,6 +82,10 @@ struct cmc_adi3d {
 	long long shared_free[3] = {0, 0, 0};   // cells shared by two segments with a BC_FREE row (informational)
 	int mode = CMC_MODE_FAST;
 	int tma_mask = default_tma_mask();
+	// option "local_output": GetLayer of a run with one process per GPU leaves every rank's output rows on that rank (rows
+	// [lo, hi) of the arrays the rank passed, cmc_adi3d_output_rows) instead of gathering everything on rank 0 - N host links
+	// carry the result instead of one
+	int local_output = 0;
 	int tma_shape = 0;               // option "tma_shape": 0 = automatic, else lines per tile + 256 * CTAs per tile (kernels_tma.cu)
 	// option "xs" / CMC_XS=1: one-pass slab-coupled x-sweep (kernels_tma.cu XS).  Off by default: measured on 2 and 4 B200s it
 	// loses to the two-pass form (4.81 against 4.07 ms and 3.28 against 1.92 ms per x-sweep at 512^3, profiles/r02_variants.md)
@@ -1271,7 +1275,8 @@ struct Engine : cmc_adi3d {
 			use(s);
 			cudaStream_t stream = s->stream;
 			launch_clear_out<FT>(s->L, s->role[2], s->layer(CMC_LAYER_NEXT), (FT)CMC_MISSING_VALUE, stream, &launches);
-			const size_t need = (nccl && rank == 0) ? outN : (size_t)std::max(0, hi[s->index] - lo[s->index]) * rowN;
+			const bool gather = nccl && !local_output;
+			const size_t need = (gather && rank == 0) ? outN : (size_t)std::max(0, hi[s->index] - lo[s->index]) * rowN;
 			if (async) { int rc = s->io_setup(); if (rc) return rc; }
 			const int k = async ? (s->out_idx ^= 1) : s->out_idx;
 			if (s->out_pending[k]) {          // this staging set still feeds an earlier asynchronous copy
@@ -1290,12 +1295,12 @@ struct Engine : cmc_adi3d {
 			s->d_outvel = s->d_outvel2[k]; s->d_outT = s->d_outT2[k];
 			// slab-local output buffer starts at output row lo (rank 0 of an NCCL run: at row 0, it also receives)
 			const int oi0 = lo[s->index], oi1 = hi[s->index];
-			const size_t shift = (nccl && rank == 0) ? 0 : (size_t)std::max(oi0, 0) * rowN;
+			const size_t shift = (gather && rank == 0) ? 0 : (size_t)std::max(oi0, 0) * rowN;
 			if (oi1 > oi0)
 				launch_filter<FT>(s->L, s->clayer(CMC_LAYER_NEXT), ox, oy, oz, oi0, oi1, s->d_outvel - 3 * shift, s->d_outT - shift, stream, &launches);
 		}
 		span_end();
-		if (nccl) {
+		if (nccl && !local_output) {
 			Slab<FT> *s = slabs[0];
 			std::vector<P2P> ops;
 			if (rank == 0) {
@@ -1323,7 +1328,8 @@ struct Engine : cmc_adi3d {
 				const int oi0 = lo[s->index], oi1 = hi[s->index];
 				if (oi1 <= oi0) continue;
 				use(s);
-				const size_t o0 = (size_t)oi0 * rowN, cnt = (size_t)(oi1 - oi0) * rowN;
+				// (one process per GPU with local_output: the caller's arrays hold this rank's rows only)
+				const size_t o0 = nccl ? 0 : (size_t)oi0 * rowN, cnt = (size_t)(oi1 - oi0) * rowN;
 				cudaStream_t cs = s->stream;
 				if (async) { CU_TRY(cudaEventRecord(s->ev_filtered, s->stream)); CU_TRY(cudaStreamWaitEvent(s->io_out, s->ev_filtered, 0)); cs = s->io_out; }
 				CU_TRY(cudaMemcpyAsync((FT *)vel + 3 * o0, s->d_outvel, cnt * 3 * sizeof(FT), cudaMemcpyDeviceToHost, cs));
@@ -1618,6 +1624,22 @@ int cmc_adi3d_destroy(cmc_adi3d *h)
 
 #define H_CHECK(h) if (!(h)) return fail(CMC_ERR_INVALID, "null handle")
 
+int cmc_adi3d_output_rows(const cmc_adi3d *h, int outdimx, int *row_lo, int *row_hi)
+{
+	H_CHECK(h);
+	if (outdimx == 0) outdimx = h->G.nx;
+	if (outdimx < 0) return fail(CMC_ERR_INVALID, "output_rows: negative output dimension");
+	int lo = outdimx, hi = 0;
+	for (int i = 0; i < outdimx; i++) {          // source plane of output row i: i * dimx / outdimx (TimeLayer3D.h:842-854)
+		const int x = (int)((long long)i * h->G.nx / outdimx);
+		if (x >= h->L.x0 && x < h->L.x0 + h->L.nx) { if (i < lo) lo = i; if (i + 1 > hi) hi = i + 1; }
+	}
+	if (hi <= lo) lo = hi = 0;
+	if (row_lo) *row_lo = lo;
+	if (row_hi) *row_hi = hi;
+	return CMC_OK;
+}
+
 int cmc_adi3d_slab(const cmc_adi3d *h, int *x0, int *nx)
 {
 	H_CHECK(h);
@@ -1730,6 +1752,7 @@ int cmc_adi3d_set_option(cmc_adi3d *h, const char *key, int64_t value)
 	}
 	if (!strcmp(key, "tma")) { h->tma_mask = (int)value & 3; return CMC_OK; }
 	if (!strcmp(key, "xs")) { h->xs_enabled = value != 0; return CMC_OK; }
+	if (!strcmp(key, "local_output")) { h->local_output = value != 0; return CMC_OK; }
 	if (!strcmp(key, "tma_shape")) {
 		const int nl = (int)value & 255, cl = (int)value >> 8;
 		if (value != 0 && !((nl == 8 || nl == 16) && (cl == 1 || cl == 2))) return fail(CMC_ERR_INVALID, "set_option tma_shape: 0, or lines per tile (8 | 16) + 256 * CTAs per tile (1 | 2)");
@@ -1752,6 +1775,7 @@ int cmc_adi3d_get_option(const cmc_adi3d *h, const char *key, int64_t *value)
 	if (!strcmp(key, "tma")) { *value = h->tma_mask; return CMC_OK; }
 	if (!strcmp(key, "tma_shape")) { *value = h->tma_shape; return CMC_OK; }
 	if (!strcmp(key, "xs")) { *value = h->xs_enabled; return CMC_OK; }
+	if (!strcmp(key, "local_output")) { *value = h->local_output; return CMC_OK; }
 	if (!strncmp(key, "tilectr", 7) && key[7] >= '0' && key[7] <= '9') { return const_cast<cmc_adi3d *>(h)->debug_counter(atoi(key + 7), value); }
 	if (!strcmp(key, "nzp")) { *value = h->L.nzp; return CMC_OK; }
 	if (!strcmp(key, "jb")) { *value = h->L.nblk == 1 ? 0 : (1 << h->L.jbs); return CMC_OK; }   // rows per y-block, 0 = one block

@@ -209,6 +209,13 @@ class AdiSolver3D:
     def GetLayerWait(self):
         _check(load_library().cmc_adi3d_get_layer_wait(self._h))
 
+    def output_rows(self, outdimx=0):
+        """Rows [lo, hi) of the GetLayer output whose source planes this handle holds (option "local_output": what this rank
+        receives)."""
+        lo, hi = C.c_int32(0), C.c_int32(0)
+        _check(load_library().cmc_adi3d_output_rows(self._h, int(outdimx or self.case.dimx), C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def write_layer_async(self, u, v, w, T):
         """Start the upload of a whole layer (dense arrays of this handle's planes) on the copy stream."""
         arrs = [np.ascontiguousarray(a, dtype=self.ft) for a in (u, v, w, T)]

@@ -181,6 +181,11 @@ int cmc_adi3d_get_layer(cmc_adi3d *h, void *vel_xyz, double *T, int outdimx, int
  * cmc_adi3d_write_layer_async uploads a whole layer (u, v, w, T: dense arrays of this handle's planes) on the copy stream
  * into a staging buffer while the solver keeps computing; cmc_adi3d_write_layer_commit(layer) orders the solver's stream
  * behind that upload and scatters the staging buffer into the layer (the asynchronous form of cmc_adi3d_write_field x 4). */
+/* Distributed output (one process per GPU): with option "local_output" = 1 (cmc_adi3d_set_option) GetLayer gathers nothing -
+ * every rank receives the output rows whose source planes it holds, rows [row_lo, row_hi) of the whole output, stored from
+ * the start of the arrays IT passed ((row_hi - row_lo) * outdimy * outdimz entries) - so N host links carry the result instead
+ * of rank 0's alone (parallel output files, like the per-node slices of Grid3D::Init_GPU in the other direction). */
+int cmc_adi3d_output_rows(const cmc_adi3d *h, int outdimx, int *row_lo, int *row_hi);
 int cmc_adi3d_get_layer_async(cmc_adi3d *h, void *vel_xyz, double *T, int outdimx, int outdimy, int outdimz);
 int cmc_adi3d_get_layer_wait(cmc_adi3d *h);
 int cmc_adi3d_write_layer_async(cmc_adi3d *h, const void *u, const void *v, const void *w, const void *T);

@@ -51,6 +51,18 @@ def main():
         v, T = many.GetLayer(*case.outdims)
         if rank == 0:
             assert np.allclose(v, v1, rtol=0, atol=tol * 1e5) and np.allclose(T, T1, rtol=0, atol=tol * 1e5), "GetLayer differs"
+        # distributed output: every rank receives the output rows of its own slab, compactly
+        many.set_option("local_output", 1)
+        lo, hi = many.output_rows(case.outdims[0])
+        rown = case.outdims[1] * case.outdims[2]
+        vl = np.full((max(hi - lo, 1) * rown, 3), -7.0, dtype=v1.dtype); Tl = np.full(max(hi - lo, 1) * rown, -7.0)
+        many.GetLayer(*case.outdims, vel=vl, T=Tl)
+        many.set_option("local_output", 0)
+        if hi > lo:
+            assert np.allclose(vl[: (hi - lo) * rown], v1[lo * rown:hi * rown], rtol=0, atol=tol * 1e5), "local GetLayer (velocity) differs"
+            assert np.allclose(Tl[: (hi - lo) * rown], T1[lo * rown:hi * rown], rtol=0, atol=tol * 1e5), "local GetLayer (T) differs"
+        rows = torch.tensor([hi - lo], device="cuda"); dist.all_reduce(rows)
+        assert int(rows.item()) == case.outdims[0], "the ranks' output rows do not cover the output"
         s1, sN = one.field_sums(0), many.field_sums(0)
         for n in "uvwT":
             assert abs(s1[n][0] - sN[n][0]) <= tol * max(abs(s1[n][1]) ** 0.5, 1.0) * 1e3, ("checksum", n, s1[n], sN[n])
