@@ -900,7 +900,7 @@ struct Engine : cmc_adi3d {
 	}
 	int kernel_kind(int dir) const override
 	{
-		if (multi() && dir == CMC_DIR_X) return fused_x() ? 5 : 4;
+		if (multi() && dir == CMC_DIR_X && mode == CMC_MODE_FAST) return fused_x() ? 5 : 4;
 		if (!fast_ok(dir)) return 0;
 		if (want_tma(dir) && tma_sweep_supported(slabs[0]->L, dir)) return 3;
 		return want_ring(dir) && ring_sweep_supported(slabs[0]->L, dir) ? 2 : 1;
@@ -932,12 +932,13 @@ struct Engine : cmc_adi3d {
 			if (!(push_mode() && halos_ready))
 				if ((rc = halo_exchange(t_is_c ? CMC_LAYER_CUR : CMC_LAYER_TEMP))) return rc;   // x-stencils of the sweep read the neighbours' planes
 			const bool coupled = multi() && dir == CMC_DIR_X;
-			const bool fused = coupled && fused_x();
+			const bool exact_x = coupled && mode != CMC_MODE_FAST;          // bit-exact mode: the Thomas recurrence runs through the slabs as a chain
+			const bool fused = coupled && !exact_x && fused_x();
 			if (fused) xs_epoch++;
 			// the neighbours have finished their previous sweep: their stores into this slab's guard planes are complete,
 			// and they no longer read the guard planes this sweep is about to overwrite on their side
 			await(neighbour_mask());
-			if (coupled && !fused) {
+			if (coupled && !fused && !exact_x) {
 				// partitioned solve along the decomposed axis: spike pass -> coefficients to the line owners -> interface
 				// solve -> neighbour values back -> coupled sweep.  (replaces LaunchSolveSegments_X, AdiSolver3D.cu:524-640)
 				span_begin(CMC_TIMING_X_SPIKE);
@@ -969,7 +970,14 @@ struct Engine : cmc_adi3d {
 			}
 			span_begin(CMC_TIMING_SWEEP_X + dir);
 			std::vector<char> swapped(slabs.size(), 0);
-			for (size_t si = 0; si < slabs.size(); si++) {
+			if (exact_x) {
+				if ((rc = exact_x_chain(dt, cur_layer, next_layer, t_is_c))) return rc;
+				for (auto *s : slabs) {
+					use(s);
+					launch_merge<FT>(s->L, s->role[dir], s->clayer(next_layer), s->layer(CMC_LAYER_TEMP), s->stream, &launches);
+				}
+			}
+			for (size_t si = 0; si < slabs.size() && !exact_x; si++) {
 				Slab<FT> *s = slabs[si];
 				use(s);
 				cudaStream_t stream = s->stream;
@@ -1014,6 +1022,74 @@ struct Engine : cmc_adi3d {
 			span_end();
 			publish();
 		}
+		return CMC_OK;
+	}
+
+	// CMC_MODE_EXACT along the decomposed axis: forward elimination from the first slab to the last, back substitution from the
+	// last to the first; between neighbours one x-plane of (c' of both matrices, d' of u, v, w, T) goes up and one plane of the
+	// carried solution comes down.  The operations are those of the undivided line, in the same order: the result is
+	// bit-identical with the single-slab run (and the reference CPU solver); the slabs work one after the other along x.
+	int exact_x_chain(FT dt, int cur_layer, int next_layer, bool t_is_c)
+	{
+		auto args = [&](Slab<FT> *s) {
+			SweepArgs<FT> A = sweep_args(s, CMC_DIR_X, dt, cur_layer, next_layer);
+			if (t_is_c)
+				for (int q = 0; q < 4; q++) A.temp[q] = s->field[s->slot[CMC_LAYER_CUR]][q];
+			return A;
+		};
+		const int nb = slabs[0]->L.nblk;
+		const size_t pb = sizeof(FT) * (size_t)slabs[0]->L.plane;
+		auto six = [&](Slab<FT> *s, FT *(&f)[6]) { f[0] = s->cv; f[1] = s->cT; for (int q = 0; q < 4; q++) f[2 + q] = s->field[s->slot[next_layer]][q]; };
+		auto piece = [&](Slab<FT> *s, FT *f, int plane, int b) { return f + (long long)b * s->L.bstride + s->L.idx(plane, 0, 0); };
+		if (nccl) {
+			Slab<FT> *s = slabs[0];
+			FT *f[6]; six(s, f);
+			SweepArgs<FT> A = args(s);
+			auto xfer = [&](int first, int plane, int peer, bool send) -> int {
+				std::vector<P2P> ops;
+				for (int k = first; k < 6; k++)
+					for (int b = 0; b < nb; b++)
+						ops.push_back(send ? P2P{piece(s, f[k], plane, b), nullptr, pb, peer} : P2P{nullptr, piece(s, f[k], plane, b), pb, peer});
+				if (nccl_exchange(nccl, ops.data(), (int)ops.size(), stream)) return fail(CMC_ERR_COMM, nccl_error());
+				launches += 1;
+				return CMC_OK;
+			};
+			int rc;
+			if (rank > 0 && (rc = xfer(0, -1, rank - 1, false))) return rc;
+			launch_exact_x_pass<FT>(true, A, stream, &launches);
+			if (rank + 1 < nranks && (rc = xfer(0, s->L.nx - 1, rank + 1, true))) return rc;
+			if (rank + 1 < nranks && (rc = xfer(2, s->L.nx, rank + 1, false))) return rc;
+			launch_exact_x_pass<FT>(false, A, stream, &launches);
+			if (rank > 0 && (rc = xfer(2, -1, rank - 1, true))) return rc;
+			return CMC_OK;
+		}
+		for (size_t si = 0; si < slabs.size(); si++) {
+			Slab<FT> *s = slabs[si];
+			if (si > 0) {
+				Slab<FT> *p = slabs[si - 1];
+				FT *fs[6], *fp[6]; six(s, fs); six(p, fp);
+				join_streams();
+				use(s);
+				for (int k = 0; k < 6; k++)
+					for (int b = 0; b < nb; b++) CU_TRY(cudaMemcpyAsync(piece(s, fs[k], -1, b), piece(p, fp[k], p->L.nx - 1, b), pb, cudaMemcpyDefault, s->stream));
+			}
+			use(s);
+			launch_exact_x_pass<FT>(true, args(s), s->stream, &launches);
+		}
+		for (size_t si = slabs.size(); si-- > 0;) {
+			Slab<FT> *s = slabs[si];
+			if (si + 1 < slabs.size()) {
+				Slab<FT> *u = slabs[si + 1];
+				FT *fs[6], *fu[6]; six(s, fs); six(u, fu);
+				join_streams();
+				use(s);
+				for (int k = 2; k < 6; k++)
+					for (int b = 0; b < nb; b++) CU_TRY(cudaMemcpyAsync(piece(s, fs[k], s->L.nx, b), piece(u, fu[k], -1, b), pb, cudaMemcpyDefault, s->stream));
+			}
+			use(s);
+			launch_exact_x_pass<FT>(false, args(s), s->stream, &launches);
+		}
+		join_streams();
 		return CMC_OK;
 	}
 
@@ -1106,14 +1182,12 @@ struct Engine : cmc_adi3d {
 	{
 		int rc;
 		if (ng < 0 || nl < 0) return fail(CMC_ERR_INVALID, "time_step: negative iteration count");
-		if (multi() && mode != CMC_MODE_FAST)     // before anything is enqueued or any layer is touched
-			return fail(CMC_ERR_UNSUPPORTED, "slab-decomposed runs support CMC_MODE_FAST only");
 		const FT dt = (FT)dt_in;                                   // FluidSolver3D.cpp:242 casts to FTYPE
 		// fast mode folds two full-field passes into the sweeps (identical arithmetic, fewer HBM round trips):
 		//  * temp <- cur (:320): the first Z sweep reads `cur` as its linearisation layer;
 		//  * the post-X MergeLayerTo (:354): the last X sweep of a global iteration relaxes twice.
 		const bool fold_copy = ng > 0 && nl > 0 && fast_ok(CMC_DIR_Z);
-		const bool fold_merge = nl > 0 && (multi() || fast_ok(CMC_DIR_X));
+		const bool fold_merge = nl > 0 && mode == CMC_MODE_FAST && (multi() || fast_ok(CMC_DIR_X));
 		if ((rc = step_prologue_impl(!fold_copy))) return rc;
 		// push mode: every sweep stores its boundary planes into the neighbours' guard planes itself (temp' always,
 		// `next` by the x-sweep, which makes the guard planes of the next step's `cur` valid as well), so one explicit
@@ -1184,7 +1258,6 @@ struct Engine : cmc_adi3d {
 		if (!have_lines) return fail(CMC_ERR_INVALID, "solve_direction: call cmc_adi3d_build_lines first");
 		if (dir < 0 || dir > 2 || cur_layer < 0 || cur_layer > 3 || next_layer < 0 || next_layer > 3 || cur_layer == next_layer)
 			return fail(CMC_ERR_INVALID, "solve_direction: bad direction or layers");
-		if (multi() && mode != CMC_MODE_FAST) return fail(CMC_ERR_UNSUPPORTED, "slab-decomposed runs support CMC_MODE_FAST only");
 		CU_TRY(cudaSetDevice(device));
 		halos_dirty = true;
 		int rc = solve_direction_impl(dir, (FT)dt, nl, cur_layer, next_layer);

@@ -8,6 +8,8 @@ namespace cmc {
 template <typename FT>
 void launch_exact_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
 template <typename FT>
+void launch_exact_x_pass(bool forward, const SweepArgs<FT> &A, cudaStream_t s, long long *launches);
+template <typename FT>
 void launch_thomas_batch(int nsys, int n, FT *a, FT *b, FT *c, FT *d, FT *x, cudaStream_t s);
 
 // ---- kernels_fast.cu -----------------------------------------------------------------------------

@@ -53,6 +53,13 @@ __global__ void __launch_bounds__(128) k_exact_forward(const SweepArgs<FT> A)
 	RowConst<FT> K; K.init(A, DIR);
 	const long long sx = A.L.plane, sz = 1;
 	FT cpv = 0, cpT = 0, dp[4] = {0, 0, 0, 0};
+	if (DIR == 0 && A.xs_me > 0) {
+		// slab of a decomposed grid: the line continues from the lower slab - its last row's c', d' were copied into this slab's
+		// guard plane, so the elimination goes on with exactly the operations of the undivided line
+		const long long im = ln.at<DIR>(A.L, -1);
+		cpv = A.cv[im]; cpT = A.cT[im];
+		dp[0] = A.next[0][im]; dp[1] = A.next[1][im]; dp[2] = A.next[2][im]; dp[3] = A.next[3][im];
+	}
 	for (int p = 0; p < n; p++) {
 		const long long id = ln.at<DIR>(A.L, p);
 		const int jj = DIR == 1 ? p : ln.j;
@@ -97,6 +104,10 @@ __global__ void __launch_bounds__(128) k_exact_backward(const SweepArgs<FT> A)
 	if (!line_of_thread<DIR>(A.L, (long long)blockIdx.x * blockDim.x + threadIdx.x, ln)) return;
 	const int n = ln.n;
 	FT x[4] = {0, 0, 0, 0};
+	if (DIR == 0 && A.xs_me + 1 < A.xs_P) {     // the value the upper slab's back substitution carried across its first row
+		const long long ip = ln.at<DIR>(A.L, n);
+		x[0] = A.next[0][ip]; x[1] = A.next[1][ip]; x[2] = A.next[2][ip]; x[3] = A.next[3][ip];
+	}
 	for (int p = n - 1; p >= 0; p--) {
 		const long long id = ln.at<DIR>(A.L, p);
 		const unsigned r = A.role[id];
@@ -126,6 +137,10 @@ __global__ void __launch_bounds__(128) k_exact_backward(const SweepArgs<FT> A)
 			x[3] = (d[3] - A.next[3][im] * a_T) / den_T;
 		}
 	}
+	if (DIR == 0 && A.xs_me > 0) {              // (the guard plane's copy of the lower slab's d' has served its purpose above)
+		const long long im = ln.at<DIR>(A.L, -1);
+		A.next[0][im] = x[0]; A.next[1][im] = x[1]; A.next[2][im] = x[2]; A.next[3][im] = x[3];
+	}
 }
 
 template <typename FT>
@@ -142,6 +157,22 @@ void launch_exact_sweep(int dir, const SweepArgs<FT> &A, cudaStream_t s, long lo
 	}
 	if (launches) *launches += 2;
 }
+
+// the two passes on their own: slabs of a decomposed grid run them as a chain along x (forward from the first slab to the last,
+// back substitution from the last to the first, cmc_adi.cu)
+template <typename FT>
+void launch_exact_x_pass(bool forward, const SweepArgs<FT> &A, cudaStream_t s, long long *launches)
+{
+	const Layout &L = A.L;
+	const long long lines = (long long)L.ny * L.nz;
+	const int bs = 128;
+	const unsigned grid = (unsigned)((lines + bs - 1) / bs);
+	if (forward) k_exact_forward<FT, 0><<<grid, bs, 0, s>>>(A);
+	else k_exact_backward<FT, 0><<<grid, bs, 0, s>>>(A);
+	if (launches) *launches += 1;
+}
+template void launch_exact_x_pass<float>(bool, const SweepArgs<float> &, cudaStream_t, long long *);
+template void launch_exact_x_pass<double>(bool, const SweepArgs<double> &, cudaStream_t, long long *);
 
 template void launch_exact_sweep<float>(int, const SweepArgs<float> &, cudaStream_t, long long *);
 template void launch_exact_sweep<double>(int, const SweepArgs<double> &, cudaStream_t, long long *);
