@@ -106,6 +106,14 @@ struct cmc_adi3d {
 	struct Span { int kind; cudaEvent_t a, b; };
 	std::vector<Span> spans;
 	std::vector<size_t> open_spans;          // indices of the spans begun and not yet ended (innermost last)
+	std::vector<cudaEvent_t> span_events;    // events of collected spans, reused: nothing is created inside a timed loop after warm-up
+	cudaEvent_t span_event()
+	{
+		cudaEvent_t e = nullptr;
+		if (!span_events.empty()) { e = span_events.back(); span_events.pop_back(); }
+		else cudaEventCreate(&e);
+		return e;
+	}
 	double kind_ms[CMC_TIMING_KINDS] = {};
 	long long kind_calls[CMC_TIMING_KINDS] = {};
 	void span_begin(int kind)
@@ -113,7 +121,7 @@ struct cmc_adi3d {
 		if (!profile) return;
 		Span sp; sp.kind = kind;
 		cudaSetDevice(device);                  // (a handle with slabs on several devices may have left another one current)
-		cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
+		sp.a = span_event(); sp.b = span_event();
 		cudaEventRecord(sp.a, stream);          // (slabs on several devices: the first slab's stream)
 		open_spans.push_back(spans.size());     // (spans nest: the residual span contains a halo exchange on the NCCL transport)
 		spans.push_back(sp);
@@ -134,7 +142,7 @@ struct cmc_adi3d {
 			float ms = 0.f;
 			if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { kind_ms[sp.kind] += ms; kind_calls[sp.kind]++; }
 			else cudaGetLastError();            // (a span that an error return left open: not an error of a later call)
-			cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+			span_events.push_back(sp.a); span_events.push_back(sp.b);
 		}
 		spans.clear();
 	}
@@ -428,6 +436,8 @@ struct Engine : cmc_adi3d {
 		}
 		if (stream) cudaStreamSynchronize(stream);
 		spans_collect();
+		for (cudaEvent_t e : span_events) cudaEventDestroy(e);
+		span_events.clear();
 		if (p2p) peer_unmap(&pm);
 		if (d_timeout) cudaFree(d_timeout);
 		for (auto *s : slabs) delete s;
