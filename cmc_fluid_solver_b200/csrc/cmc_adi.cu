@@ -260,7 +260,7 @@ struct Slab {
 		return CMC_OK;
 	}
 
-	int init(const Layout &g, int x0, int nx, int alloc_nx, int dev, cudaStream_t s, int idx, int nslabs)
+	int init(const Layout &g, int x0, int nx, int alloc_nx, int dev, cudaStream_t s, int idx, int nslabs, bool with_xs = false)
 	{
 		device = dev; stream = s; G = g; index = idx;
 		L = G; L.x0 = x0; L.shape(nx, G.ny, G.nz, G.nzp, G.jbs, alloc_nx);
@@ -271,7 +271,8 @@ struct Slab {
 			const size_t cb = nslabs > 1 ? up(sizeof(FT) * lpo * 16 * nslabs) : 0, bb = nslabs > 1 ? up(sizeof(FT) * lpo * 8 * nslabs) : 0;
 			// (lines padded to whole 16-line tiles)
 			const size_t xlines = (size_t)G.ny * (size_t)((G.nz + 15) / 16 * 16);
-			const size_t xtb = nslabs > 1 ? up(sizeof(unsigned long long) * xlines * 16 * (sizeof(FT) / 4) * nslabs) : 0;
+			// (only when the one-pass slab-coupled x-sweep is switched on at creation: 0.5 GB per slab at 512^2 lines and 8 slabs)
+			const size_t xtb = (nslabs > 1 && with_xs) ? up(sizeof(unsigned long long) * xlines * 16 * (sizeof(FT) / 4) * nslabs) : 0;
 			flag_off = 20 * fb + cb + bb + xtb;
 			arena_bytes = flag_off + 256;
 			CU_TRY(cudaMalloc((void **)&arena, arena_bytes));
@@ -282,7 +283,7 @@ struct Slab {
 			if (nslabs > 1) {
 				xcoef_recv = reinterpret_cast<FT *>(arena + 20 * fb);
 				xbnd_recv = reinterpret_cast<FT *>(arena + 20 * fb + cb);
-				xs_tab = reinterpret_cast<unsigned long long *>(arena + 20 * fb + cb + bb);
+				if (xtb) xs_tab = reinterpret_cast<unsigned long long *>(arena + 20 * fb + cb + bb);
 			}
 		}
 		for (int q = 0; q < 4; q++) if ((rc = dalloc(nodev[q], (size_t)L.total))) return rc;
@@ -463,11 +464,12 @@ struct Engine : cmc_adi3d {
 	// slabs' kernels to run at the same time (one process per GPU with mapped peer memory, or one process driving several
 	// devices - not the emulation of several slabs on one stream), whole 8-row chunks in every slab and the same tile
 	// shape for all slabs.  Every rank evaluates this from the same global split, so all take the same path.
-	// Option "xs" / CMC_XS=1 switches it on (see xs_enabled).
+	// CMC_XS=1 at creation switches it on (see xs_enabled; option "xs" can switch it off and on again afterwards).
 	int xs_epoch = 0;
 	bool fused_x() const
 	{
 		if (!multi() || !xs_enabled || mode != CMC_MODE_FAST || !want_tma(CMC_DIR_X)) return false;
+		if (!slabs[0]->xs_tab) return false;                 // (the tables exist only when the option was on at creation: CMC_XS=1)
 		if (!((nccl && p2p) || multi_device)) return false;
 		int nl = -1;
 		for (int r = 0; r < nslabs_total; r++) {
@@ -556,7 +558,7 @@ struct Engine : cmc_adi3d {
 				{ const int device = sdev; CU_TRY(cudaSetDevice(sdev)); CU_TRY(cudaStreamCreateWithFlags(&sstream, cudaStreamNonBlocking)); }
 				s->owns_stream = true;
 			}
-			int rc = s->init(G, x0, nx, ntotal > 1 ? nx_max : nx, sdev, sstream, first_slab + i, ntotal);
+			int rc = s->init(G, x0, nx, ntotal > 1 ? nx_max : nx, sdev, sstream, first_slab + i, ntotal, xs_enabled != 0);
 			if (rc) return rc;
 			if (multi_device) { const int device = sdev; CU_TRY(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming)); }
 			dev_bytes += s->bytes;

@@ -482,8 +482,8 @@ static unsigned launch_dir(int GP, const SweepArgs<FT> &A, cudaStream_t s, long 
 	case 32: return launch_one<FT, DIR, 32>(A, s, trace, dry);
 	case 128: return launch_one<FT, 2, 128, 0, 2>(A, s, trace, dry);       // (z only: fast_sweep_supported)
 	default: {
-		// z lines of 512 rows: fewer lines per CTA, more independent CTAs per SM (CMC_NLZ = 2, 4 or 8 lines per CTA)
-		static const int nlz = getenv("CMC_NLZ") ? atoi(getenv("CMC_NLZ")) : 2;     // measured, 512^3 fp64: 4.00 / 4.17 / 4.65 ms for 2 / 4 / 8 lines
+		// z lines of 512 rows: fewer lines per CTA, more independent CTAs per SM (CMC_NLZ = 1, 2, 4 or 8 lines per CTA)
+		static const int nlz = getenv("CMC_NLZ") ? atoi(getenv("CMC_NLZ")) : 1;     // measured, 512^3 fp64: 3.85 / 3.92 / 4.17 / 4.65 ms for 1 / 2 / 4 / 8 lines
 		if (DIR == 2 && nlz == 4) return launch_one<FT, DIR, 64, 0, 4>(A, s, trace, dry);
 		if (DIR == 2 && nlz == 2) return launch_one<FT, DIR, 64, 0, 2>(A, s, trace, dry);
 		if (DIR == 2 && nlz == 1) return launch_one<FT, DIR, 64, 0, 1>(A, s, trace, dry);

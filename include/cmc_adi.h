@@ -193,8 +193,11 @@ int cmc_adi3d_write_layer_commit(cmc_adi3d *h, int layer);
 
 /* ---- options ----  "mode": CMC_MODE_FAST | CMC_MODE_EXACT;  "tma": bit 0 / bit 1 = run the x / y sweeps as TMA-staged
  * persistent tiles where the grid allows (kernels_tma.cu; default from the environment variable CMC_TMA);  "profile": 0|1|2 (see cmc_adi3d_get_timing);
+ * "tma_shape": 0 = measured default, else lines per tile (8 | 16) + 256 * CTAs per tile (1 | 2) of the TMA kernel;  "local_output": 0|1 (see
+ * cmc_adi3d_output_rows);  "xs": 0|1 = one-pass slab-coupled x-sweep (off by default - it measured slower than the two-pass form;
+ * its tables exist only when the environment variable CMC_XS=1 was set at creation);
  * read-only: "kernel_x" / "kernel_y" / "kernel_z" (which kernel a sweep along that axis runs: 0 exact Thomas kernels,
- * 1 direct-load partition kernel, 2 cp.async ring kernel, 3 TMA-staged tile kernel, 4 slab-coupled x-sweep),
+ * 1 direct-load partition kernel, 2 cp.async ring kernel, 3 TMA-staged tile kernel, 4 slab-coupled x-sweep in two passes, 5 in one pass),
  * "nzp" (padded z-line length), "jb" (rows per y-block of the field storage, 0 = one block), "exchange" (how slabs exchange planes and interface systems: 0 single slab,
  * 1 NCCL send/recv groups, 2 stores fused into the sweep kernels (slabs on one device), 3 the same into peer memory
  * over NVLink - every rank maps the other ranks' exchange arena with CUDA IPC, 4 the same between the devices of one
