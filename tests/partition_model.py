@@ -100,3 +100,52 @@ def slab_coupled_solve(a, b, c, d, x_left, x_right):
     a0 = a.copy(); a0[:, 0] = 0
     c0 = c.copy(); c0[:, -1] = 0
     return thomas(a0, b, c0, d)
+
+
+def slab_open_solve(a, b, c, d):
+    """One-pass form (kernel k_tma_sweep XS / CTA pair): the slab's rows solved ONCE with two extra right-hand sides, so that
+    every row is known up to the two neighbour values:   x = y - p * x_left - q * x_right   (shapes (lines, nx)).
+    Row 0 / row nx-1 of (y, p, q) are the coefficients (f, pf, qf) / (l, pl, ql) that go to the other slabs."""
+    a0 = a.copy(); a0[:, 0] = 0
+    c0 = c.copy(); c0[:, -1] = 0
+    e_first = np.zeros_like(d); e_first[:, 0] = a[:, 0]
+    e_last = np.zeros_like(d); e_last[:, -1] = c[:, -1]
+    return thomas(a0, b, c0, d), thomas(a0, b, c0, e_first), thomas(a0, b, c0, e_last)
+
+
+def pair_interface(l0, ql0, f1, pf1):
+    """Two parts of a line (the CTA pair of k_tma_sweep, or two slabs): L_0 + ql_0 F_1 = l_0 , F_1 + pf_1 L_0 = f_1 in closed
+    form.  Returns (x_last of the lower part, x_first of the upper part)."""
+    L0 = (l0 - ql0 * f1) / (1.0 - ql0 * pf1)
+    return L0, f1 - pf1 * L0
+
+
+def thomas_chain(a, b, c, d, slabs):
+    """CMC_MODE_EXACT on a decomposed grid (exact_x_chain, kernels_exact.cu): the same recurrence, slab by slab - the forward
+    elimination hands (c', d') of a slab's last row to the next slab, the back substitution hands the first row's solution back.
+    Same operations in the same order as thomas(): the result is bit-identical."""
+    a, b, c, d = (np.array(v, dtype=np.float64) for v in (a, b, c, d))
+    c[..., -1] = 0
+    cp, dp = np.empty_like(c), np.empty_like(d)
+    carry = None
+    for x0, nx in slabs:                                   # forward, first slab -> last
+        for i in range(x0, x0 + nx):
+            if i == 0:
+                cp[..., 0] = c[..., 0] / b[..., 0]; dp[..., 0] = d[..., 0] / b[..., 0]
+            else:
+                pc, pd = (cp[..., i - 1], dp[..., i - 1]) if i > x0 else carry
+                den = b[..., i] - a[..., i] * pc
+                cp[..., i] = c[..., i] / den
+                dp[..., i] = (d[..., i] - pd * a[..., i]) / den
+        carry = (cp[..., x0 + nx - 1].copy(), dp[..., x0 + nx - 1].copy())       # the plane that goes to the next slab
+    x = np.empty_like(d)
+    up = None
+    for x0, nx in reversed(slabs):                         # back substitution, last slab -> first
+        for i in range(x0 + nx - 1, x0 - 1, -1):
+            if i == d.shape[-1] - 1:
+                x[..., i] = dp[..., i]
+            else:
+                nxt = x[..., i + 1] if i + 1 < x0 + nx else up
+                x[..., i] = dp[..., i] - cp[..., i] * nxt
+        up = x[..., x0].copy()                             # the plane that goes back to the previous slab
+    return x

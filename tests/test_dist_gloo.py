@@ -94,3 +94,62 @@ def test_partitioned_solve_over_gloo(world):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert ret["err"] < 1e-12 and ret["mean_ok"]
+
+
+def test_one_pass_completion_single_process():
+    """The algebra of the one-pass slab-coupled sweep and of the CTA-pair tiles: every slab solves its rows once with two
+    spike columns, all slabs see all first / last row coefficients, each solves the interface for itself and completes
+    x = y - p x_left - q x_right - equal to the undivided Thomas solve; two parts: the closed-form 2x2 interface."""
+    a, b, c, d = _system(29, 128, 3)
+    ref = P.thomas(a, b, c, d)
+    for nsl in (2, 3, 8):
+        slabs = P.split_even(128, nsl)
+        parts = [P.slab_open_solve(a[:, x0:x0 + nx], b[:, x0:x0 + nx], c[:, x0:x0 + nx], d[:, x0:x0 + nx]) for x0, nx in slabs]
+        f, pf, qf = (np.stack([pt[i][:, 0] for pt in parts]) for i in range(3))
+        l, pl, ql = (np.stack([pt[i][:, -1] for pt in parts]) for i in range(3))
+        xl, xr = P.interface_solve(f, pf, qf, l, pl, ql)
+        for r, (x0, nx) in enumerate(slabs):
+            y, p, q = parts[r]
+            x = y - p * xl[r][:, None] - q * xr[r][:, None]
+            assert np.abs(x - ref[:, x0:x0 + nx]).max() < 1e-12
+        if nsl == 2:
+            L0, F1 = P.pair_interface(l[0], ql[0], f[1], pf[1])
+            assert np.abs(L0 - xl[1]).max() < 1e-13 and np.abs(F1 - xr[0]).max() < 1e-13
+
+
+def _worker_one_pass(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lines, n = 33, 48 * world
+        a, b, c, d = _system(lines, n, 11)
+        x0, nx = P.split_even(n, world)[rank]
+        sl = slice(x0, x0 + nx)
+        y, p, q = P.slab_open_solve(a[:, sl], b[:, sl], c[:, sl], d[:, sl])
+        mine = torch.from_numpy(np.stack([y[:, 0], p[:, 0], q[:, 0], y[:, -1], p[:, -1], q[:, -1]]).copy())       # (6, lines)
+        everyone = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(everyone, mine)                         # every slab's coefficients go to every slab (the kernel: peer stores)
+        coef = np.stack([t.numpy() for t in everyone])          # (P, 6, lines)
+        xl, xr = P.interface_solve(*(coef[:, i, :] for i in range(6)))
+        x = y - p * xl[rank][:, None] - q * xr[rank][:, None]   # finished from what the slab already holds: nothing is read twice
+        err = torch.tensor([float(np.abs(x - P.thomas(a, b, c, d)[:, sl]).max())], dtype=torch.float64)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            ret["err"] = float(err.item())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_one_pass_completion_over_gloo(world):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_one_pass, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret["err"] < 1e-12
+
+
+def test_exact_chain_is_bit_identical_with_the_undivided_recurrence():
+    a, b, c, d = _system(23, 90, 5)
+    ref = P.thomas(a, b, c, d)
+    for slabs in (P.split_even(90, 2), P.split_even(90, 4), [(0, 8), (8, 50), (58, 32)]):
+        assert np.array_equal(P.thomas_chain(a, b, c, d, slabs), ref)
