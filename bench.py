@@ -172,7 +172,7 @@ def reference_arm(args):
         "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": bench_config(args, world=args.gpus),
-        "sample": sample, "sample_grid": list(r["dims"]), "steps_timed": r["steps"],
+        "sample": sample, "sample_grid": list(r["dims"]), "steps_timed": r["steps"], "warmup_run": 1,
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
