@@ -6,18 +6,18 @@
 // direct-load kernel is latency bound (ncu, profiles/r01_ncu_sweeps_final.md): one 512-thread CTA per SM owns the
 // register file, ~150 LDG and ~64 STG per thread per tile go through the LSU (lg_throttle 2.0-2.3 stall cycles per
 // issue), its load phases are separated by barriers and HBM idles while the SM solves (DRAM 42 % busy).  Here
-//   * one persistent CTA per SM walks over its tiles (tile = 8 neighbouring lines x all rows of the line);
+//   * persistent CTAs walk over their tiles (tile = 8 or 16 neighbouring lines x all rows of the line; one 512-thread CTA per
+//     SM at 512 rows; tile shapes, the CTA-pair form and the one-pass slab coupling: see the kernel's own comment);
 //   * every input field of a tile arrives by ONE bulk-tensor copy per field (a 5-D box that gathers the 64-byte row
 //     segments of the tile - rows 256 KB (x) / 4 KB (y) apart - straight into a shared-memory slot laid out
 //     [row-in-chunk][chunk][line], which the compute threads read without bank conflicts); thread 0 issues them, an
 //     mbarrier per slot counts the bytes in;
-//   * six slots (6 x 32 KB in fp64), eleven copies per tile, each issued one solve phase (or more) before its use:
+//   * five slots (5 x 32 KB in fp64), eleven copies per tile, each issued one solve phase (or more) before its use:
 //         slot 0: temp[DIR]            (resident from the u,v,w phase to the dissipation function)
 //         slot 1: temp.T   -> the first other temp component
 //         slot 2: cur.u    -> the second other temp component
-//         slot 3: cur.v    -> temp[DIR] of the cross-line neighbour below (j-1 for x lines, i-1 for y lines)
-//         slot 4: cur.w    -> temp[DIR] of the cross-line neighbour above
-//         slot 5: cur.T    -> temp.T (for the relaxation of T at the end)
+//         slot 3: cur.v    -> temp[DIR] of the cross-line neighbour below (j-1 for x lines, i-1 for y lines) -> cur.T
+//         slot 4: cur.w    -> temp[DIR] of the cross-line neighbour above -> temp.T (for the relaxation of T at the end)
 //     so HBM streams while the SM eliminates / solves the reduced systems, and the LSU only sees shared-memory loads and
 //     the result stores;
 //   * no global load in the common path except the k +- 1 neighbours of the two edge lines of a tile.
